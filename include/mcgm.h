@@ -1,0 +1,181 @@
+/*
+ * mcgm.h — C ABI of libmcgm.so, the B200 (sm_100a) implementation of the
+ * MultimodalController-gated conv block hot path.
+ *
+ * The reference (diaoenmao/Multimodal-Controller-for-Generative-Models) has no
+ * FFI of its own: its boundary is the Python nn.Module API
+ * (src/modules/modules.py:49-85, src/models/mcgan.py:193-203).  Every entry
+ * point below replaces the PyTorch library calls that one reference line (or a
+ * run of lines) dispatches to; the citation sits on each declaration.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host.
+ *   - activations are NHWC ("channels last"): x[((n*H + h)*W + w)*C + c].
+ *   - conv weights are KRSC: w[((k*R + r)*S + s)*C + c]  (k = out channel).
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = ok, negative = error (see MCGM_E_*); the message is
+ *     available from mcgm_last_error() (thread-local, valid until next call).
+ *   - nothing here allocates device memory; callers pass workspaces whose size
+ *     comes from the *_workspace_bytes() helpers.
+ *   - dtype codes: MCGM_F32 = 0, MCGM_BF16 = 1.
+ */
+#ifndef MCGM_H_
+#define MCGM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCGM_F32 0
+#define MCGM_BF16 1
+
+#define MCGM_E_ARG (-1)      /* bad argument / unsupported shape */
+#define MCGM_E_CUDA (-2)     /* CUDA runtime / driver error */
+#define MCGM_E_UNSUPPORTED (-3)
+
+/* gate flags */
+#define MCGM_GATE_BN 1        /* y = a*x+b with a = gamma*rstd, b = beta - mean*a */
+#define MCGM_GATE_RELU 2      /* ReLU before the mask */
+#define MCGM_GATE_UP2 4       /* nearest 2x upsample on write (fwd) / 2x2 sum on read (bwd) */
+#define MCGM_GATE_MASK 8      /* multiply by codebook[label[n], c] */
+
+/* conv epilogue flags */
+#define MCGM_EPI_BIAS 1
+#define MCGM_EPI_RES 2        /* out += res[n,h,w,:]           (same resolution)   */
+#define MCGM_EPI_RES_UP2 4    /* out += res[n,h/2,w/2,:]       (nearest-upsampled) */
+#define MCGM_EPI_RELU 8
+#define MCGM_EPI_MASK 16      /* out *= codebook[label[n], c]  */
+#define MCGM_EPI_TANH 32
+#define MCGM_EPI_POSMASK 64   /* out *= (aux[n,h,w,c] > 0)  — ReLU backward fused in dgrad */
+
+const char* mcgm_last_error(void);
+int mcgm_version(void);
+/* number of SMs of the current device (grid sizing), or negative error */
+int mcgm_sm_count(void);
+
+/* ---- codebook ------------------------------------------------------------
+ * Replaces `indicator.matmul(self.codebook)` (src/modules/modules.py:73): the
+ * {0,1} fp32 codebook [M,C] is bit-packed once to [M, ceil(C/32)] uint32 words
+ * (bit c%32 of word c/32); the mask of sample n is row label[n]. */
+int mcgm_pack_codebook(const float* codebook, int M, int C, uint32_t* bits, void* stream);
+
+/* ---- MultimodalController.forward (src/modules/modules.py:71-76) ----------
+ * y[n,p,c] = x[n,p,c] * code(n,c), P = positions per sample (H*W, or 1 for 2-D x).
+ * nchw = 1: x is NCHW-contiguous (the reference's layout), i.e. y[n,c,p] = x[n,c,p]*code(n,c).
+ * code comes from (labels,bits) when labels != NULL, else from dense fp32 code[N,C]
+ * (the general `indicator @ codebook` case).  Backward is the same call on dy. */
+int mcgm_mc_forward(const void* x, void* y, int dtype, int nchw, int N, int P, int C,
+                    const int32_t* labels, const uint32_t* bits, int M,
+                    const float* code, void* stream);
+
+/* ---- BatchNorm2d statistics (train mode; src/models/mcgan.py:15,20,56 →
+ * torch native_batch_norm).  x is [P_total, C].  Writes mean[C], rstd[C]
+ * (biased variance, eps inside the sqrt) and, when running_mean != NULL, the
+ * momentum update with the UNBIASED variance.  workspace: see below. */
+size_t mcgm_bn_stats_workspace_bytes(int C);
+int mcgm_bn_stats(const void* x, int dtype, long P_total, int C,
+                  float* mean, float* rstd,
+                  float* running_mean, float* running_var, float momentum, float eps,
+                  void* workspace, void* stream);
+
+/* ---- fused gate forward: BN-apply → ReLU → (2x nearest upsample) → MC mask
+ * (src/models/mcgan.py:15-18, 20-22, 56-58; D's ReLU→MC :104-105 with flags
+ * without MCGM_GATE_BN).  x [N,H,W,C]; y [N,H',W',C] (H'=2H with UP2);
+ * y_raw (optional, may be NULL) receives mask*x at the INPUT resolution — the
+ * shortcut branch `mc_1(up(x))` of GenResBlock (mcgan.py:26-30) commuted with
+ * the upsample, or DisResBlock's raw-gated shortcut (mcgan.py:111-115). */
+int mcgm_gate_fwd(const void* x, void* y, void* y_raw, int dtype,
+                  int N, int H, int W, int C,
+                  const int32_t* labels, const uint32_t* bits, int M,
+                  const float* mean, const float* rstd,
+                  const float* gamma, const float* beta,
+                  int flags, void* stream);
+
+/* ---- fused gate backward.  dy [N,H',W',C]; d_raw (optional) is the gradient
+ * that arrived at y_raw.  With MCGM_GATE_BN it runs the two-pass BN backward
+ * (reduce: dgamma,dbeta; apply: dx) — both passes are launched by this call.
+ * workspace: mcgm_gate_bwd_workspace_bytes(C). */
+size_t mcgm_gate_bwd_workspace_bytes(int C);
+int mcgm_gate_bwd(const void* dy, const void* d_raw, const void* x, void* dx, int dtype,
+                  int N, int H, int W, int C,
+                  const int32_t* labels, const uint32_t* bits, int M,
+                  const float* mean, const float* rstd,
+                  const float* gamma, const float* beta,
+                  float* dgamma, float* dbeta,
+                  int flags, void* workspace, void* stream);
+
+/* ---- weight packing: fp32 OIHW master [K,C,R,S] (state_dict layout) →
+ * bf16 KRSC for the forward conv and bf16 CRSK with flipped taps for dgrad
+ * (either output may be NULL).  `inv_sigma` (device scalar, may be NULL)
+ * multiplies the weight: the W/sigma of spectral norm (src/models/utils.py:17-21
+ * → torch.nn.utils.spectral_norm compute_weight). */
+int mcgm_pack_weight(const float* w_oihw, int K, int C, int R, int S,
+                     const float* inv_sigma, void* w_krsc_bf16, void* w_crsk_flip_bf16,
+                     void* stream);
+/* fp32 KRSC gradient → fp32 OIHW (+= if accumulate) */
+int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int S,
+                      float* dw_oihw, int accumulate, void* stream);
+
+/* ---- implicit-GEMM convolution, tcgen05 + TMA (replaces cudnn_convolution at
+ * src/models/mcgan.py:19,23,29,59,77-85,103-128).  stride 1, pad (R-1)/2,
+ * R=S in {1,3}; x bf16 NHWC [N,H,W,Cin] with Cin % 64 == 0; w bf16 KRSC
+ * [Cout,R,S,Cin]; out NHWC [N,H,W,Cout], out_dtype bf16 or f32.
+ * dgrad is the same call with the flipped CRSK weight from mcgm_pack_weight.
+ * Epilogue (flags MCGM_EPI_*): +bias[Cout] (fp32), +res (bf16 NHWC, same-res
+ * or half-res), ReLU, MC mask by (labels,bits), tanh, (aux>0) masking. */
+int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype,
+                  int N, int H, int W, int Cin, int Cout, int R, int S,
+                  const float* bias, const void* res, const void* aux,
+                  const int32_t* labels, const uint32_t* bits, int M,
+                  int flags, void* stream);
+
+/* ---- weight gradient, tcgen05 + TMA with MN-major operands straight from the
+ * NHWC tensors: dw[k,r,s,c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-pad,w+s-pad,c].
+ * x [N,H,W,Cin] bf16, dy [N,H,W,Cout] bf16 (Cin,Cout % 64 == 0), dw fp32 KRSC.
+ * Deterministic split-K: partials in workspace, fixed-order reduction.
+ * dbias (optional) = sum over pixels of dy. */
+size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S);
+int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias,
+                    int N, int H, int W, int Cin, int Cout, int R, int S,
+                    void* workspace, void* stream);
+
+/* ---- thin convolutions: one side has <= 4 channels (RGB image side of
+ * Conv2d(3,128,...) mcgan.py:77,87 and Conv2d(256,3,3,1,1) mcgan.py:59).
+ * HBM-bound CUDA-core kernels.  `thin` is fp32 NHWC [N,H,W,Ct] (Ct <= 4),
+ * `wide` is bf16 NHWC [N,H,W,Cw] (Cw % 8 == 0), kern is fp32 [R*S][Ct][Cw].
+ *   wide_from_thin : wide[p,c]  = sum_{t,j} thin[p+off(t), j] * kern[t][j][c]  (+bias, ReLU, mask)
+ *   thin_from_wide : thin[p,j]  = sum_{t,c} wide[p+off(t), c] * kern[t][j][c]  (+bias, tanh)
+ *   kern_grad      : dkern[t][j][c] = sum_p thin[p+off(t), j] * wide[p, c]
+ * off(t) = (r - pad, s - pad), t = r*S + s. */
+int mcgm_thin_wide_from_thin(const float* thin, const float* kern, void* wide,
+                             int N, int H, int W, int Ct, int Cw, int R, int S,
+                             const float* bias, const int32_t* labels, const uint32_t* bits, int M,
+                             const void* aux, int flags, void* stream);
+int mcgm_thin_thin_from_wide(const void* wide, const float* kern, float* thin,
+                             int N, int H, int W, int Ct, int Cw, int R, int S,
+                             const float* bias, int flags, void* stream);
+size_t mcgm_thin_kern_grad_workspace_bytes(int Ct, int Cw, int R, int S);
+int mcgm_thin_kern_grad(const float* thin, const void* wide, float* dkern,
+                        int N, int H, int W, int Ct, int Cw, int R, int S,
+                        void* workspace, void* stream);
+
+/* ---- pooling / resampling helpers on bf16 NHWC (AvgPool2d(2) mcgan.py:81,88;
+ * Upsample backward = 2x2 sum).  avgpool2: y[n,h,w,c] = scale * sum_{2x2} x;
+ * upsample2_add: y[n,h,w,c] = a[n,h,w,c] + b[n,h/2,w/2,c] (b may be NULL → copy-upsample of a at half res is not needed). */
+int mcgm_pool2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream);
+int mcgm_unpool2(const void* dy, void* dx, int dtype, int N, int H, int W, int C, float scale, void* stream);
+
+/* ---- debug / bring-up: override shared-memory-descriptor fields of the tcgen05
+ * kernels (key 0/1: K-major LBO/SBO bytes, 2/3: MN-major LBO/SBO bytes, 4: version,
+ * 5: layout code).  Lets one GPU session try several encodings.  Not used by the
+ * product path. */
+int mcgm_debug_set(int key, uint64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCGM_H_ */

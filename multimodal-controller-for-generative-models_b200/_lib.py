@@ -1,0 +1,91 @@
+"""ctypes binding of libmcgm.so (the C ABI declared in include/mcgm.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing, or a call returns non-zero, a Python exception is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcgm.so")
+
+F32, BF16 = 0, 1
+GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK = 1, 2, 4, 8
+EPI_BIAS, EPI_RES, EPI_RES_UP2, EPI_RELU, EPI_MASK, EPI_TANH, EPI_POSMASK = 1, 2, 4, 8, 16, 32, 64
+
+# name -> (restype, argtypes); every symbol of include/mcgm.h
+SIGNATURES = {
+    "mcgm_last_error": (c_char_p, []),
+    "mcgm_version": (c_int, []),
+    "mcgm_sm_count": (c_int, []),
+    "mcgm_pack_codebook": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mcgm_mc_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mcgm_bn_stats_workspace_bytes": (c_size_t, [c_int]),
+    "mcgm_bn_stats": (c_int, [c_void_p, c_int, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_float, c_float, c_void_p, c_void_p]),
+    "mcgm_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_void_p]),
+    "mcgm_gate_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "mcgm_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mcgm_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcgm_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mcgm_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mcgm_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p]),
+    "mcgm_thin_wide_from_thin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "mcgm_thin_thin_from_wide": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_int, c_void_p]),
+    "mcgm_thin_kern_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mcgm_thin_kern_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p]),
+    "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mcgm_unpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mcgm_debug_set": (c_int, [c_int, c_uint64]),
+}
+
+_lib = None
+launch_count = 0          # number of libmcgm entry-point calls that launch kernels (bench: gpu_launches)
+
+
+def load():
+    """Load libmcgm.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; non-zero -> RuntimeError(mcgm_last_error())."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mcgm_last_error()
+        raise RuntimeError(f"{name} failed ({rc}): {msg.decode() if msg else '?'}")
+    launch_count += 1
+    return rc
+
+
+def query(name, *args):
+    """Call a size/version query (no error convention)."""
+    return getattr(load(), name)(*args)

@@ -1,0 +1,796 @@
+// conv_umma.cu — implicit-GEMM convolution on 5th-gen tensor cores.
+//
+// Replaces the cudnn_convolution / convolution_backward calls behind
+// nn.Conv2d in the MC block (src/models/mcgan.py:19,23,29,59,77-85,103-128).
+//
+//   forward / dgrad  : D[pixels, Cout] = sum_{tap, ci} X[pixel + tap, ci] * Wt[Cout, tap, ci]
+//     A = a 128-pixel tile (TN images x TH rows x TW cols) x 64 input channels, fetched
+//         per filter tap by ONE 4-D TMA box whose (w,h) origin is shifted by the tap;
+//         out-of-bounds box elements are zero-filled by TMA == the conv zero padding.
+//         No im2col buffer exists anywhere.
+//     B = [Cout tile, 64] slab of the KRSC weight, 2-D TMA box.
+//     Both land in smem as 128-byte rows with the 128B swizzle == the canonical
+//     K-major UMMA layout; tcgen05.mma (M=128, N=Cout tile, K=16) accumulates in TMEM.
+//   wgrad            : D[Cout, Cin] (per tap) = sum_pixels dY[pixel, co] * X[pixel + tap, ci]
+//     the reduction dimension is the pixel index, which is the SLOW dimension of NHWC,
+//     so both operands are fed as MN-major UMMA operands straight from the NHWC tensors.
+//
+// Kernel structure (both): 6 warps — warp 0 lane 0 = TMA producer, warp 1 lane 0 =
+// MMA issuer, warps 2..5 = epilogue (one TMEM lane quadrant each).  Persistent
+// over tiles, smem ring of kStages, double-buffered TMEM accumulator so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mcgm {
+
+// ---------------------------------------------------------------------------
+// tensor-map plumbing (driver entry point fetched at run time; no -lcuda)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d[4];
+  uint32_t b[4];
+  int rank;
+  bool operator==(const MapKey& o) const {
+    if (ptr != o.ptr || rank != o.rank) return false;
+    for (int i = 0; i < 4; ++i)
+      if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
+    return true;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)k.rank * 0x9e3779b97f4a7c15ull;
+    for (int i = 0; i < 4; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
+    return h;
+  }
+};
+
+// bf16 tensor, dims innermost-first, dense strides, 128B swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{};
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t bdim[4], estr[4];
+  uint64_t stride = 2;  // bytes
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu)",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// debug knobs (bring-up only): descriptor field overrides
+// ---------------------------------------------------------------------------
+struct DescKnobs {
+  uint32_t k_lbo = 16, k_sbo = 1024;         // K-major operands
+  uint32_t mn_lbo = 8192, mn_sbo = 1024;     // MN-major operands
+  uint32_t version = 1, layout = 2;
+};
+static DescKnobs g_knobs;
+
+// ---------------------------------------------------------------------------
+// forward kernel
+// ---------------------------------------------------------------------------
+static constexpr int kConvThreads = 192;
+static constexpr int kTileM = 128;
+static constexpr int kBlockK = 64;                       // bf16 elements = 128 B rows
+static constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
+
+struct ConvFwdParams {
+  int N, H, W, Cin, Cout, R, S, pad;
+  int TW, TH, TN, tiles_w, tiles_h;
+  int n_tiles, total_tiles;
+  int kpt, num_kb;
+  uint64_t desc_templ;
+  uint32_t idesc;
+  const float* bias;
+  const __nv_bfloat16* res;
+  const __nv_bfloat16* aux;
+  const int32_t* labels;
+  const uint32_t* bits;
+  int words;
+  int flags;
+  void* out;
+};
+
+template <int BN>
+struct FwdCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {16,64,128,256} -> power of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename OutT>
+__device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uint32_t (&acc)[32], int ncols,
+                                                     long pix, int n, int h, int w, int col0, bool valid) {
+  // acc: fp32 bit patterns of `ncols` consecutive output channels starting at col0
+  if (!valid) return;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  const int flags = p.flags;
+  if (flags & MCGM_EPI_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols && col0 + i < p.Cout) v[i] += __ldg(p.bias + col0 + i);
+  }
+  if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
+    long rpix = pix;
+    if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+    const __nv_bfloat16* rp = p.res + rpix * p.Cout + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (i < ncols) {
+        Vec<__nv_bfloat16> r;
+        r.load(rp + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i + j] += r.v[j];
+      }
+    }
+  }
+  if (flags & MCGM_EPI_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (flags & MCGM_EPI_MASK) {
+    const uint32_t m = __ldg(p.bits + (size_t)__ldg(p.labels + n) * p.words + (col0 >> 5)) >> (col0 & 31);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.0f;
+  }
+  if (flags & MCGM_EPI_POSMASK) {
+    const __nv_bfloat16* ap = p.aux + pix * p.Cout + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (i < ncols) {
+        Vec<__nv_bfloat16> r;
+        r.load(ap + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+      }
+    }
+  }
+  if (flags & MCGM_EPI_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+  }
+  OutT* op = reinterpret_cast<OutT*>(p.out) + pix * p.Cout + col0;
+  if ((p.Cout & 7) == 0) {
+    constexpr int V = Vec<OutT>::N;
+#pragma unroll
+    for (int i = 0; i < 32; i += V) {
+      if (i < ncols) {
+        Vec<OutT> o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = v[i + j];
+        o.store(op + i);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < ncols && col0 + i < p.Cout) {
+        if constexpr (sizeof(OutT) == 4) op[i] = v[i];
+        else op[i] = __float2bfloat16(v[i]);
+      }
+    }
+  }
+}
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const ConvFwdParams p) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.TW;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+        const int cout0 = nt * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
+          const int r = tap / p.S, s = tap - r * p.S;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          tma_load_4d(sa, &tmap_x, full_bar(stage), cb * kBlockK, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, cout0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      int stage = 0, phase = 0, it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = smem_desc(p.desc_templ, sa);
+          const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quadrant = warp % 4) =====
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1, aphase = (it >> 1) & 1;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int w = (mt % p.tiles_w) * p.TW + tw;
+      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+      const int n = (mt / (p.tiles_w * p.tiles_h)) * p.TN + tn;
+      const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+      const long pix = ((long)n * p.H + h) * p.W + w;
+      const int cout0 = nt * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      constexpr int CW = BN < 32 ? BN : 32;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CW) {
+        uint32_t acc[32];
+        if constexpr (CW == 32) tmem_ld32(t_row + c, acc);
+        else tmem_ld16(t_row + c, acc);
+        tmem_ld_wait();
+        epilogue_store_chunk<BN, OutT>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad kernel: one (cout tile, cin tile, tap, k-split) work item per CTA
+// ---------------------------------------------------------------------------
+struct WgradParams {
+  int N, H, W, Cin, Cout, R, S, pad;
+  int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 pixels
+  int total_kb, splits, kb_per_split;
+  int cout_tiles, cin_tiles, taps;
+  uint64_t desc_templ;
+  uint32_t idesc;
+  float* partial;                       // [splits][Cout*R*S*Cin]
+};
+
+template <int BN>
+struct WgCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradParams p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int id = blockIdx.x;
+  const int split = id % p.splits; id /= p.splits;
+  const int tap = id % p.taps; id /= p.taps;
+  const int cin_t = id % p.cin_tiles;
+  const int cout_t = id / p.cin_tiles;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+  const int r = tap / p.S, s = tap - r * p.S;
+  const int co0 = cout_t * kTileM, ci0 = cin_t * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int w0 = (kb % p.kb_w) * p.KW;
+        const int h0 = ((kb / p.kb_w) % p.kb_h) * p.KH;
+        const int n0 = (kb / (p.kb_w * p.kb_h)) * p.KN;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kTileM / 64; ++j)
+          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0, h0, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sa + kABytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j, w0 + s - p.pad,
+                      h0 + r - p.pad, n0);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint64_t adesc = smem_desc(p.desc_templ, sa);
+        const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
+                   (kb > kb0) || (k != 0));
+        umma_commit(empty_bar(stage));
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int co = co0 + quad * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t per_split = (size_t)p.Cout * p.taps * p.Cin;
+    float* dst = p.partial + (size_t)split * per_split + ((size_t)co * p.taps + tap) * p.Cin + ci0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t acc[32];
+      tmem_ld32(t_row + c, acc);
+      tmem_ld_wait();
+      if (co < p.Cout && kb1 > kb0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + c + i) =
+              make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                          __uint_as_float(acc[i + 3]));
+      } else if (co < p.Cout) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/,
+                                    float* __restrict__ dw) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(partial)[i];
+    for (int s = 1; s < splits; ++s) {
+      float4 b = reinterpret_cast<const float4*>(partial)[(size_t)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = a;
+  }
+}
+
+// column sums of a bf16 [P, C] matrix (bias gradient): partial per block, then fixed-order finish
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long P, int C, float* __restrict__ partial) {
+  const int CG = C / 8;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, PL = blockDim.x / CG;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (long q = (long)blockIdx.x * PL + pl; q < P; q += (long)gridDim.x * PL) {
+    Vec<__nv_bfloat16> v;
+    v.load(x + q * C + cg * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += v.v[i];
+  }
+  extern __shared__ float sm[];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[pl * C + cg * 8 + i] = s[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < PL; ++l) a += sm[l * C + c];
+    partial[(size_t)blockIdx.x * C + c] = a;
+  }
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  double S = 0.0;
+  for (int b = lane; b < nblocks; b += 32) S += (double)partial[(size_t)b * C + warp];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+  if (lane == 0) out[warp] = (float)S;
+}
+
+// ---------------------------------------------------------------------------
+// weight layout kernels
+// ---------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int K, int C, int R, int S,
+                                   const float* __restrict__ inv_sigma, __nv_bfloat16* __restrict__ krsc,
+                                   __nv_bfloat16* __restrict__ crsk_flip) {
+  const long total = (long)K * C * R * S;
+  const float sc = inv_sigma ? __ldg(inv_sigma) : 1.0f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    // i indexes the KRSC destination so the bf16 writes are coalesced
+    long t = i;
+    const int c = (int)(t % C); t /= C;
+    const int s = (int)(t % S); t /= S;
+    const int r = (int)(t % R);
+    const int k = (int)(t / R);
+    const float v = w[(((long)k * C + c) * R + r) * S + s] * sc;
+    const __nv_bfloat16 b = __float2bfloat16(v);
+    if (krsc) krsc[i] = b;
+    if (crsk_flip) crsk_flip[(((long)c * R + (R - 1 - r)) * S + (S - 1 - s)) * K + k] = b;
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw_krsc, int K, int C, int R, int S,
+                                    float* __restrict__ dw_oihw, int accumulate) {
+  const long total = (long)K * C * R * S;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = (int)(t % C); t /= C;
+    const int s = (int)(t % S); t /= S;
+    const int r = (int)(t % R);
+    const int k = (int)(t / R);
+    const long o = (((long)k * C + c) * R + r) * S + s;
+    dw_oihw[o] = accumulate ? dw_oihw[o] + dw_krsc[i] : dw_krsc[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static bool pick_pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
+  // a box of `npix` pixels: as many columns as fit, then rows, then images
+  int tw = W < npix ? W : npix;
+  if (npix % tw) return false;
+  int rem = npix / tw;
+  int th = H < rem ? H : rem;
+  if (rem % th) return false;
+  int tn = rem / th;
+  if (W % tw || H % th) return false;
+  *bw = tw; *bh = th; *bn = tn;
+  return true;
+}
+
+template <int BN, typename OutT>
+static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFwdParams& p, cudaStream_t st) {
+  using Cfg = FwdCfg<BN>;
+  auto kern = conv_fwd_kernel<BN, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  int sms = sm_count();
+  if (sms <= 0) return fail(MCGM_E_CUDA, "cannot query SM count");
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mx, mw, p);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, int grid,
+                        cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  auto kern = conv_wgrad_kernel<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mdy, mx, p);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+struct WgradPlan {
+  int BN, cout_tiles, cin_tiles, taps, splits, kb_per_split, total_kb, KW, KH, KN;
+  size_t per_split;  // floats
+};
+
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
+  if (Cin % 64 || Cout % 64) return fail(MCGM_E_UNSUPPORTED, "wgrad: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
+  if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "wgrad: only 1x1 and 3x3 kernels");
+  if (!pick_pixel_box(H, W, 64, &pl->KW, &pl->KH, &pl->KN))
+    return fail(MCGM_E_UNSUPPORTED, "wgrad: H=%d W=%d cannot be tiled into 64-pixel boxes", H, W);
+  pl->BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  pl->cin_tiles = Cin / pl->BN;
+  pl->cout_tiles = (Cout + kTileM - 1) / kTileM;
+  pl->taps = R * S;
+  const int n_boxes = (N + pl->KN - 1) / pl->KN;
+  pl->total_kb = n_boxes * (H / pl->KH) * (W / pl->KW);
+  const int tiles = pl->cout_tiles * pl->cin_tiles * pl->taps;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int splits = (sms + tiles - 1) / tiles;          // about one wave
+  if (splits > pl->total_kb) splits = pl->total_kb;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  pl->kb_per_split = (pl->total_kb + splits - 1) / splits;
+  pl->splits = (pl->total_kb + pl->kb_per_split - 1) / pl->kb_per_split;
+  pl->per_split = (size_t)Cout * pl->taps * Cin;
+  return 0;
+}
+
+}  // namespace mcgm
+
+using namespace mcgm;
+
+extern "C" int mcgm_debug_set(int key, uint64_t value) {
+  switch (key) {
+    case 0: g_knobs.k_lbo = (uint32_t)value; break;
+    case 1: g_knobs.k_sbo = (uint32_t)value; break;
+    case 2: g_knobs.mn_lbo = (uint32_t)value; break;
+    case 3: g_knobs.mn_sbo = (uint32_t)value; break;
+    case 4: g_knobs.version = (uint32_t)value; break;
+    case 5: g_knobs.layout = (uint32_t)value; break;
+    default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
+  }
+  return 0;
+}
+
+extern "C" int mcgm_pack_weight(const float* w_oihw, int K, int C, int R, int S, const float* inv_sigma,
+                                void* w_krsc_bf16, void* w_crsk_flip_bf16, void* stream) {
+  MCGM_CHECK_ARG(w_oihw && (w_krsc_bf16 || w_crsk_flip_bf16) && K > 0 && C > 0 && R > 0 && S > 0, "pack_weight: bad arguments");
+  const long total = (long)K * C * R * S;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, K, C, R, S, inv_sigma,
+                                                                   (__nv_bfloat16*)w_krsc_bf16,
+                                                                   (__nv_bfloat16*)w_crsk_flip_bf16);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int S, float* dw_oihw, int accumulate,
+                                 void* stream) {
+  MCGM_CHECK_ARG(dw_krsc && dw_oihw && K > 0 && C > 0 && R > 0 && S > 0, "unpack_wgrad: bad arguments");
+  const long total = (long)K * C * R * S;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  unpack_wgrad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dw_krsc, K, C, R, S, dw_oihw, accumulate);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, const float* bias, const void* res, const void* aux,
+                             const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
+  MCGM_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv_fwd: bad arguments");
+  MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "conv_fwd: out_dtype %d unsupported", out_dtype);
+  if (Cin % kBlockK) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cin=%d must be a multiple of 64 (use the thin kernels)", Cin);
+  if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: only 1x1 and 3x3 kernels (got %dx%d)", R, S);
+  if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "conv_fwd: BIAS flag without bias");
+  if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) MCGM_CHECK_ARG(res && (Cout % 8 == 0), "conv_fwd: RES flag needs res and Cout %% 8 == 0");
+  if (flags & MCGM_EPI_RES_UP2) MCGM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv_fwd: RES_UP2 needs even H, W");
+  if (flags & MCGM_EPI_MASK) MCGM_CHECK_ARG(labels && bits && M > 0 && Cout % 32 == 0, "conv_fwd: MASK needs labels, bits and Cout %% 32 == 0");
+  if (flags & MCGM_EPI_POSMASK) MCGM_CHECK_ARG(aux && (Cout % 8 == 0), "conv_fwd: POSMASK needs aux and Cout %% 8 == 0");
+
+  ConvFwdParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = (R - 1) / 2;
+  if (!pick_pixel_box(H, W, kTileM, &p.TW, &p.TH, &p.TN))
+    return fail(MCGM_E_UNSUPPORTED, "conv_fwd: H=%d W=%d cannot be tiled into 128-pixel boxes", H, W);
+  p.tiles_w = W / p.TW;
+  p.tiles_h = H / p.TH;
+  const int tiles_nb = (N + p.TN - 1) / p.TN;
+  int BN;
+  if (Cout % 256 == 0) BN = 256;
+  else if (Cout % 128 == 0) BN = 128;
+  else if (Cout % 64 == 0) BN = 64;
+  else if (Cout <= 16) BN = 16;
+  else return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d unsupported (multiple of 64, or <= 16)", Cout);
+  p.n_tiles = (Cout + BN - 1) / BN;
+  p.total_tiles = p.tiles_w * p.tiles_h * tiles_nb * p.n_tiles;
+  p.kpt = Cin / kBlockK;
+  p.num_kb = R * S * p.kpt;
+  p.desc_templ = make_smem_desc_hi_lbo(g_knobs.k_lbo, g_knobs.k_sbo, g_knobs.version, g_knobs.layout);
+  p.idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+  p.bias = bias; p.res = (const __nv_bfloat16*)res; p.aux = (const __nv_bfloat16*)aux;
+  p.labels = labels; p.bits = bits; p.words = (Cout + 31) / 32; p.flags = flags; p.out = out;
+
+  CUtensorMap mx, mw;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    if (int e = make_tmap(&mx, x, 4, dims, box)) return e;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)R * S * Cin, (uint64_t)Cout};
+    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    if (int e = make_tmap(&mw, w, 2, dims, box)) return e;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f32 = out_dtype == MCGM_F32;
+  switch (BN) {
+    case 256: return f32 ? launch_fwd<256, float>(mx, mw, p, st) : launch_fwd<256, __nv_bfloat16>(mx, mw, p, st);
+    case 128: return f32 ? launch_fwd<128, float>(mx, mw, p, st) : launch_fwd<128, __nv_bfloat16>(mx, mw, p, st);
+    case 64: return f32 ? launch_fwd<64, float>(mx, mw, p, st) : launch_fwd<64, __nv_bfloat16>(mx, mw, p, st);
+    default: return f32 ? launch_fwd<16, float>(mx, mw, p, st) : launch_fwd<16, __nv_bfloat16>(mx, mw, p, st);
+  }
+}
+
+extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {
+  WgradPlan pl;
+  if (plan_wgrad(N, H, W, Cin, Cout, R, S, &pl)) return 0;
+  size_t bytes = (size_t)pl.splits * pl.per_split * sizeof(float);
+  bytes += (size_t)148 * 4 * Cout * sizeof(float);  // bias-gradient partials
+  return bytes;
+}
+
+extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
+                               int Cout, int R, int S, void* workspace, void* stream) {
+  MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
+  WgradPlan pl;
+  if (int e = plan_wgrad(N, H, W, Cin, Cout, R, S, &pl)) return e;
+  WgradParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = (R - 1) / 2;
+  p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = W / pl.KW; p.kb_h = H / pl.KH;
+  p.total_kb = pl.total_kb; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
+  p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps;
+  p.desc_templ = make_smem_desc_hi_lbo(g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
+  p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1);
+  p.partial = (float*)workspace;
+
+  CUtensorMap mdy, mx;
+  const uint32_t box[4] = {64u, (uint32_t)pl.KW, (uint32_t)pl.KH, (uint32_t)pl.KN};
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    if (int e = make_tmap(&mdy, dy, 4, dims, box)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    if (int e = make_tmap(&mx, x, 4, dims, box)) return e;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = pl.cout_tiles * pl.cin_tiles * pl.taps * pl.splits;
+  int e;
+  switch (pl.BN) {
+    case 256: e = launch_wgrad<256>(mdy, mx, p, grid, st); break;
+    case 128: e = launch_wgrad<128>(mdy, mx, p, grid, st); break;
+    default: e = launch_wgrad<64>(mdy, mx, p, grid, st); break;
+  }
+  if (e) return e;
+  const size_t n4 = pl.per_split / 4;
+  long blocks = (long)((n4 + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw);
+  MCGM_LAUNCH_CHECK();
+  if (dbias) {
+    if (Cout % 8 || (Cout / 8) > 256 || 256 % (Cout / 8))
+      return fail(MCGM_E_UNSUPPORTED, "conv_wgrad: dbias needs Cout/8 dividing 256");
+    float* bpart = p.partial + (size_t)pl.splits * pl.per_split;
+    const int CG = Cout / 8, PL = 256 / CG;
+    const long P = (long)N * H * W;
+    long nb = (P + PL - 1) / PL;
+    if (nb > 148 * 4) nb = 148 * 4;
+    colsum_partial_kernel<<<(int)nb, 256, (size_t)PL * Cout * sizeof(float), st>>>((const __nv_bfloat16*)dy, P, Cout, bpart);
+    MCGM_LAUNCH_CHECK();
+    colsum_finalize_kernel<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(bpart, (int)nb, Cout, dbias);
+    MCGM_LAUNCH_CHECK();
+  }
+  return 0;
+}

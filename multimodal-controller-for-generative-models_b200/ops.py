@@ -1,0 +1,423 @@
+"""Tensor-level wrappers and ``torch.autograd.Function``s over the C ABI.
+
+Internal activation layout is NHWC: tensors of shape ``[N, H, W, C]``, contiguous,
+bf16 (or fp32 for the gate kernels).  PyTorch is used for device memory, streams and
+autograd bookkeeping only; every kernel launched here comes from libmcgm.so.
+Shape / dtype / contiguity problems raise ``ValueError`` (the reference's error
+style, e.g. src/utils.py:126); a failing native call raises ``RuntimeError``.
+"""
+import torch
+
+from . import _lib
+from ._lib import (BF16, EPI_BIAS, EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_TANH, F32,
+                   GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2)
+
+
+# --------------------------------------------------------------------------- helpers
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise ValueError(f"Not valid dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mcgm_b200 kernels run on CUDA tensors only; there is no CPU fallback")
+        if not t.is_contiguous():
+            raise ValueError("Not valid layout: tensor must be contiguous")
+
+
+_workspaces = {}
+
+
+def _workspace(tag, nbytes, device):
+    """Persistent per-(tag, device) scratch buffer, grown on demand (never shrinks)."""
+    key = (tag, device)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+class PackedCodebook:
+    """Bit-packed device copy of a MultimodalController codebook (mcgm_pack_codebook)."""
+
+    def __init__(self, codebook):
+        _check_cuda(codebook)
+        if codebook.dim() != 2 or codebook.dtype != torch.float32:
+            raise ValueError("Not valid codebook (float32 [num_mode, input_size])")
+        self.M, self.C = codebook.shape
+        self.words = (self.C + 31) // 32
+        self.bits = torch.empty(self.M, self.words, dtype=torch.int32, device=codebook.device)
+        _lib.call("mcgm_pack_codebook", codebook.data_ptr(), self.M, self.C, self.bits.data_ptr(), _stream())
+
+
+def as_labels(labels):
+    """int32 device labels from int64/int32 labels."""
+    if labels.dtype == torch.int32:
+        return labels
+    return labels.to(torch.int32)
+
+
+# --------------------------------------------------------------------------- raw calls
+def mc_mask(x, labels=None, packed=None, code=None, nchw=False):
+    """y = x * code(n, c) — MultimodalController.forward (src/modules/modules.py:71-76)."""
+    _check_cuda(x, labels, code)
+    N = x.shape[0]
+    if nchw:
+        C = x.shape[1]
+        P = x.numel() // max(N * C, 1)
+    else:
+        C = x.shape[-1]
+        P = x.numel() // max(N * C, 1)
+    y = torch.empty_like(x)
+    if N == 0:
+        return y
+    if labels is not None:
+        _lib.call("mcgm_mc_forward", x.data_ptr(), y.data_ptr(), _dtype_code(x), int(nchw), N, P, C,
+                  labels.data_ptr(), packed.bits.data_ptr(), packed.M, 0, _stream())
+    else:
+        if code.dtype != torch.float32 or code.shape != (N, C):
+            raise ValueError("Not valid code (float32 [N, C])")
+        _lib.call("mcgm_mc_forward", x.data_ptr(), y.data_ptr(), _dtype_code(x), int(nchw), N, P, C,
+                  0, 0, 0, code.data_ptr(), _stream())
+    return y
+
+
+def bn_stats(x, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
+    """Train-mode batch statistics of an NHWC tensor -> (mean, rstd), updates running stats in place."""
+    _check_cuda(x, running_mean, running_var)
+    C = x.shape[-1]
+    P = x.numel() // C
+    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = _workspace("bn", _lib.query("mcgm_bn_stats_workspace_bytes", C), x.device)
+    _lib.call("mcgm_bn_stats", x.data_ptr(), _dtype_code(x), P, C, mean.data_ptr(), rstd.data_ptr(),
+              _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), ws.data_ptr(), _stream())
+    return mean, rstd
+
+
+def gate_fwd(x, flags, labels=None, packed=None, mean=None, rstd=None, gamma=None, beta=None, want_raw=False):
+    _check_cuda(x, labels, mean, rstd, gamma, beta)
+    N, H, W, C = x.shape
+    up = 2 if flags & GATE_UP2 else 1
+    y = torch.empty(N, H * up, W * up, C, dtype=x.dtype, device=x.device)
+    y_raw = torch.empty_like(x) if want_raw else None
+    _lib.call("mcgm_gate_fwd", x.data_ptr(), y.data_ptr(), _ptr(y_raw), _dtype_code(x), N, H, W, C,
+              _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
+              _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), flags, _stream())
+    return y, y_raw
+
+
+def gate_bwd(dy, d_raw, x, flags, labels=None, packed=None, mean=None, rstd=None, gamma=None, beta=None):
+    _check_cuda(dy, d_raw, x, labels)
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    dgamma = dbeta = None
+    ws = None
+    if flags & GATE_BN:
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws = _workspace("gate_bwd", _lib.query("mcgm_gate_bwd_workspace_bytes", C), x.device)
+    _lib.call("mcgm_gate_bwd", _ptr(dy), _ptr(d_raw), x.data_ptr(), dx.data_ptr(), _dtype_code(x), N, H, W, C,
+              _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
+              _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(dgamma), _ptr(dbeta), flags,
+              _ptr(ws), _stream())
+    return dx, dgamma, dbeta
+
+
+def pack_weight(w, inv_sigma=None, want_fwd=True, want_flip=True):
+    """fp32 OIHW -> (bf16 KRSC, bf16 CRSK with flipped taps)."""
+    _check_cuda(w, inv_sigma)
+    if w.dtype != torch.float32 or w.dim() != 4:
+        raise ValueError("Not valid weight (float32 [K, C, R, S])")
+    K, C, R, S = w.shape
+    fwd = torch.empty(K, R, S, C, dtype=torch.bfloat16, device=w.device) if want_fwd else None
+    flip = torch.empty(C, R, S, K, dtype=torch.bfloat16, device=w.device) if want_flip else None
+    _lib.call("mcgm_pack_weight", w.data_ptr(), K, C, R, S, _ptr(inv_sigma), _ptr(fwd), _ptr(flip), _stream())
+    return fwd, flip
+
+
+def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None, labels=None, packed=None,
+             flags=0):
+    """Implicit-GEMM conv (tcgen05): x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> [N,H,W,Cout]."""
+    _check_cuda(x, w_krsc, bias, res, aux, labels)
+    if x.dtype != torch.bfloat16 or w_krsc.dtype != torch.bfloat16:
+        raise ValueError("Not valid dtype: conv operands must be bfloat16")
+    N, H, W, Cin = x.shape
+    Cout, R, S, Cin2 = w_krsc.shape
+    if Cin2 != Cin:
+        raise ValueError(f"Not valid weight: Cin {Cin2} != input channels {Cin}")
+    out = torch.empty(N, H, W, Cout, dtype=out_dtype, device=x.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    _lib.call("mcgm_conv_fwd", x.data_ptr(), w_krsc.data_ptr(), out.data_ptr(),
+              F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, R, S,
+              _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
+              packed.M if packed else 0, flags, _stream())
+    return out
+
+
+def conv_wgrad(x, dy, R, S, want_bias=True):
+    """dw (fp32 KRSC [Cout,R,S,Cin]) and dbias from NHWC bf16 x and dy."""
+    _check_cuda(x, dy)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    nbytes = _lib.query("mcgm_conv_wgrad_workspace_bytes", N, H, W, Cin, Cout, R, S)
+    if nbytes == 0:
+        raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} R={R}")
+    ws = _workspace("wgrad", nbytes, x.device)
+    dw = torch.empty(Cout, R, S, Cin, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    _lib.call("mcgm_conv_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, R, S,
+              ws.data_ptr(), _stream())
+    return dw, db
+
+
+def pool2(x, scale):
+    """y[n,h,w,c] = scale * sum of the 2x2 window (AvgPool2d(2) with scale=.25; upsample backward with 1)."""
+    _check_cuda(x)
+    N, H, W, C = x.shape
+    if H % 2 or W % 2:
+        raise ValueError("Not valid shape for 2x2 pooling")
+    y = torch.empty(N, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+    _lib.call("mcgm_pool2", x.data_ptr(), y.data_ptr(), _dtype_code(x), N, H // 2, W // 2, C, float(scale), _stream())
+    return y
+
+
+def unpool2(dy, scale):
+    """dx[n,2h+i,2w+j,c] = scale * dy[n,h,w,c] (AvgPool2d backward with .25; nearest upsample with 1)."""
+    _check_cuda(dy)
+    N, H, W, C = dy.shape
+    dx = torch.empty(N, 2 * H, 2 * W, C, dtype=dy.dtype, device=dy.device)
+    _lib.call("mcgm_unpool2", dy.data_ptr(), dx.data_ptr(), _dtype_code(dy), N, H, W, C, float(scale), _stream())
+    return dx
+
+
+def wide_from_thin(thin, kern, Cw, R, S, bias=None, labels=None, packed=None, aux=None, flags=0):
+    _check_cuda(thin, kern, bias, labels, aux)
+    N, H, W, Ct = thin.shape
+    wide = torch.empty(N, H, W, Cw, dtype=torch.bfloat16, device=thin.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    _lib.call("mcgm_thin_wide_from_thin", thin.data_ptr(), kern.data_ptr(), wide.data_ptr(), N, H, W, Ct, Cw, R, S,
+              _ptr(bias), _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
+              _ptr(aux), flags, _stream())
+    return wide
+
+
+def thin_from_wide(wide, kern, Ct, R, S, bias=None, flags=0):
+    _check_cuda(wide, kern, bias)
+    N, H, W, Cw = wide.shape
+    thin = torch.empty(N, H, W, Ct, dtype=torch.float32, device=wide.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    _lib.call("mcgm_thin_thin_from_wide", wide.data_ptr(), kern.data_ptr(), thin.data_ptr(), N, H, W, Ct, Cw, R, S,
+              _ptr(bias), flags, _stream())
+    return thin
+
+
+def kern_grad(thin, wide, R, S):
+    _check_cuda(thin, wide)
+    N, H, W, Ct = thin.shape
+    Cw = wide.shape[-1]
+    ws = _workspace("kgrad", _lib.query("mcgm_thin_kern_grad_workspace_bytes", Ct, Cw, R, S), thin.device)
+    dk = torch.empty(R * S, Ct, Cw, dtype=torch.float32, device=thin.device)
+    _lib.call("mcgm_thin_kern_grad", thin.data_ptr(), wide.data_ptr(), dk.data_ptr(), N, H, W, Ct, Cw, R, S,
+              ws.data_ptr(), _stream())
+    return dk
+
+
+# --------------------------------------------------------------------------- autograd Functions
+class MCMaskFn(torch.autograd.Function):
+    """x * code.detach() (src/modules/modules.py:75): dx = dy * code, nothing flows to the indicator."""
+
+    @staticmethod
+    def forward(ctx, x, labels, packed, code, nchw):
+        ctx.labels, ctx.packed, ctx.code, ctx.nchw = labels, packed, code, nchw
+        return mc_mask(x, labels, packed, code, nchw)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return mc_mask(dy.contiguous(), ctx.labels, ctx.packed, ctx.code, ctx.nchw), None, None, None, None
+
+
+class GateFn(torch.autograd.Function):
+    """BN(train) -> ReLU -> [2x nearest upsample] -> MC mask, plus the optional raw-gated output.
+
+    Restates src/models/mcgan.py:15-18 / 20-22 / 56-58 (with BN) and :104-105 (without).
+    Returns (y, y_raw or None).
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, labels, packed, flags, running_mean, running_var, momentum, eps, want_raw):
+        mean = rstd = None
+        if flags & GATE_BN:
+            mean, rstd = bn_stats(x, running_mean, running_var, momentum, eps)
+        y, y_raw = gate_fwd(x, flags, labels, packed, mean, rstd, gamma, beta, want_raw)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.labels, ctx.packed, ctx.flags, ctx.want_raw = labels, packed, flags, want_raw
+        if want_raw:
+            return y, y_raw
+        ctx.mark_non_differentiable()
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, d_raw):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous() if dy is not None else None
+        d_raw = d_raw.contiguous() if d_raw is not None else None
+        if dy is None and d_raw is None:
+            return (None,) * 11
+        if dy is None and (ctx.flags & GATE_BN):
+            up = 2 if ctx.flags & GATE_UP2 else 1
+            N, H, W, C = x.shape
+            dy = torch.zeros(N, H * up, W * up, C, dtype=x.dtype, device=x.device)
+        dx, dgamma, dbeta = gate_bwd(dy, d_raw, x, ctx.flags, ctx.labels, ctx.packed, mean, rstd, gamma, beta)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+class ConvFn(torch.autograd.Function):
+    """3x3 / 1x1 stride-1 conv on tensor cores with fused epilogue.
+
+    w is the fp32 OIHW master weight (state_dict layout).  ``gate`` = (labels, packed):
+    out = mask * relu(conv + bias) — D's Conv→ReLU→MC (src/models/mcgan.py:103-108).
+    ``res`` / ``res_up``: residual add of a same-resolution / half-resolution tensor (the
+    ResBlock sum mcgan.py:42, with the shortcut's nearest upsample folded in).
+    ``premask_dx``: the input x is itself a ReLU-gated activation with no other consumer,
+    so dgrad emits dx * 1[x > 0] (masked-gradient epilogue) and the producer of x is told
+    (``grad_premasked``) not to mask again.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs):
+        wf, wflip = packs if packs is not None else pack_weight(w)
+        flags = 0
+        labels = packed = None
+        if gate is not None:
+            labels, packed = gate
+            flags |= EPI_RELU | EPI_MASK
+        if res is not None:
+            flags |= EPI_RES_UP2 if res_up else EPI_RES
+        out = conv_fwd(x, wf, torch.bfloat16, bias, res, None, labels, packed, flags)
+        ctx.save_for_backward(x, out if gate is not None else None)
+        ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
+        ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
+        ctx.gated, ctx.premask_dx, ctx.grad_premasked = gate is not None, premask_dx, grad_premasked
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        K, C, R, S = ctx.wshape
+        if ctx.gated and not ctx.grad_premasked:
+            # d(pre) = dout * 1[out > 0]   (mask already folded: out == 0 where masked)
+            dout = torch.where(out > 0, dout, torch.zeros_like(dout))
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            if ctx.premask_dx:
+                dx = conv_fwd(dout, ctx.wflip, torch.bfloat16, None, None, x, None, None, EPI_POSMASK)
+            else:
+                dx = conv_fwd(dout, ctx.wflip, torch.bfloat16)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw_krsc, db = conv_wgrad(x, dout, R, S, want_bias=ctx.has_bias)
+            dw = dw_krsc.permute(0, 3, 1, 2)          # KRSC -> OIHW view
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = pool2(dout, 1.0) if ctx.res_up else dout
+        return dx, dw, db, dres, None, None, None, None, None
+
+
+class WideFromThinFn(torch.autograd.Function):
+    """Conv2d(Ct<=4 -> Cw) on an fp32 NHWC image, optional ReLU+mask epilogue (mcgan.py:77-79, 87)."""
+
+    @staticmethod
+    def forward(ctx, thin, w, bias, gate, grad_premasked):
+        K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
+        kern = w.detach().permute(2, 3, 1, 0).reshape(R * S, C, K).contiguous()
+        flags, labels, packed = 0, None, None
+        if gate is not None:
+            labels, packed = gate
+            flags = EPI_RELU | EPI_MASK
+        out = wide_from_thin(thin, kern, K, R, S, bias, labels, packed, None, flags)
+        ctx.save_for_backward(thin, w, out if gate is not None else None)
+        ctx.gated, ctx.has_bias, ctx.grad_premasked = gate is not None, bias is not None, grad_premasked
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        thin, w, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        K, C, R, S = w.shape
+        if ctx.gated and not ctx.grad_premasked:
+            dout = torch.where(out > 0, dout, torch.zeros_like(dout))
+        dthin = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dthin[p,j] = sum_{t,c} dout[p - off(t), c] w[c,j,t]  ->  kern[t'][j][c] = w[c, j, flip(t')]
+            kern = w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(R * S, C, K).contiguous()
+            dthin = thin_from_wide(dout, kern, C, R, S)
+        if ctx.needs_input_grad[1]:
+            dk = kern_grad(thin, dout, R, S)                   # [T][Ct][Cw]
+            dw = dk.reshape(R, S, C, K).permute(3, 2, 0, 1)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dout.float().sum(dim=(0, 1, 2))
+        return dthin, dw, db, None, None
+
+
+class ThinFromWideFn(torch.autograd.Function):
+    """Conv2d(Cw -> Ct<=4) producing an fp32 NHWC image, optional tanh (mcgan.py:59-60)."""
+
+    @staticmethod
+    def forward(ctx, wide, w, bias, tanh):
+        K, C, R, S = w.shape                                   # OIHW: K = Ct, C = Cw
+        kern = w.detach().permute(2, 3, 0, 1).reshape(R * S, K, C).contiguous()
+        out = thin_from_wide(wide, kern, K, R, S, bias, EPI_TANH if tanh else 0)
+        ctx.save_for_backward(wide, w, out if tanh else None)
+        ctx.tanh, ctx.has_bias = tanh, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        wide, w, out = ctx.saved_tensors
+        K, C, R, S = w.shape
+        dout = dout.contiguous()
+        if ctx.tanh:
+            dout = dout * (1.0 - out * out)                     # fp32 [N,H,W,3]: tiny
+        dwide = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dwide[p,c] = sum_{t,j} dout[p - off(t), j] w[j,c,t]  ->  kern[t'][j][c] = w[j, c, flip(t')]
+            kern = w.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(R * S, K, C).contiguous()
+            dwide = wide_from_thin(dout, kern, C, R, S)
+        if ctx.needs_input_grad[1]:
+            # dw[j,c,t] = sum_p dout[p,j] wide[p+off(t),c] = sum_q dout[q - off(t), j] wide[q, c]
+            dk = kern_grad(dout, wide, R, S)                   # dk[t'][j][c] with off(t') = -off(t)
+            dw = dk.reshape(R, S, K, C).flip(0, 1).permute(2, 3, 0, 1)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dout.sum(dim=(0, 1, 2))
+        return dwide, dw, db, None
+
+
+class Pool2Fn(torch.autograd.Function):
+    """AvgPool2d(2) on NHWC (src/models/mcgan.py:81,88,109,114)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return pool2(x, 0.25)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return unpool2(dy.contiguous(), 0.25)

@@ -1,0 +1,161 @@
+"""The MCGAN training step (src/train_gan.py:128-194, core :139-176) on the B200 kernels,
+plus one-process-per-GPU data parallelism (replaces nn.DataParallel, train_gan.py:96-98).
+
+``train_step`` restates the reference loop body: ``iter['discriminator']`` D updates
+(zero_grad both nets; D(real); G(z1); D(G.detach()); hinge; backward; Adam) followed by
+``iter['generator']`` G updates (G(z2); D(G); -mean; backward; Adam).  Noise can be injected
+(``z=[z1.., z2]``) so that a parity run and the oracle see identical randomness.  Losses stay
+on the device; nothing in the step synchronises with the host.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .config import GAN_HYPER, cfg
+
+
+def make_optimizer(model, lr, betas):
+    """Adam with torch defaults eps=1e-8, no amsgrad (src/train_gan.py:223-236)."""
+    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas)
+
+
+def make_optimizers(model):
+    return {
+        'generator': make_optimizer(model.generator, GAN_HYPER['lr']['generator'], GAN_HYPER['betas']['generator']),
+        'discriminator': make_optimizer(model.discriminator, GAN_HYPER['lr']['discriminator'],
+                                        GAN_HYPER['betas']['discriminator']),
+    }
+
+
+class GradAllReduce:
+    """Data-parallel gradient averaging over NCCL (or gloo in CPU tests).
+
+    Each net's gradients live in ONE flat fp32 buffer (``p.grad`` are views), cut into
+    buckets in reverse parameter order.  A post-accumulate hook counts the parameters of a
+    bucket as autograd finishes them; when a bucket is complete its all-reduce is issued
+    asynchronously on the communication stream, overlapping the rest of backward.
+    ``finish()`` waits for the outstanding work and divides by the world size.
+    BatchNorm statistics stay per-rank, as with the reference's DataParallel replicas.
+    """
+
+    def __init__(self, module, bucket_bytes=8 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        self.views = []
+        for p in self.params:
+            g = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = g
+            self.views.append(g)
+            off += p.numel()
+        # buckets over the flat buffer, filled from the END (backward reaches late layers first)
+        self.buckets = []           # (start, stop, n_params)
+        self.bucket_of = {}
+        start = stop = total
+        count = 0
+        for p in reversed(self.params):
+            start -= p.numel()
+            count += 1
+            self.bucket_of[id(p)] = len(self.buckets)
+            if (stop - start) * 4 >= bucket_bytes:
+                self.buckets.append([start, stop, count])
+                stop, count = start, 0
+        if count:
+            self.buckets.append([start, stop, count])
+        self.pending = [0] * len(self.buckets)
+        self.handles = []
+        self.enabled = True
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero_grad(self):
+        """Replacement for optimizer.zero_grad(): one memset, grads stay views of the flat buffer."""
+        self.flat.zero_()
+        for p, g in zip(self.params, self.views):
+            p.grad = g
+        self.pending = [0] * len(self.buckets)
+        self.handles = []
+
+    def _hook(self, p):
+        if not self.enabled:
+            return
+        b = self.bucket_of[id(p)]
+        self.pending[b] += 1
+        if self.pending[b] == self.buckets[b][2]:
+            s, e, _ = self.buckets[b]
+            self.handles.append(dist.all_reduce(self.flat[s:e], group=self.group, async_op=True))
+
+    def finish(self):
+        if self.world == 1:
+            return
+        # parameters that received no gradient this step (unused) still need their bucket reduced
+        for b, (s, e, n) in enumerate(self.buckets):
+            if self.pending[b] != n:
+                self.handles.append(dist.all_reduce(self.flat[s:e], group=self.group, async_op=True))
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        self.flat.div_(self.world)
+
+
+def hinge_d(d_real, d_fake):
+    """relu(1 - D(x)).mean() + relu(1 + D(G(z))).mean()   (src/train_gan.py:154)."""
+    return F.relu(1.0 - d_real).mean() + F.relu(1.0 + d_fake).mean()
+
+
+def train_step(model, optimizer, input, z=None, reducers=None):
+    """One reference iteration on a batch ``{'img': [N,C,H,W] fp32, 'label': [N] int64}``.
+
+    z: optional list of ``iter_D + iter_G`` latent tensors [N, latent] (injected noise).
+    reducers: optional ``{'generator': GradAllReduce, 'discriminator': GradAllReduce}``.
+    Returns ``{'loss_D', 'loss_G', 'loss'}`` as device tensors (no host sync).
+    """
+    img, label = input['img'], input[cfg.get('subset', 'label')]
+    n = img.size(0)
+    n_d, n_g = GAN_HYPER['iter']['discriminator'], GAN_HYPER['iter']['generator']
+    zi = iter(z) if z is not None else None
+
+    def draw():
+        if zi is not None:
+            return next(zi)
+        return torch.randn(n, model.latent_size, device=img.device)
+
+    def zero():
+        if reducers is not None:
+            reducers['discriminator'].zero_grad()
+            reducers['generator'].zero_grad()
+        else:
+            optimizer['discriminator'].zero_grad()
+            optimizer['generator'].zero_grad()
+
+    d_loss = g_loss = None
+    for _ in range(n_d):                                       # (1) update D   train_gan.py:139-158
+        zero()
+        if reducers is not None:
+            reducers['generator'].enabled = False              # G receives no gradient in the D step
+        d_x = model.discriminate(img, label)
+        generated = model.generate(label, draw())
+        d_g = model.discriminate(generated.detach(), label)
+        d_loss = hinge_d(d_x, d_g)
+        d_loss.backward()
+        if reducers is not None:
+            reducers['discriminator'].finish()
+            reducers['generator'].enabled = True
+        optimizer['discriminator'].step()
+    for _ in range(n_g):                                       # (2) update G   train_gan.py:162-176
+        zero()
+        if reducers is not None:
+            reducers['discriminator'].enabled = False          # D's grads are discarded by the next zero_grad
+        generated = model.generate(label, draw())
+        g_loss = -model.discriminate(generated, label).mean()
+        g_loss.backward()
+        if reducers is not None:
+            reducers['generator'].finish()
+            reducers['discriminator'].enabled = True
+        optimizer['generator'].step()
+    return {'loss': (d_loss - g_loss).abs(), 'loss_D': d_loss, 'loss_G': g_loss}
