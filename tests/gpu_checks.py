@@ -1,0 +1,285 @@
+"""GPU parity checks: every kernel family of libmcgm.so against the oracle / plain torch fp32
+on identical seeded inputs.  Each check returns a list of (label, error, tolerance) rows;
+tests/test_gpu_kernels.py asserts on them and tools/gpu_bringup.py prints them all.
+
+Tolerances (written here, used everywhere):
+  EXACT      0          integer / bit work: packed codebook, masks
+  F32        2e-5       fp32 storage kernels, and bf16-input kernels compared on the SAME
+                        bf16-rounded inputs with fp32 output (only the summation order differs)
+  BF16_OUT   6e-3       same, but the result is stored in bf16 (one rounding: 2^-8 relative)
+"""
+import torch
+import torch.nn.functional as F
+
+from mcgm_b200 import _lib, ops
+from mcgm_b200._lib import (EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_TANH, GATE_BN, GATE_MASK,
+                            GATE_RELU, GATE_UP2)
+from oracle import mcgan_oracle as O
+
+EXACT, F32_TOL, BF16_OUT = 0.0, 2e-5, 6e-3
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def nhwc(x):   # NCHW -> NHWC contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _codebook(M, C, seed):
+    torch.manual_seed(seed)
+    return O.make_codebook(M, C, 0.5)
+
+
+# ----------------------------------------------------------------------------- codebook / mask
+def check_codebook_and_mask():
+    rows = []
+    for (M, C, N, HW) in [(10, 256, 8, 16), (100, 128, 5, 4), (1623, 512, 6, 4), (7, 64, 3, 1)]:
+        cb = _codebook(M, C, 11 + M)
+        packed = ops.PackedCodebook(cb.to(DEV))
+        bits = packed.bits.cpu().numpy().view("uint32")
+        import numpy as np
+        want = np.zeros((M, (C + 31) // 32), dtype=np.uint32)
+        cbn = cb.numpy().astype(np.uint32)
+        for c in range(C):
+            want[:, c // 32] |= cbn[:, c] << np.uint32(c % 32)
+        rows.append((f"pack_codebook M={M} C={C}", float((bits != want).sum()), EXACT))
+        g = torch.Generator().manual_seed(M)
+        labels = torch.randint(0, M, (N,), generator=g)
+        ind = O.one_hot(labels, M)
+        side = int(HW ** 0.5)
+        x = torch.randn(N, C, side, side, generator=g) if HW > 1 else torch.randn(N, C, generator=g)
+        ref = O.mc_mask(x, ind, cb)
+        xd = x.to(DEV)
+        lab = labels.to(DEV).to(torch.int32)
+        # NCHW fp32 (the reference layout), label path and dense-code path
+        y = ops.mc_mask(xd, lab, packed, None, nchw=x.dim() > 2)
+        rows.append((f"mc_mask nchw f32 labels M={M} C={C}", float((y.cpu() != ref).sum()), EXACT))
+        code = ind.matmul(cb).to(DEV).contiguous()
+        y = ops.mc_mask(xd, None, None, code, nchw=x.dim() > 2)
+        rows.append((f"mc_mask nchw f32 code M={M} C={C}", float((y.cpu() != ref).sum()), EXACT))
+        if x.dim() > 2:
+            xb = nhwc(x).to(DEV).to(torch.bfloat16)
+            y = ops.mc_mask(xb, lab, packed, None, nchw=False)
+            refb = nhwc(O.mc_mask(nchw(xb.float().cpu()), ind, cb)).to(torch.bfloat16)
+            rows.append((f"mc_mask nhwc bf16 labels M={M} C={C}", float((y.cpu() != refb).sum()), EXACT))
+    return rows
+
+
+# ----------------------------------------------------------------------------- BN stats + gate
+def _gate_ref(x_nchw, gamma, beta, ind, cb, bn, relu, up, rm=None, rv=None):
+    h = x_nchw
+    if bn:
+        h = F.batch_norm(h, rm, rv, gamma, beta, True, 0.1, 1e-5)
+    if relu:
+        h = F.relu(h)
+    if up:
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    return O.mc_mask(h, ind, cb)
+
+
+def check_gate():
+    rows = []
+    cases = [(4, 8, 8, 256, 10, True, True, True), (3, 16, 16, 128, 10, True, True, False),
+             (2, 4, 4, 64, 5, False, True, False), (5, 8, 8, 512, 1623, True, True, True),
+             (2, 32, 32, 256, 10, True, True, False)]
+    for dtype in (torch.float32, torch.bfloat16):
+        for (N, H, W, C, M, bn, relu, up) in cases:
+            g = torch.Generator().manual_seed(N * 131 + C)
+            cb = _codebook(M, C, C + M)
+            labels = torch.randint(0, M, (N,), generator=g)
+            ind = O.one_hot(labels, M)
+            x = (torch.randn(N, C, H, W, generator=g) * 1.5 + 0.3).to(dtype).float()   # representable in dtype
+            gamma = (1 + 0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+            beta = (0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+            rm, rv = torch.zeros(C), torch.ones(C)
+            xr = x.clone().requires_grad_(True)
+            y_ref = _gate_ref(xr, gamma, beta, ind, cb, bn, relu, up, rm, rv)
+            raw_ref = O.mc_mask(xr, ind, cb)
+            up_f = 2 if up else 1
+            dy = torch.randn(N, C, H * up_f, W * up_f, generator=g).to(dtype).float()
+            draw = torch.randn(N, C, H, W, generator=g).to(dtype).float()
+            ((y_ref * dy).sum() + (raw_ref * draw).sum()).backward()
+
+            flags = (GATE_BN if bn else 0) | (GATE_RELU if relu else 0) | (GATE_UP2 if up else 0) | GATE_MASK
+            packed = ops.PackedCodebook(cb.to(DEV))
+            lab = labels.to(DEV).to(torch.int32)
+            xd = nhwc(x).to(DEV).to(dtype)
+            gd, bd = gamma.detach().to(DEV), beta.detach().to(DEV)
+            rmd, rvd = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+            mean = rstd = None
+            tag = f"{str(dtype)[6:]} N{N} {H}x{W} C{C} M{M} bn{int(bn)} up{int(up)}"
+            tol = F32_TOL if dtype == torch.float32 else BF16_OUT
+            if bn:
+                mean, rstd = ops.bn_stats(xd, rmd, rvd, 0.1, 1e-5)
+                rows.append((f"bn_stats mean {tag}", rel(mean, x.mean(dim=(0, 2, 3))), 1e-4))
+                rows.append((f"bn_stats rstd {tag}", rel(rstd, (x.var(dim=(0, 2, 3), unbiased=False) + 1e-5).rsqrt()), F32_TOL))
+                rows.append((f"bn running_mean {tag}", rel(rmd, rm), 1e-4))
+                rows.append((f"bn running_var {tag}", rel(rvd, rv), F32_TOL))
+            y, raw = ops.gate_fwd(xd, flags, lab, packed, mean, rstd, gd if bn else None, bd if bn else None, True)
+            rows.append((f"gate_fwd y {tag}", rel(nchw(y.float()), y_ref), tol))
+            rows.append((f"gate_fwd raw {tag}", float((nchw(raw.float()).cpu() != raw_ref.detach()).sum()), EXACT))
+            dx, dg, db = ops.gate_bwd(nhwc(dy).to(DEV).to(dtype), nhwc(draw).to(DEV).to(dtype), xd, flags, lab, packed,
+                                      mean, rstd, gd if bn else None, bd if bn else None)
+            rows.append((f"gate_bwd dx {tag}", rel(nchw(dx.float()), xr.grad), tol * (4 if bn else 1)))
+            if bn:
+                rows.append((f"gate_bwd dgamma {tag}", rel(dg, gamma.grad), 1e-4))
+                rows.append((f"gate_bwd dbeta {tag}", rel(db, beta.grad), 1e-4))
+    return rows
+
+
+def check_pool():
+    rows = []
+    g = torch.Generator().manual_seed(5)
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(3, 64, 8, 8, generator=g).to(dtype).float()
+        y = ops.pool2(nhwc(x).to(DEV).to(dtype), 0.25)
+        tol = F32_TOL if dtype == torch.float32 else BF16_OUT
+        rows.append((f"pool2 {dtype}", rel(nchw(y.float()), F.avg_pool2d(x, 2)), tol))
+        d = ops.unpool2(nhwc(x).to(DEV).to(dtype), 1.0)
+        rows.append((f"unpool2 {dtype}", rel(nchw(d.float()), F.interpolate(x, scale_factor=2, mode="nearest")), EXACT + 1e-12))
+    return rows
+
+
+# ----------------------------------------------------------------------------- tensor-core conv
+CONV_SHAPES = [  # N, H, W, Cin, Cout, R
+    (2, 32, 32, 64, 64, 3), (4, 8, 8, 128, 128, 3), (2, 16, 16, 256, 256, 3), (8, 4, 4, 64, 128, 1),
+    (3, 16, 16, 128, 256, 1), (2, 8, 8, 64, 3, 3), (1, 32, 32, 256, 128, 3), (5, 8, 8, 64, 64, 3),
+]
+
+
+def _conv_inputs(N, H, W, Cin, Cout, R, seed=0):
+    g = torch.Generator().manual_seed(seed + N * 7 + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(Cout, generator=g)
+    return g, x, w, b
+
+
+def check_conv_fwd(shapes=CONV_SHAPES):
+    rows = []
+    for (N, H, W, Cin, Cout, R) in shapes:
+        g, x, w, b = _conv_inputs(N, H, W, Cin, Cout, R)
+        ref = F.conv2d(x, w, b, padding=(R - 1) // 2)
+        xd = nhwc(x).to(DEV).to(torch.bfloat16)
+        wf, wflip = ops.pack_weight(w.to(DEV))
+        rows.append((f"pack_weight krsc {Cout}x{Cin}x{R}", float((wf.float().cpu() != w.permute(0, 2, 3, 1)).sum()), EXACT))
+        tag = f"N{N} {H}x{W} {Cin}->{Cout} k{R}"
+        y = ops.conv_fwd(xd, wf, torch.float32, b.to(DEV))
+        rows.append((f"conv_fwd f32 {tag}", rel(nchw(y), ref), F32_TOL))
+        y = ops.conv_fwd(xd, wf, torch.bfloat16, b.to(DEV))
+        rows.append((f"conv_fwd bf16 {tag}", rel(nchw(y.float()), ref), BF16_OUT))
+        if Cout % 64 == 0:
+            # dgrad == forward conv with the flipped / transposed weight
+            dy = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16).float()
+            xr = x.clone().requires_grad_(True)
+            F.conv2d(xr, w, None, padding=(R - 1) // 2).backward(dy)
+            dx = ops.conv_fwd(nhwc(dy).to(DEV).to(torch.bfloat16), wflip, torch.float32)
+            rows.append((f"conv dgrad f32 {tag}", rel(nchw(dx), xr.grad), F32_TOL))
+    return rows
+
+
+def check_conv_epilogues():
+    rows = []
+    N, H, W, Cin, Cout, R, M = 4, 8, 8, 64, 128, 3, 10
+    g, x, w, b = _conv_inputs(N, H, W, Cin, Cout, R, seed=3)
+    cb = _codebook(M, Cout, 77)
+    labels = torch.randint(0, M, (N,), generator=g)
+    ind = O.one_hot(labels, M)
+    packed = ops.PackedCodebook(cb.to(DEV))
+    lab = labels.to(DEV).to(torch.int32)
+    xd = nhwc(x).to(DEV).to(torch.bfloat16)
+    wf, _ = ops.pack_weight(w.to(DEV))
+    base = F.conv2d(x, w, b, padding=1)
+    res = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16).float()
+    res_lo = torch.randn(N, Cout, H // 2, W // 2, generator=g).to(torch.bfloat16).float()
+    aux = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16).float()
+    bd = b.to(DEV)
+    y = ops.conv_fwd(xd, wf, torch.float32, bd, nhwc(res).to(DEV).to(torch.bfloat16), None, None, None, EPI_RES)
+    rows.append(("conv epi +res", rel(nchw(y), base + res), F32_TOL))
+    y = ops.conv_fwd(xd, wf, torch.float32, bd, nhwc(res_lo).to(DEV).to(torch.bfloat16), None, None, None, EPI_RES_UP2)
+    rows.append(("conv epi +up2(res)", rel(nchw(y), base + F.interpolate(res_lo, scale_factor=2, mode="nearest")), F32_TOL))
+    y = ops.conv_fwd(xd, wf, torch.float32, bd, None, None, lab, packed, EPI_RELU | EPI_MASK)
+    rows.append(("conv epi relu*mask", rel(nchw(y), O.mc_mask(F.relu(base), ind, cb)), F32_TOL))
+    y = ops.conv_fwd(xd, wf, torch.float32, bd, None, nhwc(aux).to(DEV).to(torch.bfloat16), None, None, EPI_POSMASK)
+    rows.append(("conv epi posmask", rel(nchw(y), base * (aux > 0)), F32_TOL))
+    y = ops.conv_fwd(xd, wf, torch.float32, bd, None, None, None, None, EPI_TANH)
+    rows.append(("conv epi tanh", rel(nchw(y), torch.tanh(base)), F32_TOL))
+    return rows
+
+
+def check_conv_wgrad(shapes=CONV_SHAPES):
+    rows = []
+    for (N, H, W, Cin, Cout, R) in shapes:
+        if Cout % 64:
+            continue
+        g, x, w, b = _conv_inputs(N, H, W, Cin, Cout, R, seed=9)
+        dy = torch.randn(N, Cout, H, W, generator=g).to(torch.bfloat16).float()
+        wr = w.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        F.conv2d(x, wr, br, padding=(R - 1) // 2).backward(dy)
+        dw, db = ops.conv_wgrad(nhwc(x).to(DEV).to(torch.bfloat16), nhwc(dy).to(DEV).to(torch.bfloat16), R, R)
+        tag = f"N{N} {H}x{W} {Cin}->{Cout} k{R}"
+        rows.append((f"conv wgrad {tag}", rel(dw.permute(0, 3, 1, 2), wr.grad), F32_TOL))
+        rows.append((f"conv dbias {tag}", rel(db, br.grad), F32_TOL))
+    return rows
+
+
+# ----------------------------------------------------------------------------- thin convs
+def check_thin():
+    rows = []
+    for (N, H, W, Ct, Cw, R) in [(3, 8, 8, 3, 128, 3), (2, 32, 32, 3, 64, 3), (4, 16, 16, 3, 128, 1),
+                                 (2, 8, 8, 1, 64, 3), (2, 16, 16, 3, 256, 3)]:
+        g = torch.Generator().manual_seed(N + Cw)
+        M = 10
+        cb = _codebook(M, Cw, 5)
+        labels = torch.randint(0, M, (N,), generator=g)
+        ind = O.one_hot(labels, M)
+        packed = ops.PackedCodebook(cb.to(DEV))
+        lab = labels.to(DEV).to(torch.int32)
+        tag = f"N{N} {H}x{W} Ct{Ct} Cw{Cw} k{R}"
+        pad = (R - 1) // 2
+        # thin -> wide  (Conv2d(3, Cw))
+        img = torch.randn(N, Ct, H, W, generator=g)
+        w = torch.randn(Cw, Ct, R, R, generator=g) * 0.3
+        b = torch.randn(Cw, generator=g)
+        imr, wr = img.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        out_ref = O.mc_mask(F.relu(F.conv2d(imr, wr, b, padding=pad)), ind, cb)
+        dy = torch.randn(N, Cw, H, W, generator=g).to(torch.bfloat16).float()
+        out_ref.backward(dy)
+        imd = nhwc(img).to(DEV).requires_grad_(True)
+        wd = w.to(DEV).requires_grad_(True)
+        out = ops.WideFromThinFn.apply(imd, wd, b.to(DEV), (lab, packed), False)
+        rows.append((f"wide_from_thin fwd {tag}", rel(nchw(out.float()), out_ref), BF16_OUT))
+        out.backward(nhwc(dy).to(DEV).to(torch.bfloat16))
+        # the GPU masks dy with its own (bf16-rounded) output sign; identical except at exact zeros
+        rows.append((f"wide_from_thin dthin {tag}", rel(nchw(imd.grad), imr.grad), 2e-3))
+        rows.append((f"wide_from_thin dw {tag}", rel(wd.grad, wr.grad), 2e-3))
+        # wide -> thin  (Conv2d(Cw, 3) + tanh)
+        xw = torch.randn(N, Cw, H, W, generator=g).to(torch.bfloat16).float()
+        w2 = torch.randn(Ct, Cw, R, R, generator=g) / (Cw * R * R) ** 0.5
+        b2 = torch.randn(Ct, generator=g) * 0.1
+        xr, w2r, b2r = xw.clone().requires_grad_(True), w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+        o_ref = torch.tanh(F.conv2d(xr, w2r, b2r, padding=pad))
+        dth = torch.randn(N, Ct, H, W, generator=g)
+        o_ref.backward(dth)
+        xwd = nhwc(xw).to(DEV).to(torch.bfloat16).requires_grad_(True)
+        w2d, b2d = w2.to(DEV).requires_grad_(True), b2.to(DEV).requires_grad_(True)
+        o = ops.ThinFromWideFn.apply(xwd, w2d, b2d, True)
+        rows.append((f"thin_from_wide fwd {tag}", rel(nchw(o), o_ref), F32_TOL))
+        o.backward(nhwc(dth).to(DEV))
+        rows.append((f"thin_from_wide dwide {tag}", rel(nchw(xwd.grad.float()), xr.grad), BF16_OUT))
+        rows.append((f"thin_from_wide dw {tag}", rel(w2d.grad, w2r.grad), 1e-4))
+        rows.append((f"thin_from_wide db {tag}", rel(b2d.grad, b2r.grad), 1e-4))
+    return rows
+
+
+ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
+                     check_conv_wgrad, check_thin]
