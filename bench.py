@@ -1,0 +1,291 @@
+"""bench.py — MCGAN G+D training throughput (images/s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host cores
+
+A "step" is ONE reference training iteration (src/train_gan.py:139-176: 5 D updates + 1 G
+update, hinge loss, Adam) of the CIFAR10-shaped MCGAN (32x32x3, 10 modes, controller rate
+0.5, G widths 256x4, D widths 128x4, latent 128) at batch 512 per GPU, bf16 activations with
+fp32 accumulation, synthetic data, random-init weights (seed 0).  One JSON line is printed by
+rank 0.  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MCGAN G+D train imgs/s"
+WORKLOAD = "MCGAN CIFAR10-shaped 32x32x3, 10 modes, control 0.5, one iteration = 5 D + 1 G updates (train_gan.py:139-176)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference(batch, steps, warmup, threads=None):
+    """The reference algorithm (oracle port: same torch CPU ops as the reference modules) on the
+    host cores: `steps` iterations of 5D+1G at `batch` images.  Returns (img/s, cores, s/iter)."""
+    import torch
+    from mcgm_b200 import cfg, models, process_control
+    from oracle import mcgan_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg.update(device="cpu", data_name="CIFAR10", model_name="mcgan", control={"controller_rate": "0.5"})
+    process_control()
+    cfg["classes_size"] = 10
+    torch.manual_seed(0)
+    sd = O.make_trainable(models.mcgan().state_dict())
+    opt = O.make_adams(sd)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    label = torch.randint(0, 10, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        zs = [torch.randn(batch, 128, generator=g) for _ in range(6)]
+        t0 = time.perf_counter()
+        O.train_iteration(sd, opt, img, label, zs, 10, [2, 1, 1])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return batch / per, torch.get_num_threads(), per
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    value, cores, per = cpu_reference(args.ref_batch, steps, warmup)
+    sample = (f"{steps} iterations (5D+1G) at batch {args.ref_batch} after {warmup} warm-up, oracle port of the "
+              f"reference modules (torch CPU fp32 ops), {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": args.ref_batch, "parallelism": "cpu"},
+            "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if local == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from mcgm_b200 import _lib, cfg, models, ops, process_control, train_gan
+    _lib.load()
+
+    cfg.update(device=str(dev), data_name="CIFAR10", model_name="mcgan", control={"controller_rate": "0.5"})
+    process_control()
+    cfg["classes_size"] = 10
+    torch.manual_seed(0)                      # identical weights / codebooks / SN vectors on every rank
+    model = models.mcgan().to(dev)
+    model.train(True)
+    opt = train_gan.make_optimizers(model)
+    reducers = None
+    if world > 1:
+        reducers = {"generator": train_gan.GradAllReduce(model.generator),
+                    "discriminator": train_gan.GradAllReduce(model.discriminator)}
+    B = args.batch
+    g = torch.Generator().manual_seed(1 + rank)            # per-rank data shard
+    n_host = 4
+    host_img = [(torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).pin_memory() for _ in range(n_host)]
+    host_lab = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_img = [t.to(dev) for t in host_img]
+    dev_lab = [t.to(dev) for t in host_lab]
+    host_loss = torch.zeros(3, dtype=torch.float32).pin_memory()
+    torch.manual_seed(100 + rank)                          # z stream
+
+    def step_resident(i):
+        return train_gan.train_step(model, opt, {"img": dev_img[i % n_host], "label": dev_lab[i % n_host]},
+                                    reducers=reducers)
+
+    def step_e2e(i):
+        img = host_img[i % n_host].to(dev, non_blocking=True)
+        lab = host_lab[i % n_host].to(dev, non_blocking=True)
+        out = train_gan.train_step(model, opt, {"img": img, "label": lab}, reducers=reducers)
+        host_loss.copy_(torch.stack([out["loss"], out["loss_D"], out["loss_G"]]).float(), non_blocking=True)
+        return out
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) , _lib.launch_count - c0
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e(0)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    loss_host = [float(v) for v in host_loss]
+
+    # per-kernel roofline: one extra instrumented iteration (CUDA events around each native call)
+    roof = roof_gate = roof_wgrad = None
+    if not args.no_kernel_profile:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "_src": "fallback"}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks.update(json.load(f)); peaks["_src"] = "measured"
+        except Exception:
+            pass
+        ops.PROFILE = {}
+        step_resident(0)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+
+        def agg(tag):
+            recs = prof.get(tag, [])
+            t = sum(a.elapsed_time(b) for a, b, _ in recs) * 1e-3
+            return len(recs), t, sum(w for _, _, w in recs)
+        n, t, fl = agg("conv")
+        if n:
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"kernel": "conv_fwd_kernel (tcgen05 implicit GEMM; forward + dgrad launches)", "bound": "tensor",
+                    "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak,
+                    "traffic": None, "launches": n, "avg_us": t / n * 1e6, "share_of_step": t / (ms / args.steps * 1e-3),
+                    "peak_source": peaks["_src"] + " (cuBLAS bf16 sustained)"}
+        n, t, fl = agg("wgrad")
+        if n:
+            peak = peaks["bf16_tflops_sustained"]
+            roof_wgrad = {"kernel": "conv_wgrad_kernel (+split-K reduce, bias-grad)", "bound": "tensor",
+                          "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak,
+                          "launches": n, "avg_us": t / n * 1e6, "share_of_step": t / (ms / args.steps * 1e-3)}
+        n, t, by = agg("gate")
+        if n:
+            peak = peaks["hbm_gbs"]
+            roof_gate = {"kernel": "MC gate kernels (bn_partial, gate_fwd, gate_bwd_reduce/apply)", "bound": "hbm",
+                         "achieved": by / t / 1e9, "peak": peak, "unit": "GB/s", "frac": by / t / 1e9 / peak,
+                         "traffic": None, "launches": n, "avg_us": t / n * 1e6,
+                         "share_of_step": t / (ms / args.steps * 1e-3), "peak_source": peaks["_src"] + " (copy)"}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, per = cpu_reference(8, 2, 1)
+        cpu_base = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                    "sample": f"2 iterations (5D+1G) at batch 8 after 1 warm-up ({per:.2f} s/iteration), oracle port "
+                              f"of the reference modules (torch CPU fp32)"}
+
+    if rank == 0:
+        per = ms / args.steps
+        line = {"metric": METRIC, "value": B * world / (per * 1e-3), "unit": "img/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B,
+                           "parallelism": f"dp{world}", "schedule": "5D+1G per step",
+                           "l2": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
+                           "kernel_profile": "one extra iteration after the timed region, CUDA events per native call"},
+                "e2e": {"value": B * world / (ms_e2e / args.steps * 1e-3), "unit": "img/s",
+                        "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 + B * 8, "d2h_bytes_per_step": 12,
+                        "ms_per_step": ms_e2e / args.steps, "loss_D": loss_host[1], "loss_G": loss_host[2]},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_gate": roof_gate,
+                "roofline_wgrad": roof_wgrad, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

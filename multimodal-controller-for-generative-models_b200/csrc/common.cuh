@@ -75,6 +75,34 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
+// raw 16-byte load (keeps 4 registers until the values are needed) + conversion
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& r, float* v);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& r, float* v) {
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& r, float* v) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// pixel-index arithmetic: shifts when the extent is a power of two, else 32-bit division
+struct PixDiv {
+  uint32_t d;
+  int shift;   // >= 0: power of two
+  __host__ __device__ static PixDiv make(uint32_t d) {
+    PixDiv r; r.d = d; r.shift = -1;
+    for (int s = 0; s < 31; ++s) if ((1u << s) == d) r.shift = s;
+    return r;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return shift >= 0 ? (x >> shift) : (x / d); }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -626,7 +626,7 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int R, int S, Wgra
   const int tiles = pl->cout_tiles * pl->cin_tiles * pl->taps;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int splits = (sms + tiles - 1) / tiles;          // about one wave
+  int splits = sms / tiles;                        // at most one wave of CTAs
   if (splits > pl->total_kb) splits = pl->total_kb;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
@@ -701,8 +701,9 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   if (Cout % 256 == 0) BN = 256;
   else if (Cout % 128 == 0) BN = 128;
   else if (Cout % 64 == 0) BN = 64;
+  else if (Cout == 32) BN = 32;
   else if (Cout <= 16) BN = 16;
-  else return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d unsupported (multiple of 64, or <= 16)", Cout);
+  else return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d unsupported (multiple of 64, 32, or <= 16)", Cout);
   p.n_tiles = (Cout + BN - 1) / BN;
   p.total_tiles = p.tiles_w * p.tiles_h * tiles_nb * p.n_tiles;
   p.kpt = Cin / kBlockK;
@@ -729,6 +730,7 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
     case 256: return f32 ? launch_fwd<256, float>(mx, mw, p, st) : launch_fwd<256, __nv_bfloat16>(mx, mw, p, st);
     case 128: return f32 ? launch_fwd<128, float>(mx, mw, p, st) : launch_fwd<128, __nv_bfloat16>(mx, mw, p, st);
     case 64: return f32 ? launch_fwd<64, float>(mx, mw, p, st) : launch_fwd<64, __nv_bfloat16>(mx, mw, p, st);
+    case 32: return f32 ? launch_fwd<32, float>(mx, mw, p, st) : launch_fwd<32, __nv_bfloat16>(mx, mw, p, st);
     default: return f32 ? launch_fwd<16, float>(mx, mw, p, st) : launch_fwd<16, __nv_bfloat16>(mx, mw, p, st);
   }
 }

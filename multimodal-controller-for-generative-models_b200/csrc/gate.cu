@@ -161,21 +161,34 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
 }
 
 // ---------------------------------------------------------------------------
-// fused gate forward
+// fused gate kernels.
+//
+// Work decomposition: a TILE is TP = PL*U consecutive pixels (PL pixel lanes of the
+// block x U pixels per thread); a warp always touches whole contiguous pixel rows.
+// All U 16-byte loads of a thread are issued back to back as raw uint4 (4 registers
+// each) before any arithmetic, so one block keeps PL*U*C*elt bytes in flight.  When
+// H*W is a multiple of TP the sample index — hence the codebook row — is uniform per
+// tile and looked up once; index arithmetic is 32-bit with shifts for power-of-two
+// extents.
 // ---------------------------------------------------------------------------
+struct GateGeom {
+  int N, H, W, C;
+  uint32_t P;        // N*H*W
+  PixDiv hw, w;      // dividers by H*W and by W
+  int uniform_n;     // H*W % TP == 0
+};
+
 template <typename T, bool UP2>
-__global__ void __launch_bounds__(kGateThreads)
-gate_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ y_raw,
-                int N, int H, int W, int C,
+__global__ void __launch_bounds__(kGateThreads, 2)
+gate_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ y_raw, const GateGeom g,
                 const int32_t* __restrict__ labels, const uint32_t* __restrict__ bits, int words,
                 const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int flags) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = UP2 ? 2 : 4;
-  const int CG = C / V;
+  constexpr int U = UP2 ? 4 : 8;
+  const int C = g.C, CG = C / V;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, PL = blockDim.x / CG;
-  const int HW = H * W;
-  const long P = (long)N * HW;
+  const uint32_t TP = PL * U, HW = (uint32_t)g.H * g.W;
   const bool relu = flags & MCGM_GATE_RELU, use_mask = flags & MCGM_GATE_MASK;
   float a[V], b[V];
 #pragma unroll
@@ -188,44 +201,48 @@ gate_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ y_ra
       a[i] = 1.0f; b[i] = 0.0f;
     }
   }
-  const long stride = (long)gridDim.x * PL;
-  for (long p0 = (long)blockIdx.x * PL + pl; p0 < P; p0 += U * stride) {
-    Vec<T> v[U];
-    uint32_t m[U];
+  const uint32_t tiles = (g.P + TP - 1) / TP;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t base = tile * TP + pl;
+    uint4 raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long p = p0 + u * stride;
-      if (p < P) {
-        v[u].load(x + p * C + cg * V);
-        m[u] = use_mask ? mask_bits(bits, words, __ldg(labels + (int)(p / HW)), cg * V, V) : 0xffffffffu;
-      }
+      const uint32_t p = base + u * PL;
+      if (p < g.P) raw[u] = ldg16(x + (size_t)p * C + cg * V);
     }
+    uint32_t m_tile = 0xffffffffu;
+    if (use_mask && g.uniform_n) m_tile = mask_bits(bits, words, __ldg(labels + g.hw.div(tile * TP)), cg * V, V);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long p = p0 + u * stride;
-      if (p >= P) continue;
+      const uint32_t p = base + u * PL;
+      if (p >= g.P) continue;
+      const uint32_t n = g.hw.div(p);
+      uint32_t m = m_tile;
+      if (use_mask && !g.uniform_n) m = mask_bits(bits, words, __ldg(labels + n), cg * V, V);
+      float v[V];
+      unpack16<T>(raw[u], v);
       if (y_raw) {
         Vec<T> r;
 #pragma unroll
-        for (int i = 0; i < V; ++i) r.v[i] = ((m[u] >> i) & 1u) ? v[u].v[i] : 0.0f;
-        r.store(y_raw + p * C + cg * V);
+        for (int i = 0; i < V; ++i) r.v[i] = ((m >> i) & 1u) ? v[i] : 0.0f;
+        r.store(y_raw + (size_t)p * C + cg * V);
       }
       Vec<T> o;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float z = fmaf(a[i], v[u].v[i], b[i]);
+        float z = fmaf(a[i], v[i], b[i]);
         if (relu) z = fmaxf(z, 0.0f);
-        o.v[i] = ((m[u] >> i) & 1u) ? z : 0.0f;
+        o.v[i] = ((m >> i) & 1u) ? z : 0.0f;
       }
       if (UP2) {
-        const int n = (int)(p / HW), hw = (int)(p % HW), h = hw / W, w = hw % W;
-        T* base = y + (((long)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cg * V;
-        o.store(base);
-        o.store(base + C);
-        o.store(base + (long)2 * W * C);
-        o.store(base + (long)2 * W * C + C);
+        const uint32_t hw = p - n * HW, h = g.w.div(hw), w = hw - h * g.W;
+        T* o0 = y + (((size_t)n * 2 * g.H + 2 * h) * 2 * g.W + 2 * w) * C + cg * V;
+        o.store(o0);
+        o.store(o0 + C);
+        o.store(o0 + (size_t)2 * g.W * C);
+        o.store(o0 + (size_t)2 * g.W * C + C);
       } else {
-        o.store(y + p * C + cg * V);
+        o.store(y + (size_t)p * C + cg * V);
       }
     }
   }
@@ -239,35 +256,47 @@ gate_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ y_ra
 //   dx += mask * d_raw   (gradient of the raw-gated second output)
 // ---------------------------------------------------------------------------
 template <typename T, bool UP2>
-__device__ __forceinline__ void load_dy(Vec<T>& g, const T* __restrict__ dy, long p, int HW, int H, int W,
-                                        int C, int coff) {
-  if (UP2) {
-    const int n = (int)(p / HW), hw = (int)(p % HW), h = hw / W, w = hw % W;
-    const T* base = dy + (((long)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + coff;
-    Vec<T> t0, t1, t2, t3;
-    t0.load(base);
-    t1.load(base + C);
-    t2.load(base + (long)2 * W * C);
-    t3.load(base + (long)2 * W * C + C);
-#pragma unroll
-    for (int i = 0; i < Vec<T>::N; ++i) g.v[i] = (t0.v[i] + t1.v[i]) + (t2.v[i] + t3.v[i]);
-  } else {
-    g.load(dy + p * C + coff);
+struct DyRaw {
+  uint4 r[UP2 ? 4 : 1];
+  __device__ __forceinline__ void load(const T* __restrict__ dy, const GateGeom& g, uint32_t p, uint32_t n, int coff) {
+    if (UP2) {
+      const uint32_t HW = (uint32_t)g.H * g.W;
+      const uint32_t hw = p - n * HW, h = g.w.div(hw), w = hw - h * g.W;
+      const T* b0 = dy + (((size_t)n * 2 * g.H + 2 * h) * 2 * g.W + 2 * w) * g.C + coff;
+      r[0] = ldg16(b0);
+      r[UP2 ? 1 : 0] = ldg16(b0 + g.C);
+      r[UP2 ? 2 : 0] = ldg16(b0 + (size_t)2 * g.W * g.C);
+      r[UP2 ? 3 : 0] = ldg16(b0 + (size_t)2 * g.W * g.C + g.C);
+    } else {
+      r[0] = ldg16(dy + (size_t)p * g.C + coff);
+    }
   }
-}
+  __device__ __forceinline__ void get(float* v) const {
+    constexpr int V = Vec<T>::N;
+    unpack16<T>(r[0], v);
+    if (UP2) {
+      float t1[V], t2[V], t3[V];
+      unpack16<T>(r[UP2 ? 1 : 0], t1);
+      unpack16<T>(r[UP2 ? 2 : 0], t2);
+      unpack16<T>(r[UP2 ? 3 : 0], t3);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (v[i] + t1[i]) + (t2[i] + t3[i]);
+    }
+  }
+};
 
 template <typename T, bool UP2>
-__global__ void __launch_bounds__(kGateThreads)
-gate_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, int N, int H, int W, int C,
+__global__ void __launch_bounds__(kGateThreads, 2)
+gate_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const GateGeom g,
                        const int32_t* __restrict__ labels, const uint32_t* __restrict__ bits, int words,
                        const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int flags,
                        float* __restrict__ partial) {
   constexpr int V = Vec<T>::N;
-  const int CG = C / V;
+  constexpr int U = UP2 ? 2 : 4;
+  const int C = g.C, CG = C / V;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, PL = blockDim.x / CG;
-  const int HW = H * W;
-  const long P = (long)N * HW;
+  const uint32_t TP = PL * U;
   const bool relu = flags & MCGM_GATE_RELU, use_mask = flags & MCGM_GATE_MASK;
   float a[V], b[V], mu[V], rs[V], s1[V], s2[V];
 #pragma unroll
@@ -278,19 +307,38 @@ gate_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, int N,
     b[i] = fmaf(-mu[i], a[i], beta[c]);
     s1[i] = s2[i] = 0.0f;
   }
-  const long stride = (long)gridDim.x * PL;
-  for (long p = (long)blockIdx.x * PL + pl; p < P; p += stride) {
-    Vec<T> xv, g;
-    xv.load(x + p * C + cg * V);
-    load_dy<T, UP2>(g, dy, p, HW, H, W, C, cg * V);
-    const uint32_t m = use_mask ? mask_bits(bits, words, __ldg(labels + (int)(p / HW)), cg * V, V) : 0xffffffffu;
+  const uint32_t tiles = (g.P + TP - 1) / TP;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t base = tile * TP + pl;
+    uint4 xr[U];
+    DyRaw<T, UP2> dr[U];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float z = fmaf(a[i], xv.v[i], b[i]);
-      float gi = ((m >> i) & 1u) ? g.v[i] : 0.0f;
-      if (relu && !(z > 0.0f)) gi = 0.0f;
-      s1[i] += gi;
-      s2[i] = fmaf(gi, (xv.v[i] - mu[i]) * rs[i], s2[i]);
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = base + u * PL;
+      if (p < g.P) {
+        xr[u] = ldg16(x + (size_t)p * C + cg * V);
+        dr[u].load(dy, g, p, g.hw.div(p), cg * V);
+      }
+    }
+    uint32_t m_tile = 0xffffffffu;
+    if (use_mask && g.uniform_n) m_tile = mask_bits(bits, words, __ldg(labels + g.hw.div(tile * TP)), cg * V, V);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = base + u * PL;
+      if (p >= g.P) continue;
+      uint32_t m = m_tile;
+      if (use_mask && !g.uniform_n) m = mask_bits(bits, words, __ldg(labels + g.hw.div(p)), cg * V, V);
+      float xv[V], gv[V];
+      unpack16<T>(xr[u], xv);
+      dr[u].get(gv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float z = fmaf(a[i], xv[i], b[i]);
+        float gi = ((m >> i) & 1u) ? gv[i] : 0.0f;
+        if (relu && !(z > 0.0f)) gi = 0.0f;
+        s1[i] += gi;
+        s2[i] = fmaf(gi, (xv[i] - mu[i]) * rs[i], s2[i]);
+      }
     }
   }
   extern __shared__ float sm[];  // [2][PL][C]
@@ -328,57 +376,79 @@ __global__ void gate_bwd_finalize_kernel(const float* __restrict__ partial, int 
 }
 
 template <typename T, bool UP2>
-__global__ void __launch_bounds__(kGateThreads)
+__global__ void __launch_bounds__(kGateThreads, 2)
 gate_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ d_raw, const T* __restrict__ x,
-                      T* __restrict__ dx, int N, int H, int W, int C,
+                      T* __restrict__ dx, const GateGeom g,
                       const int32_t* __restrict__ labels, const uint32_t* __restrict__ bits, int words,
                       const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ dgamma, const float* __restrict__ dbeta, int flags) {
   constexpr int V = Vec<T>::N;
-  const int CG = C / V;
+  constexpr int U = UP2 ? 2 : 4;
+  const int C = g.C, CG = C / V;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, PL = blockDim.x / CG;
-  const int HW = H * W;
-  const long P = (long)N * HW;
+  const uint32_t TP = PL * U;
   const bool bn = flags & MCGM_GATE_BN, relu = flags & MCGM_GATE_RELU, use_mask = flags & MCGM_GATE_MASK;
-  const float invP = 1.0f / (float)P;
-  float a[V], b[V], mu[V], rs[V], k1[V], k2[V];
+  const float invP = 1.0f / (float)g.P;
+  // dx = a*(g - dbeta/P - xhat*dgamma/P) = a*g + c0 + c1*x   (xhat = (x-mu)*rs), z = a*x + b
+  float a[V], b[V], c0[V], c1[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = cg * V + i;
     if (bn) {
-      mu[i] = mean[c]; rs[i] = rstd[c];
-      a[i] = gamma[c] * rs[i];
-      b[i] = fmaf(-mu[i], a[i], beta[c]);
-      k1[i] = dbeta[c] * invP;
-      k2[i] = dgamma[c] * invP;
+      const float mu = mean[c], rs = rstd[c];
+      a[i] = gamma[c] * rs;
+      b[i] = fmaf(-mu, a[i], beta[c]);
+      c1[i] = -a[i] * rs * (dgamma[c] * invP);
+      c0[i] = -a[i] * (dbeta[c] * invP) - c1[i] * mu;
     } else {
-      mu[i] = 0.f; rs[i] = 1.f; a[i] = 1.f; b[i] = 0.f; k1[i] = k2[i] = 0.f;
+      a[i] = 1.f; b[i] = 0.f; c0[i] = c1[i] = 0.f;
     }
   }
-  const long stride = (long)gridDim.x * PL;
-  for (long p = (long)blockIdx.x * PL + pl; p < P; p += stride) {
-    Vec<T> xv, g, r, o;
-    xv.load(x + p * C + cg * V);
-    if (dy) {
-      load_dy<T, UP2>(g, dy, p, HW, H, W, C, cg * V);
-    } else {
+  const uint32_t tiles = (g.P + TP - 1) / TP;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t base = tile * TP + pl;
+    uint4 xr[U], rr[U];
+    DyRaw<T, UP2> dr[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) g.v[i] = 0.0f;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = base + u * PL;
+      if (p < g.P) {
+        xr[u] = ldg16(x + (size_t)p * C + cg * V);
+        if (dy) dr[u].load(dy, g, p, g.hw.div(p), cg * V);
+        if (d_raw) rr[u] = ldg16(d_raw + (size_t)p * C + cg * V);
+      }
     }
-    if (d_raw) r.load(d_raw + p * C + cg * V);
-    const uint32_t m = use_mask ? mask_bits(bits, words, __ldg(labels + (int)(p / HW)), cg * V, V) : 0xffffffffu;
+    uint32_t m_tile = 0xffffffffu;
+    if (use_mask && g.uniform_n) m_tile = mask_bits(bits, words, __ldg(labels + g.hw.div(tile * TP)), cg * V, V);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float z = fmaf(a[i], xv.v[i], b[i]);
-      const bool on = (m >> i) & 1u;
-      float gi = on ? g.v[i] : 0.0f;
-      if (relu && !(z > 0.0f)) gi = 0.0f;
-      float d = bn ? a[i] * (gi - k1[i] - (xv.v[i] - mu[i]) * rs[i] * k2[i]) : gi;
-      if (d_raw && on) d += r.v[i];
-      o.v[i] = d;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = base + u * PL;
+      if (p >= g.P) continue;
+      uint32_t m = m_tile;
+      if (use_mask && !g.uniform_n) m = mask_bits(bits, words, __ldg(labels + g.hw.div(p)), cg * V, V);
+      float xv[V], gv[V], rv[V];
+      unpack16<T>(xr[u], xv);
+      if (dy) {
+        dr[u].get(gv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) gv[i] = 0.0f;
+      }
+      if (d_raw) unpack16<T>(rr[u], rv);
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float z = fmaf(a[i], xv[i], b[i]);
+        const bool on = (m >> i) & 1u;
+        float gi = on ? gv[i] : 0.0f;
+        if (relu && !(z > 0.0f)) gi = 0.0f;
+        float d = bn ? fmaf(a[i], gi, fmaf(c1[i], xv[i], c0[i])) : gi;
+        if (d_raw && on) d += rv[i];
+        o.v[i] = d;
+      }
+      o.store(dx + (size_t)p * C + cg * V);
     }
-    o.store(dx + p * C + cg * V);
   }
 }
 
@@ -521,18 +591,29 @@ extern "C" int mcgm_bn_stats(const void* x, int dtype, long P_total, int C, floa
   return 0;
 }
 
+static GateGeom make_geom(int N, int H, int W, int C, int TP) {
+  GateGeom g;
+  g.N = N; g.H = H; g.W = W; g.C = C;
+  g.P = (uint32_t)((long)N * H * W);
+  g.hw = PixDiv::make((uint32_t)(H * W));
+  g.w = PixDiv::make((uint32_t)W);
+  g.uniform_n = ((H * W) % TP) == 0;
+  return g;
+}
+
 template <typename T>
 static int gate_fwd_t(const void* x, void* y, void* y_raw, int N, int H, int W, int C, int CG,
                       const int32_t* labels, const uint32_t* bits, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, int flags, cudaStream_t st) {
   const int PL = kGateThreads / CG, words = (C + 31) / 32;
-  const long P = (long)N * H * W;
   const bool up = flags & MCGM_GATE_UP2;
-  const int grid = gate_grid((P + (up ? 1 : 3)) / (up ? 2 : 4), PL, 148 * 8);
+  const int TP = PL * (up ? 4 : 8);
+  const GateGeom g = make_geom(N, H, W, C, TP);
+  const int grid = gate_grid(g.P, TP, 148 * 8);
   if (up)
-    gate_fwd_kernel<T, true><<<grid, kGateThreads, 0, st>>>((const T*)x, (T*)y, (T*)y_raw, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, flags);
+    gate_fwd_kernel<T, true><<<grid, kGateThreads, 0, st>>>((const T*)x, (T*)y, (T*)y_raw, g, labels, bits, words, mean, rstd, gamma, beta, flags);
   else
-    gate_fwd_kernel<T, false><<<grid, kGateThreads, 0, st>>>((const T*)x, (T*)y, (T*)y_raw, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, flags);
+    gate_fwd_kernel<T, false><<<grid, kGateThreads, 0, st>>>((const T*)x, (T*)y, (T*)y_raw, g, labels, bits, words, mean, rstd, gamma, beta, flags);
   MCGM_LAUNCH_CHECK();
   return 0;
 }
@@ -542,6 +623,7 @@ extern "C" int mcgm_gate_fwd(const void* x, void* y, void* y_raw, int dtype, int
                              const float* rstd, const float* gamma, const float* beta, int flags,
                              void* stream) {
   MCGM_CHECK_ARG(x && y && N >= 0 && H > 0 && W > 0, "gate_fwd: bad arguments");
+  MCGM_CHECK_ARG((long)N * H * W < (1L << 31), "gate_fwd: more than 2^31 pixels");
   if (flags & MCGM_GATE_MASK) MCGM_CHECK_ARG(labels && bits && M > 0, "gate_fwd: MASK needs labels and bits");
   if (flags & MCGM_GATE_BN) MCGM_CHECK_ARG(mean && rstd && gamma && beta, "gate_fwd: BN needs mean/rstd/gamma/beta");
   if (N == 0) return 0;
@@ -563,25 +645,26 @@ static int gate_bwd_t(const void* dy, const void* d_raw, const void* x, void* dx
                       const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
                       int flags, void* workspace, cudaStream_t st) {
   const int PL = kGateThreads / CG, words = (C + 31) / 32;
-  const long P = (long)N * H * W;
   const bool up = flags & MCGM_GATE_UP2;
+  const int TP = PL * (up ? 2 : 4);
+  const GateGeom g = make_geom(N, H, W, C, TP);
   if (flags & MCGM_GATE_BN) {
-    const int grid = gate_grid(P, PL, kMaxPartialBlocks);
+    const int grid = gate_grid(g.P, TP, kMaxPartialBlocks);
     const size_t smem = (size_t)2 * PL * C * sizeof(float);
     float* partial = (float*)workspace;
     if (up)
-      gate_bwd_reduce_kernel<T, true><<<grid, kGateThreads, smem, st>>>((const T*)dy, (const T*)x, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, flags, partial);
+      gate_bwd_reduce_kernel<T, true><<<grid, kGateThreads, smem, st>>>((const T*)dy, (const T*)x, g, labels, bits, words, mean, rstd, gamma, beta, flags, partial);
     else
-      gate_bwd_reduce_kernel<T, false><<<grid, kGateThreads, smem, st>>>((const T*)dy, (const T*)x, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, flags, partial);
+      gate_bwd_reduce_kernel<T, false><<<grid, kGateThreads, smem, st>>>((const T*)dy, (const T*)x, g, labels, bits, words, mean, rstd, gamma, beta, flags, partial);
     MCGM_LAUNCH_CHECK();
     gate_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(partial, grid, C, dgamma, dbeta);
     MCGM_LAUNCH_CHECK();
   }
-  const int grid = gate_grid(P, PL, 148 * 8);
+  const int grid = gate_grid(g.P, TP, 148 * 8);
   if (up)
-    gate_bwd_apply_kernel<T, true><<<grid, kGateThreads, 0, st>>>((const T*)dy, (const T*)d_raw, (const T*)x, (T*)dx, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, dgamma, dbeta, flags);
+    gate_bwd_apply_kernel<T, true><<<grid, kGateThreads, 0, st>>>((const T*)dy, (const T*)d_raw, (const T*)x, (T*)dx, g, labels, bits, words, mean, rstd, gamma, beta, dgamma, dbeta, flags);
   else
-    gate_bwd_apply_kernel<T, false><<<grid, kGateThreads, 0, st>>>((const T*)dy, (const T*)d_raw, (const T*)x, (T*)dx, N, H, W, C, labels, bits, words, mean, rstd, gamma, beta, dgamma, dbeta, flags);
+    gate_bwd_apply_kernel<T, false><<<grid, kGateThreads, 0, st>>>((const T*)dy, (const T*)d_raw, (const T*)x, (T*)dx, g, labels, bits, words, mean, rstd, gamma, beta, dgamma, dbeta, flags);
   MCGM_LAUNCH_CHECK();
   return 0;
 }
@@ -591,6 +674,7 @@ extern "C" int mcgm_gate_bwd(const void* dy, const void* d_raw, const void* x, v
                              const float* mean, const float* rstd, const float* gamma, const float* beta,
                              float* dgamma, float* dbeta, int flags, void* workspace, void* stream) {
   MCGM_CHECK_ARG((dy || d_raw) && x && dx && N >= 0 && H > 0 && W > 0, "gate_bwd: bad arguments");
+  MCGM_CHECK_ARG((long)N * H * W < (1L << 31), "gate_bwd: more than 2^31 pixels");
   if (flags & MCGM_GATE_MASK) MCGM_CHECK_ARG(labels && bits && M > 0, "gate_bwd: MASK needs labels and bits");
   if (flags & MCGM_GATE_BN)
     MCGM_CHECK_ARG(dy && mean && rstd && gamma && beta && dgamma && dbeta && workspace,

@@ -208,6 +208,65 @@ __global__ void kern_grad_finalize_kernel(const float* __restrict__ partial, int
   dkern[i] = (float)a;
 }
 
+// ---------------------------------------------------------------------------
+// im2col / col2im of the THIN tensor.  With them every thin convolution becomes a
+// 1x1 GEMM on the tensor cores that touches the wide tensor exactly once:
+//   U[p, t*Ct + j] = thin[p + sgn*off(t), j]          (bf16, KU = 64 columns, zero padded)
+//   wide_from_thin : wide = U x Wmat^T            (conv_fwd 1x1, Cin = 64)
+//   kernel grads   : dWmat = dY^T x U             (conv_wgrad 1x1)
+//   thin_from_wide : T = wide x Wmat^T (fp32 [P, CT]);  thin[p, j] = sum_t T[p + off(t), t*Ct + j]
+// ---------------------------------------------------------------------------
+__global__ void thin_im2col_kernel(const float* __restrict__ thin, __nv_bfloat16* __restrict__ U, int N, int H,
+                                   int W, int Ct, int R, int S, int sgn, int KU) {
+  const int pad = (R - 1) / 2, T = R * S;
+  const int groups = KU / 8;
+  const long total = (long)N * H * W * groups;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(e % groups);
+    const long p = e / groups;
+    const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
+    Vec<__nv_bfloat16> o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = gidx * 8 + i;
+      float v = 0.0f;
+      if (col < T * Ct) {
+        const int t = col / Ct, j = col - t * Ct;
+        const int r = t / S, s = t - r * S;
+        const int hh = h + sgn * (r - pad), ww = w + sgn * (s - pad);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(thin + (((long)n * H + hh) * W + ww) * Ct + j);
+      }
+      o.v[i] = v;
+    }
+    o.store(U + p * KU + gidx * 8);
+  }
+}
+
+__global__ void thin_col2im_kernel(const float* __restrict__ Tm, int CT, float* __restrict__ thin, int N, int H,
+                                   int W, int Ct, int R, int S, const float* __restrict__ bias, int flags) {
+  const int pad = (R - 1) / 2;
+  const long total = (long)N * H * W;
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+    const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
+    float acc[kMaxCt];
+#pragma unroll
+    for (int j = 0; j < kMaxCt; ++j) acc[j] = (j < Ct && (flags & MCGM_EPI_BIAS)) ? __ldg(bias + j) : 0.0f;
+    for (int r = 0; r < R; ++r) {
+      const int hh = h + r - pad;
+      if (hh < 0 || hh >= H) continue;
+      for (int s = 0; s < S; ++s) {
+        const int ww = w + s - pad;
+        if (ww < 0 || ww >= W) continue;
+        const float* tp = Tm + (((long)n * H + hh) * W + ww) * CT + (r * S + s) * Ct;
+#pragma unroll
+        for (int j = 0; j < kMaxCt; ++j)
+          if (j < Ct) acc[j] += __ldg(tp + j);
+      }
+    }
+    for (int j = 0; j < Ct; ++j) thin[p * Ct + j] = (flags & MCGM_EPI_TANH) ? tanhf(acc[j]) : acc[j];
+  }
+}
+
 static constexpr int kKernGradBlocks = 148 * 2;
 
 }  // namespace mcgm
@@ -295,6 +354,32 @@ extern "C" int mcgm_thin_kern_grad(const float* thin, const void* wide, float* d
   MCGM_LAUNCH_CHECK();
   const int total = R * S * Ct * Cw;
   kern_grad_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, (int)blocks, total, dkern);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, int W, int Ct, int R, int S,
+                                int flip, int KU, void* stream) {
+  MCGM_CHECK_ARG(thin && U_bf16 && N > 0 && H > 0 && W > 0, "thin_im2col: bad arguments");
+  MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && KU % 8 == 0 && R * S * Ct <= KU, "thin_im2col: Ct=%d R=%d S=%d do not fit KU=%d", Ct, R, S, KU);
+  const long total = (long)N * H * W * (KU / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  thin_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(thin, (__nv_bfloat16*)U_bf16, N, H, W, Ct, R, S,
+                                                                   flip ? -1 : 1, KU);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, int Ct, int R, int S,
+                                const float* bias, int flags, void* stream) {
+  MCGM_CHECK_ARG(T && thin && N > 0 && H > 0 && W > 0, "thin_col2im: bad arguments");
+  MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && R * S * Ct <= CT, "thin_col2im: Ct=%d R=%d S=%d do not fit CT=%d", Ct, R, S, CT);
+  if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "thin_col2im: BIAS without bias");
+  const long total = (long)N * H * W;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  thin_col2im_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(T, CT, thin, N, H, W, Ct, R, S, bias, flags);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

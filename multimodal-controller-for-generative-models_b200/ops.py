@@ -40,6 +40,28 @@ def _check_cuda(*tensors):
             raise ValueError("Not valid layout: tensor must be contiguous")
 
 
+# Optional per-kernel timing (bench.py): PROFILE = {} enables CUDA-event pairs around the
+# tagged native calls; each record is (tag, start_event, end_event, work) with work in
+# algorithmic bytes (HBM-bound kernels) or flops (tensor-core kernels).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(ev, tag, work):
+    if ev is None:
+        return
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    PROFILE.setdefault(tag, []).append((ev, end, work))
+
+
 _workspaces = {}
 
 
@@ -106,8 +128,11 @@ def bn_stats(x, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
     mean = torch.empty(C, dtype=torch.float32, device=x.device)
     rstd = torch.empty(C, dtype=torch.float32, device=x.device)
     ws = _workspace("bn", _lib.query("mcgm_bn_stats_workspace_bytes", C), x.device)
+    ev = _prof_begin()
     _lib.call("mcgm_bn_stats", x.data_ptr(), _dtype_code(x), P, C, mean.data_ptr(), rstd.data_ptr(),
               _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), ws.data_ptr(), _stream())
+    _lib.launch_count += 1                       # partial + finalize kernels
+    _prof_end(ev, "gate", x.numel() * x.element_size())
     return mean, rstd
 
 
@@ -117,9 +142,11 @@ def gate_fwd(x, flags, labels=None, packed=None, mean=None, rstd=None, gamma=Non
     up = 2 if flags & GATE_UP2 else 1
     y = torch.empty(N, H * up, W * up, C, dtype=x.dtype, device=x.device)
     y_raw = torch.empty_like(x) if want_raw else None
+    ev = _prof_begin()
     _lib.call("mcgm_gate_fwd", x.data_ptr(), y.data_ptr(), _ptr(y_raw), _dtype_code(x), N, H, W, C,
               _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
               _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), flags, _stream())
+    _prof_end(ev, "gate", (x.numel() + y.numel() + (x.numel() if want_raw else 0)) * x.element_size())
     return y, y_raw
 
 
@@ -133,10 +160,17 @@ def gate_bwd(dy, d_raw, x, flags, labels=None, packed=None, mean=None, rstd=None
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = _workspace("gate_bwd", _lib.query("mcgm_gate_bwd_workspace_bytes", C), x.device)
+    ev = _prof_begin()
     _lib.call("mcgm_gate_bwd", _ptr(dy), _ptr(d_raw), x.data_ptr(), dx.data_ptr(), _dtype_code(x), N, H, W, C,
               _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
               _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(dgamma), _ptr(dbeta), flags,
               _ptr(ws), _stream())
+    if flags & GATE_BN:
+        _lib.launch_count += 2
+    passes = 2 if flags & GATE_BN else 1          # BN: reduce pass + apply pass both read dy and x
+    nbytes = passes * ((dy.numel() if dy is not None else 0) + x.numel()) + x.numel()
+    nbytes += d_raw.numel() if d_raw is not None else 0
+    _prof_end(ev, "gate", nbytes * x.element_size())
     return dx, dgamma, dbeta
 
 
@@ -165,10 +199,12 @@ def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None,
     out = torch.empty(N, H, W, Cout, dtype=out_dtype, device=x.device)
     if bias is not None:
         flags |= EPI_BIAS
+    ev = _prof_begin()
     _lib.call("mcgm_conv_fwd", x.data_ptr(), w_krsc.data_ptr(), out.data_ptr(),
               F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, R, S,
               _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
               packed.M if packed else 0, flags, _stream())
+    _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * R * S)
     return out
 
 
@@ -183,8 +219,11 @@ def conv_wgrad(x, dy, R, S, want_bias=True):
     ws = _workspace("wgrad", nbytes, x.device)
     dw = torch.empty(Cout, R, S, Cin, dtype=torch.float32, device=x.device)
     db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    ev = _prof_begin()
     _lib.call("mcgm_conv_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, R, S,
               ws.data_ptr(), _stream())
+    _lib.launch_count += 3 if want_bias else 1
+    _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S)
     return dw, db
 
 
@@ -342,50 +381,98 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, db, dres, None, None, None, None, None
 
 
+def thin_im2col(thin, R, S, flip=False, KU=64):
+    """U[p, t*Ct + j] = thin[p +/- off(t), j] as bf16 [N,H,W,KU] (zero padded)."""
+    _check_cuda(thin)
+    if thin.dtype != torch.float32:
+        raise ValueError("Not valid dtype: thin tensors are float32")
+    N, H, W, Ct = thin.shape
+    U = torch.empty(N, H, W, KU, dtype=torch.bfloat16, device=thin.device)
+    _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), N, H, W, Ct, R, S, int(flip), KU, _stream())
+    return U
+
+
+def thin_col2im(T, Ct, R, S, bias=None, tanh=False):
+    """thin[p, j] = bias[j] + sum_t T[p + off(t), t*Ct + j], optional tanh; T fp32 [N,H,W,CT]."""
+    _check_cuda(T, bias)
+    N, H, W, CT = T.shape
+    out = torch.empty(N, H, W, Ct, dtype=torch.float32, device=T.device)
+    flags = (EPI_BIAS if bias is not None else 0) | (EPI_TANH if tanh else 0)
+    _lib.call("mcgm_thin_col2im", T.data_ptr(), CT, out.data_ptr(), N, H, W, Ct, R, S, _ptr(bias), flags, _stream())
+    return out
+
+
+def _pad_rows(m, rows):
+    """[r, c] -> [rows, c] zero padded (tiny weight matrices)."""
+    if m.shape[0] == rows:
+        return m
+    return torch.cat([m, m.new_zeros(rows - m.shape[0], m.shape[1])], 0)
+
+
+def _pad_cols(m, cols):
+    if m.shape[1] == cols:
+        return m
+    return torch.cat([m, m.new_zeros(m.shape[0], cols - m.shape[1])], 1)
+
+
+_KU = 64          # im2col width of the thin tensor (R*S*Ct <= 36 taps*channels, padded to one 64-wide K block)
+
+
 class WideFromThinFn(torch.autograd.Function):
-    """Conv2d(Ct<=4 -> Cw) on an fp32 NHWC image, optional ReLU+mask epilogue (mcgan.py:77-79, 87)."""
+    """Conv2d(Ct<=4 -> Cw) on an fp32 NHWC image, optional ReLU+mask epilogue
+    (src/models/mcgan.py:77-79, 87).  im2col of the 3-channel image (tiny) turns it into a
+    1x1 tcgen05 GEMM with K = 64; the weight gradient is the 1x1 wgrad GEMM; the image
+    gradient (needed in the G update) is a 1x1 GEMM to [P, 32] followed by col2im."""
 
     @staticmethod
     def forward(ctx, thin, w, bias, gate, grad_premasked):
         K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
-        kern = w.detach().permute(2, 3, 1, 0).reshape(R * S, C, K).contiguous()
+        U = thin_im2col(thin, R, S, False, _KU)
+        wm = _pad_cols(w.detach().permute(0, 2, 3, 1).reshape(K, R * S * C), _KU)
+        wm = wm.to(torch.bfloat16).reshape(K, 1, 1, _KU).contiguous()
         flags, labels, packed = 0, None, None
         if gate is not None:
             labels, packed = gate
             flags = EPI_RELU | EPI_MASK
-        out = wide_from_thin(thin, kern, K, R, S, bias, labels, packed, None, flags)
-        ctx.save_for_backward(thin, w, out if gate is not None else None)
+        out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags)
+        ctx.save_for_backward(U, w, out if gate is not None else None)
         ctx.gated, ctx.has_bias, ctx.grad_premasked = gate is not None, bias is not None, grad_premasked
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        thin, w, out = ctx.saved_tensors
+        U, w, out = ctx.saved_tensors
         dout = dout.contiguous()
         K, C, R, S = w.shape
         if ctx.gated and not ctx.grad_premasked:
             dout = torch.where(out > 0, dout, torch.zeros_like(dout))
         dthin = dw = db = None
         if ctx.needs_input_grad[0]:
-            # dthin[p,j] = sum_{t,c} dout[p - off(t), c] w[c,j,t]  ->  kern[t'][j][c] = w[c, j, flip(t')]
-            kern = w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(R * S, C, K).contiguous()
-            dthin = thin_from_wide(dout, kern, C, R, S)
-        if ctx.needs_input_grad[1]:
-            dk = kern_grad(thin, dout, R, S)                   # [T][Ct][Cw]
-            dw = dk.reshape(R, S, C, K).permute(3, 2, 0, 1)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dout.float().sum(dim=(0, 1, 2))
+            # dthin[q,j] = sum_t T[q + off(t')][(t',j)],  T[p][(t',j)] = sum_co dout[p,co] w[co,j,flip(t')]
+            CT = 32 if R * S * C <= 32 else 64
+            wd = _pad_rows(w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(R * S * C, K), CT)
+            wd = wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous()
+            T = conv_fwd(dout, wd, torch.float32)
+            dthin = thin_col2im(T, C, R, S)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)       # [K,1,1,KU]
+            dw = dwm.reshape(K, _KU)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
         return dthin, dw, db, None, None
 
 
 class ThinFromWideFn(torch.autograd.Function):
-    """Conv2d(Cw -> Ct<=4) producing an fp32 NHWC image, optional tanh (mcgan.py:59-60)."""
+    """Conv2d(Cw -> Ct<=4) producing an fp32 NHWC image, optional tanh (mcgan.py:59-60):
+    a 1x1 tcgen05 GEMM of the wide tensor against all R*S*Ct tap filters ([P, 32] fp32),
+    then a col2im gather-sum.  Backward: im2col of the image gradient, then 1x1 GEMMs."""
 
     @staticmethod
     def forward(ctx, wide, w, bias, tanh):
         K, C, R, S = w.shape                                   # OIHW: K = Ct, C = Cw
-        kern = w.detach().permute(2, 3, 0, 1).reshape(R * S, K, C).contiguous()
-        out = thin_from_wide(wide, kern, K, R, S, bias, EPI_TANH if tanh else 0)
+        CT = 32 if R * S * K <= 32 else 64
+        wm = _pad_rows(w.detach().permute(2, 3, 0, 1).reshape(R * S * K, C), CT)
+        wm = wm.to(torch.bfloat16).reshape(CT, 1, 1, C).contiguous()
+        T = conv_fwd(wide, wm, torch.float32)
+        out = thin_col2im(T, K, R, S, bias, tanh)
         ctx.save_for_backward(wide, w, out if tanh else None)
         ctx.tanh, ctx.has_bias = tanh, bias is not None
         return out
@@ -396,16 +483,16 @@ class ThinFromWideFn(torch.autograd.Function):
         K, C, R, S = w.shape
         dout = dout.contiguous()
         if ctx.tanh:
-            dout = dout * (1.0 - out * out)                     # fp32 [N,H,W,3]: tiny
+            dout = dout * (1.0 - out * out)                     # fp32 [N,H,W,Ct]: tiny
         dwide = dw = db = None
+        Ub = thin_im2col(dout, R, S, True, _KU)                 # Ub[q,(t,j)] = dout[q - off(t), j]
         if ctx.needs_input_grad[0]:
-            # dwide[p,c] = sum_{t,j} dout[p - off(t), j] w[j,c,t]  ->  kern[t'][j][c] = w[j, c, flip(t')]
-            kern = w.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(R * S, K, C).contiguous()
-            dwide = wide_from_thin(dout, kern, C, R, S)
+            wb = _pad_cols(w.detach().permute(1, 2, 3, 0).reshape(C, R * S * K), _KU)
+            wb = wb.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous()
+            dwide = conv_fwd(Ub, wb, torch.bfloat16)
         if ctx.needs_input_grad[1]:
-            # dw[j,c,t] = sum_p dout[p,j] wide[p+off(t),c] = sum_q dout[q - off(t), j] wide[q, c]
-            dk = kern_grad(dout, wide, R, S)                   # dk[t'][j][c] with off(t') = -off(t)
-            dw = dk.reshape(R, S, K, C).flip(0, 1).permute(2, 3, 0, 1)
+            dwm, _ = conv_wgrad(wide, Ub, 1, 1, want_bias=False)              # [KU,1,1,C]
+            dw = dwm.reshape(_KU, C)[:R * S * K].reshape(R, S, K, C).permute(2, 3, 0, 1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dout.sum(dim=(0, 1, 2))
         return dwide, dw, db, None

@@ -158,4 +158,5 @@ def train_step(model, optimizer, input, z=None, reducers=None):
             reducers['generator'].finish()
             reducers['discriminator'].enabled = True
         optimizer['generator'].step()
-    return {'loss': (d_loss - g_loss).abs(), 'loss_D': d_loss, 'loss_G': g_loss}
+    total = (d_loss - g_loss).abs() if d_loss is not None and g_loss is not None else None
+    return {'loss': total, 'loss_D': d_loss, 'loss_G': g_loss}
