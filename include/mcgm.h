@@ -120,6 +120,24 @@ int mcgm_pack_weight(const float* w_oihw, int K, int C, int R, int S,
 int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int S,
                       float* dw_oihw, int accumulate, void* stream);
 
+/* ---- spectral normalisation, batched over layers (src/models/utils.py:17-21 -> torch legacy
+ * spectral_norm compute_weight).  For layer i: W_host[i] fp32 [K_i, CRS_i] (weight_orig viewed as a
+ * matrix), u_host[i] [K_i], v_host[i] [CRS_i] (the weight_u / weight_v buffers, updated IN PLACE when
+ * do_iter).  state (device) receives per layer, at element offset state_off_host[i], the snapshot
+ * [1/sigma | u | v] that forward packing and backward use.  The *_host arrays are HOST arrays of
+ * device pointers / sizes; at most 16 layers per call. */
+int mcgm_sn_power_iter(int n_layers, const float* const* W_host, const int* K_host, const int* CRS_host,
+                       float* const* u_host, float* const* v_host, float* state,
+                       const long* state_off_host, int do_iter, float eps, void* stream);
+/* dW = (dW_bar - <dW_bar, W_bar> u v^T) / sigma.  dW_bar is [K][row_stride] fp32 whose rows hold
+ * R*S*C entries in (r,s,c) order (krsc = 1, the layout of mcgm_conv_wgrad) or (c,r,s) order. */
+int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const float* W_oihw,
+                       const float* sn_state, int K, int C, int R, int S, float* dW_oihw, void* stream);
+/* bf16 [K][row_stride] <- W[k,c,r,s] * inv_sigma with columns in (r,s,c) order, zero padded: the
+ * weight matrix of the im2col'd thin convolution (row_stride = 64). */
+int mcgm_pack_weight_padded(const float* w_oihw, int K, int C, int R, int S, const float* inv_sigma,
+                            void* out_bf16, int row_stride, void* stream);
+
 /* ---- implicit-GEMM convolution, tcgen05 + TMA (replaces cudnn_convolution at
  * src/models/mcgan.py:19,23,29,59,77-85,103-128).  stride 1, pad (R-1)/2,
  * R=S in {1,3}; x bf16 NHWC [N,H,W,Cin] with Cin % 64 == 0; w bf16 KRSC

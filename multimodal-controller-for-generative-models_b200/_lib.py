@@ -34,6 +34,11 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mcgm_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcgm_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mcgm_sn_power_iter": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_float, c_void_p]),
+    "mcgm_sn_weight_bwd": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p]),
+    "mcgm_pack_weight_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mcgm_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),

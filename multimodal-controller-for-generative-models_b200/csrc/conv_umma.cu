@@ -115,6 +115,9 @@ struct DescKnobs {
   uint32_t k_lbo = 16, k_sbo = 1024;         // K-major operands
   uint32_t mn_lbo = 8192, mn_sbo = 1024;     // MN-major operands
   uint32_t version = 1, layout = 2;
+  uint32_t mt2 = 1, mt2_256 = 0;             // forward conv: two M tiles per CTA (BN <= 128 / BN = 256)
+  uint32_t nt2 = 1;                          // wgrad: two filter taps per CTA (Cin tile 128)
+  uint32_t wg_splits = 0;                    // wgrad: force the split-K factor (0 = automatic)
 };
 static DescKnobs g_knobs;
 
@@ -143,12 +146,16 @@ struct ConvFwdParams {
   void* out;
 };
 
-template <int BN>
+// MT = number of 128-pixel M tiles one CTA accumulates against the SAME weight slab: the B
+// bytes fetched from L2 per MMA halve with MT = 2 (the kernel is L2->SM bound, not tensor bound).
+template <int BN, int MT>
 struct FwdCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {16,64,128,256} -> power of two
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kAccStages = (2 * MT * BN <= 512) ? 2 : 1;
+  static constexpr int kTmemRaw = kAccStages * MT * BN;
+  static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -228,11 +235,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   }
 }
 
-template <int BN, typename OutT>
+template <int BN, int MT, typename OutT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const ConvFwdParams p) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -259,25 +266,35 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // a CTA tile = MT consecutive 128-pixel M tiles x one BN-wide slab of output channels
+  const int tiles_per_img_block = p.tiles_w * p.tiles_h;
+
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0, phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-        const int w0 = (mt % p.tiles_w) * p.TW;
-        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+        const int nt = t % p.n_tiles, mt0 = (t / p.n_tiles) * MT;
         const int cout0 = nt * BN;
+        int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int mt = mt0 + j;
+          w0[j] = (mt % p.tiles_w) * p.TW;
+          h0[j] = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+          n0[j] = (mt / tiles_per_img_block) * p.TN;       // past the batch for a ragged last pair: TMA zero-fills
+        }
+        int tap = 0, cb = 0, r = 0, s = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
-          const int r = tap / p.S, s = tap - r * p.S;
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          tma_load_4d(sa, &tmap_x, full_bar(stage), cb * kBlockK, w0 + s - p.pad, h0 + r - p.pad, n0);
-          tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, cout0);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kBlockK, w0[j] + s - p.pad, h0[j] + r - p.pad, n0[j]);
+          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, cout0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++cb == p.kpt) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
         }
       }
     }
@@ -286,19 +303,22 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // ===== MMA issuer =====
       int stage = 0, phase = 0, it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1, aphase = (it >> 1) & 1;
+        const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * (MT * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = smem_desc(p.desc_templ, sa);
-          const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
+          const uint64_t bdesc = smem_desc(p.desc_templ, sa + MT * kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t adesc = smem_desc(p.desc_templ, sa + j * kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+          }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -312,25 +332,29 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int as = it & 1, aphase = (it >> 1) & 1;
-      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-      const int w = (mt % p.tiles_w) * p.TW + tw;
-      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
-      const int n = (mt / (p.tiles_w * p.tiles_h)) * p.TN + tn;
-      const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-      const long pix = ((long)n * p.H + h) * p.W + w;
+      const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
+      const int nt = t % p.n_tiles, mt0 = (t / p.n_tiles) * MT;
       const int cout0 = nt * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-      constexpr int CW = BN < 32 ? BN : 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += CW) {
-        uint32_t acc[32];
-        if constexpr (CW == 32) tmem_ld32(t_row + c, acc);
-        else tmem_ld16(t_row + c, acc);
-        tmem_ld_wait();
-        epilogue_store_chunk<BN, OutT>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
+      for (int j = 0; j < MT; ++j) {
+        const int mt = mt0 + j;
+        const int w = (mt % p.tiles_w) * p.TW + tw;
+        const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+        const int n = (mt / tiles_per_img_block) * p.TN + tn;
+        const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+        const long pix = ((long)n * p.H + h) * p.W + w;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + j * BN;
+        constexpr int CW = BN < 32 ? BN : 32;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CW) {
+          uint32_t acc[32];
+          if constexpr (CW == 32) tmem_ld32(t_row + c, acc);
+          else tmem_ld16(t_row + c, acc);
+          tmem_ld_wait();
+          epilogue_store_chunk<BN, OutT>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -352,26 +376,29 @@ struct WgradParams {
   int N, H, W, Cin, Cout, R, S, pad;
   int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 pixels
   int total_kb, splits, kb_per_split;
-  int cout_tiles, cin_tiles, taps;
+  int cout_tiles, cin_tiles, taps, tap_groups;
   uint64_t desc_templ;
   uint32_t idesc;
   float* partial;                       // [splits][Cout*R*S*Cin]
 };
 
-template <int BN>
+// NT = number of filter taps one CTA accumulates against the SAME dY tile (A operand):
+// the dY bytes fetched per MMA halve with NT = 2.
+template <int BN, int NT>
 struct WgCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kStageBytes = kABytes + NT * kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kTmemRaw = NT * BN;
+  static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int NT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, NT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -384,12 +411,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 
   int id = blockIdx.x;
   const int split = id % p.splits; id /= p.splits;
-  const int tap = id % p.taps; id /= p.taps;
+  const int tap0 = (id % p.tap_groups) * NT; id /= p.tap_groups;
   const int cin_t = id % p.cin_tiles;
   const int cout_t = id / p.cin_tiles;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
-  const int r = tap / p.S, s = tap - r * p.S;
+  const int ntaps = min(NT, p.taps - tap0);          // the last group of a 3x3 kernel holds one tap
   const int co0 = cout_t * kTileM, ci0 = cin_t * BN;
 
   if (warp == 0 && lane == 0) {
@@ -409,21 +436,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
+      int dr[NT], ds[NT];                        // tap offsets of this CTA's taps (registers: loops are unrolled)
+#pragma unroll
+      for (int q = 0; q < NT; ++q) {
+        const int tap = min(tap0 + q, p.taps - 1);
+        dr[q] = tap / p.S - p.pad;
+        ds[q] = tap % p.S - p.pad;
+      }
+      int bw = kb0 % p.kb_w, bh = (kb0 / p.kb_w) % p.kb_h, bn = kb0 / (p.kb_w * p.kb_h);
+      const uint32_t tx_bytes = kABytes + ntaps * Cfg::kBBytes;
       for (int kb = kb0; kb < kb1; ++kb) {
-        const int w0 = (kb % p.kb_w) * p.KW;
-        const int h0 = ((kb / p.kb_w) % p.kb_h) * p.KH;
-        const int n0 = (kb / (p.kb_w * p.kb_h)) * p.KN;
+        const int w0 = bw * p.KW, h0 = bh * p.KH, n0 = bn * p.KN;
         mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int j = 0; j < kTileM / 64; ++j)
           tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0, h0, n0);
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(sa + kABytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j, w0 + s - p.pad,
-                      h0 + r - p.pad, n0);
+        for (int q = 0; q < NT; ++q) {
+          if (q < ntaps) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j,
+                          w0 + ds[q], h0 + dr[q], n0);
+          }
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++bw == p.kb_w) { bw = 0; if (++bh == p.kb_h) { bh = 0; ++bn; } }
       }
     }
   } else if (warp == 1) {
@@ -434,11 +474,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint64_t adesc = smem_desc(p.desc_templ, sa);
-        const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
+        const uint32_t acc_on = kb > kb0;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
-          umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
-                   (kb > kb0) || (k != 0));
+        for (int q = 0; q < NT; ++q) {
+          if (q < ntaps) {
+            const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes + q * Cfg::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
+              umma_f16(tmem_base + q * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
+                       acc_on | (uint32_t)(k != 0));
+          }
+        }
         umma_commit(empty_bar(stage));
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -449,23 +495,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     const int co = co0 + quad * 32 + lane;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t per_split = (size_t)p.Cout * p.taps * p.Cin;
-    float* dst = p.partial + (size_t)split * per_split + ((size_t)co * p.taps + tap) * p.Cin + ci0;
+    for (int q = 0; q < ntaps; ++q) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + q * BN;
+      float* dst = p.partial + (size_t)split * per_split + ((size_t)co * p.taps + tap0 + q) * p.Cin + ci0;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t acc[32];
-      tmem_ld32(t_row + c, acc);
-      tmem_ld_wait();
-      if (co < p.Cout && kb1 > kb0) {
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t acc[32];
+        tmem_ld32(t_row + c, acc);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          const bool have = kb1 > kb0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(dst + c + i) =
-              make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
-                          __uint_as_float(acc[i + 3]));
-      } else if (co < p.Cout) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + c + i) =
+                have ? make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                   __uint_as_float(acc[i + 3]))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
   }
@@ -575,10 +622,10 @@ static bool pick_pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return true;
 }
 
-template <int BN, typename OutT>
-static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFwdParams& p, cudaStream_t st) {
-  using Cfg = FwdCfg<BN>;
-  auto kern = conv_fwd_kernel<BN, OutT>;
+template <int BN, int MT, typename OutT>
+static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParams p, cudaStream_t st) {
+  using Cfg = FwdCfg<BN, MT>;
+  auto kern = conv_fwd_kernel<BN, MT, OutT>;
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -586,17 +633,24 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFw
   }
   int sms = sm_count();
   if (sms <= 0) return fail(MCGM_E_CUDA, "cannot query SM count");
+  const int m_tiles = p.total_tiles / p.n_tiles;
+  p.total_tiles = ((m_tiles + MT - 1) / MT) * p.n_tiles;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mx, mw, p);
   MCGM_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN>
+template <int BN, int MT>
+static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFwdParams& p, bool f32, cudaStream_t st) {
+  return f32 ? launch_fwd<BN, MT, float>(mx, mw, p, st) : launch_fwd<BN, MT, __nv_bfloat16>(mx, mw, p, st);
+}
+
+template <int BN, int NT>
 static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, int grid,
                         cudaStream_t st) {
-  using Cfg = WgCfg<BN>;
-  auto kern = conv_wgrad_kernel<BN>;
+  using Cfg = WgCfg<BN, NT>;
+  auto kern = conv_wgrad_kernel<BN, NT>;
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -608,7 +662,7 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
 }
 
 struct WgradPlan {
-  int BN, cout_tiles, cin_tiles, taps, splits, kb_per_split, total_kb, KW, KH, KN;
+  int BN, NT, tap_groups, cout_tiles, cin_tiles, taps, splits, kb_per_split, total_kb, KW, KH, KN;
   size_t per_split;  // floats
 };
 
@@ -623,10 +677,13 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int R, int S, Wgra
   pl->taps = R * S;
   const int n_boxes = (N + pl->KN - 1) / pl->KN;
   pl->total_kb = n_boxes * (H / pl->KH) * (W / pl->KW);
-  const int tiles = pl->cout_tiles * pl->cin_tiles * pl->taps;
+  pl->NT = (g_knobs.nt2 && pl->taps > 1 && pl->BN <= 128) ? 2 : 1;
+  pl->tap_groups = (pl->taps + pl->NT - 1) / pl->NT;
+  const int tiles = pl->cout_tiles * pl->cin_tiles * pl->tap_groups;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int splits = sms / tiles;                        // at most one wave of CTAs
+  if (g_knobs.wg_splits) splits = (int)g_knobs.wg_splits;
   if (splits > pl->total_kb) splits = pl->total_kb;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
@@ -648,6 +705,10 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 3: g_knobs.mn_sbo = (uint32_t)value; break;
     case 4: g_knobs.version = (uint32_t)value; break;
     case 5: g_knobs.layout = (uint32_t)value; break;
+    case 6: g_knobs.mt2 = (uint32_t)value; break;
+    case 7: g_knobs.mt2_256 = (uint32_t)value; break;
+    case 8: g_knobs.nt2 = (uint32_t)value; break;
+    case 9: g_knobs.wg_splits = (uint32_t)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
   }
   return 0;
@@ -726,12 +787,17 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = out_dtype == MCGM_F32;
+  // two M tiles per CTA when there is enough work to keep every SM busy with pairs
+  const int m_tiles = p.total_tiles / p.n_tiles;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const bool pair = g_knobs.mt2 && (((m_tiles + 1) / 2) * p.n_tiles >= sms);
   switch (BN) {
-    case 256: return f32 ? launch_fwd<256, float>(mx, mw, p, st) : launch_fwd<256, __nv_bfloat16>(mx, mw, p, st);
-    case 128: return f32 ? launch_fwd<128, float>(mx, mw, p, st) : launch_fwd<128, __nv_bfloat16>(mx, mw, p, st);
-    case 64: return f32 ? launch_fwd<64, float>(mx, mw, p, st) : launch_fwd<64, __nv_bfloat16>(mx, mw, p, st);
-    case 32: return f32 ? launch_fwd<32, float>(mx, mw, p, st) : launch_fwd<32, __nv_bfloat16>(mx, mw, p, st);
-    default: return f32 ? launch_fwd<16, float>(mx, mw, p, st) : launch_fwd<16, __nv_bfloat16>(mx, mw, p, st);
+    case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(mx, mw, p, f32, st) : launch_fwd_t<256, 1>(mx, mw, p, f32, st);
+    case 128: return pair ? launch_fwd_t<128, 2>(mx, mw, p, f32, st) : launch_fwd_t<128, 1>(mx, mw, p, f32, st);
+    case 64: return pair ? launch_fwd_t<64, 2>(mx, mw, p, f32, st) : launch_fwd_t<64, 1>(mx, mw, p, f32, st);
+    case 32: return launch_fwd_t<32, 1>(mx, mw, p, f32, st);
+    default: return launch_fwd_t<16, 1>(mx, mw, p, f32, st);
   }
 }
 
@@ -752,7 +818,7 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = (R - 1) / 2;
   p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = W / pl.KW; p.kb_h = H / pl.KH;
   p.total_kb = pl.total_kb; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
-  p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps;
+  p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
   p.desc_templ = make_smem_desc_hi_lbo(g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1);
   p.partial = (float*)workspace;
@@ -768,12 +834,12 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
     if (int e = make_tmap(&mx, x, 4, dims, box)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = pl.cout_tiles * pl.cin_tiles * pl.taps * pl.splits;
+  const int grid = pl.cout_tiles * pl.cin_tiles * pl.tap_groups * pl.splits;
   int e;
   switch (pl.BN) {
-    case 256: e = launch_wgrad<256>(mdy, mx, p, grid, st); break;
-    case 128: e = launch_wgrad<128>(mdy, mx, p, grid, st); break;
-    default: e = launch_wgrad<64>(mdy, mx, p, grid, st); break;
+    case 256: e = launch_wgrad<256, 1>(mdy, mx, p, grid, st); break;
+    case 128: e = pl.NT == 2 ? launch_wgrad<128, 2>(mdy, mx, p, grid, st) : launch_wgrad<128, 1>(mdy, mx, p, grid, st); break;
+    default: e = pl.NT == 2 ? launch_wgrad<64, 2>(mdy, mx, p, grid, st) : launch_wgrad<64, 1>(mdy, mx, p, grid, st); break;
   }
   if (e) return e;
   const size_t n4 = pl.per_split / 4;

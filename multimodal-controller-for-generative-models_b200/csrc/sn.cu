@@ -1,0 +1,202 @@
+// sn.cu — spectral normalisation of the discriminator's weights, batched over layers.
+//
+// Restates the forward pre-hook of torch's legacy spectral_norm that the reference applies
+// to every Conv/Linear of D (src/models/utils.py:17-21 -> torch/nn/utils/spectral_norm.py
+// compute_weight): per layer and per training forward
+//     v <- normalize(W^T u), u <- normalize(W v)      (eps 1e-12, in place on the buffers)
+//     sigma = u . (W v),  W_bar = W / sigma,  u and v treated as constants in backward
+// In eager PyTorch that is ~12 tiny kernels per layer (x 11 layers x 11 forwards per
+// iteration); here ONE launch handles all layers (one CTA each), writes the updated u, v
+// in place, and also snapshots [1/sigma | u | v] per layer into a `state` buffer, because
+// the two D forwards of one D update use different u, v and each backward needs its own.
+//
+//   backward:  dW = (dW_bar - <dW_bar, W_bar> u v^T) / sigma
+#include "common.cuh"
+
+namespace mcgm {
+
+static constexpr int kSnMaxLayers = 16;
+static constexpr int kSnThreads = 1024;
+
+struct SnBatch {
+  const float* W[kSnMaxLayers];
+  float* u[kSnMaxLayers];
+  float* v[kSnMaxLayers];
+  int K[kSnMaxLayers];
+  int CRS[kSnMaxLayers];
+  long off[kSnMaxLayers];
+};
+
+__device__ __forceinline__ float block_sum(float x, float* red) {
+  // red: >= 33 floats of shared scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  x = warp_sum(x);
+  __syncthreads();
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__global__ void __launch_bounds__(kSnThreads)
+sn_power_iter_kernel(const SnBatch b, float* __restrict__ state, int do_iter, float eps) {
+  extern __shared__ float sm[];          // [CRS] v | [K] u | [K] W v | [40] reduction scratch
+  const int L = blockIdx.x;
+  const float* __restrict__ W = b.W[L];
+  const int K = b.K[L], CRS = b.CRS[L];
+  float* sv = sm;
+  float* su = sm + CRS;
+  float* swv = su + K;
+  float* red = swv + K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+
+  for (int k = tid; k < K; k += blockDim.x) su[k] = b.u[L][k];
+  for (int j = tid; j < CRS; j += blockDim.x) sv[j] = b.v[L][j];
+  __syncthreads();
+  if (do_iter) {
+    // v = normalize(W^T u): thread j walks a column (coalesced across threads for every row k)
+    float nrm = 0.0f;
+    for (int j = tid; j < CRS; j += blockDim.x) {
+      float a = 0.0f;
+      for (int k = 0; k < K; ++k) a = fmaf(W[(size_t)k * CRS + j], su[k], a);
+      sv[j] = a;
+      nrm = fmaf(a, a, nrm);
+    }
+    nrm = block_sum(nrm, red);
+    const float inv = 1.0f / fmaxf(sqrtf(nrm), eps);
+    for (int j = tid; j < CRS; j += blockDim.x) sv[j] *= inv;
+    __syncthreads();
+  }
+  // W v: one warp per row
+  for (int k = warp; k < K; k += nw) {
+    float a = 0.0f;
+    for (int j = lane; j < CRS; j += 32) a = fmaf(W[(size_t)k * CRS + j], sv[j], a);
+    a = warp_sum(a);
+    if (lane == 0) swv[k] = a;
+  }
+  __syncthreads();
+  if (do_iter) {
+    // u = normalize(W v)
+    float nrm = 0.0f;
+    for (int k = tid; k < K; k += blockDim.x) nrm = fmaf(swv[k], swv[k], nrm);
+    nrm = block_sum(nrm, red);
+    const float inv = 1.0f / fmaxf(sqrtf(nrm), eps);
+    for (int k = tid; k < K; k += blockDim.x) su[k] = swv[k] * inv;
+    __syncthreads();
+  }
+  float dot = 0.0f;                       // sigma = u . (W v)
+  for (int k = tid; k < K; k += blockDim.x) dot = fmaf(su[k], swv[k], dot);
+  dot = block_sum(dot, red);
+  float* st = state + b.off[L];
+  if (tid == 0) st[0] = 1.0f / dot;
+  for (int k = tid; k < K; k += blockDim.x) {
+    st[1 + k] = su[k];
+    if (do_iter) b.u[L][k] = su[k];
+  }
+  for (int j = tid; j < CRS; j += blockDim.x) {
+    st[1 + K + j] = sv[j];
+    if (do_iter) b.v[L][j] = sv[j];
+  }
+}
+
+// dW[k,c,r,s] = (dWbar[k,(r,s,c)] - s * u[k] * v[(c,r,s)]) * inv_sigma,  s = <dWbar, W> * inv_sigma
+// dWbar is [K][row_stride] with the first R*S*C entries of a row in (r,s,c) order (KRSC), or in
+// (c,r,s) order when krsc == 0.  One CTA per layer call.
+__global__ void __launch_bounds__(kSnThreads)
+sn_weight_bwd_kernel(const float* __restrict__ dwbar, long row_stride, int krsc, const float* __restrict__ W,
+                     const float* __restrict__ st /*[inv_sigma | u | v]*/, int K, int C, int R, int S,
+                     float* __restrict__ dW) {
+  __shared__ float red[40];
+  const int CRS = C * R * S;
+  const long total = (long)K * CRS;
+  const float inv_sigma = st[0];
+  const float* u = st + 1;
+  const float* v = st + 1 + K;
+  auto src_index = [&](long o) -> long {   // o indexes OIHW: ((k*C + c)*R + r)*S + s
+    const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);
+    if (!krsc) return (long)k * row_stride + rem;
+    const int c = rem / (R * S), rs = rem - c * (R * S);
+    return (long)k * row_stride + (long)rs * C + c;
+  };
+  float acc = 0.0f;
+  for (long o = threadIdx.x; o < total; o += blockDim.x) acc = fmaf(dwbar[src_index(o)], W[o], acc);
+  const float s = block_sum(acc, red) * inv_sigma;
+  for (long o = threadIdx.x; o < total; o += blockDim.x) {
+    const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);
+    dW[o] = (dwbar[src_index(o)] - s * u[k] * v[rem]) * inv_sigma;
+  }
+}
+
+// bf16 [K][row_stride] <- W[k,c,r,s] * inv_sigma in (r,s,c) order, zero padded (im2col GEMM weights)
+__global__ void pack_weight_padded_kernel(const float* __restrict__ w, int K, int C, int R, int S,
+                                          const float* __restrict__ inv_sigma, __nv_bfloat16* __restrict__ out,
+                                          int row_stride) {
+  const long total = (long)K * row_stride;
+  const float sc = inv_sigma ? __ldg(inv_sigma) : 1.0f;
+  const int RSC = R * S * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i / row_stride), col = (int)(i - (long)k * row_stride);
+    float v = 0.0f;
+    if (col < RSC) {
+      const int c = col % C, rs = col / C;
+      v = w[((long)k * C + c) * (R * S) + rs] * sc;
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace mcgm
+
+using namespace mcgm;
+
+extern "C" int mcgm_sn_power_iter(int n_layers, const float* const* W_host, const int* K_host, const int* CRS_host,
+                                  float* const* u_host, float* const* v_host, float* state,
+                                  const long* state_off_host, int do_iter, float eps, void* stream) {
+  MCGM_CHECK_ARG(n_layers > 0 && n_layers <= kSnMaxLayers, "sn_power_iter: 1..%d layers per call (got %d)", kSnMaxLayers, n_layers);
+  MCGM_CHECK_ARG(W_host && K_host && CRS_host && u_host && v_host && state && state_off_host, "sn_power_iter: bad arguments");
+  SnBatch b{};
+  int smem_floats = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    MCGM_CHECK_ARG(W_host[i] && u_host[i] && v_host[i] && K_host[i] > 0 && CRS_host[i] > 0, "sn_power_iter: layer %d invalid", i);
+    b.W[i] = W_host[i]; b.u[i] = u_host[i]; b.v[i] = v_host[i];
+    b.K[i] = K_host[i]; b.CRS[i] = CRS_host[i]; b.off[i] = state_off_host[i];
+    const int need = 2 * K_host[i] + CRS_host[i] + 64;
+    if (need > smem_floats) smem_floats = need;
+  }
+  const size_t smem = (size_t)smem_floats * sizeof(float);
+  if (smem > 200 * 1024) return fail(MCGM_E_UNSUPPORTED, "sn_power_iter: layer too large for shared memory");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MCGM_CUDA(cudaFuncSetAttribute(sn_power_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  sn_power_iter_kernel<<<n_layers, kSnThreads, smem, (cudaStream_t)stream>>>(b, state, do_iter, eps);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const float* W_oihw,
+                                  const float* sn_state, int K, int C, int R, int S, float* dW_oihw, void* stream) {
+  MCGM_CHECK_ARG(dwbar && W_oihw && sn_state && dW_oihw && K > 0 && C > 0 && R > 0 && S > 0 && row_stride >= (long)C * R * S,
+                 "sn_weight_bwd: bad arguments");
+  sn_weight_bwd_kernel<<<1, kSnThreads, 0, (cudaStream_t)stream>>>(dwbar, row_stride, krsc, W_oihw, sn_state, K, C, R, S, dW_oihw);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_pack_weight_padded(const float* w_oihw, int K, int C, int R, int S, const float* inv_sigma,
+                                       void* out_bf16, int row_stride, void* stream) {
+  MCGM_CHECK_ARG(w_oihw && out_bf16 && K > 0 && C > 0 && R > 0 && S > 0 && row_stride >= C * R * S, "pack_weight_padded: bad arguments");
+  const long total = (long)K * row_stride;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  pack_weight_padded_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, K, C, R, S, inv_sigma,
+                                                                          (__nv_bfloat16*)out_bf16, row_stride);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}

@@ -31,7 +31,7 @@ from .. import ops
 from .._lib import GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2
 from ..config import cfg
 from ..modules import MultimodalController, Wrapper
-from .utils import init_param, make_SpectralNormalization, sn_weight
+from .utils import init_param, make_SpectralNormalization
 
 
 # --------------------------------------------------------------------------- tree building
@@ -77,8 +77,9 @@ class GlobalSumPooling(nn.Module):
 class _Ctx:
     """Per-forward context: int32 mode labels on the device."""
 
-    def __init__(self, labels):
+    def __init__(self, labels, sn=None):
         self.labels = ops.as_labels(labels).contiguous()
+        self.sn = sn            # {module: spectral-norm snapshot} for this forward
 
 
 def _labels_from_indicator(indicator):
@@ -105,15 +106,14 @@ def _packs(weight):
     return packs
 
 
-def _conv(x, conv, training, res=None, res_up=False, gate=None, premask_dx=False, grad_premasked=False):
-    """tcgen05 conv through ``conv`` (an nn.Conv2d container, possibly spectral-normed)."""
+def _conv(x, conv, ctx, res=None, res_up=False, gate=None, premask_dx=False, grad_premasked=False):
+    """tcgen05 conv through ``conv`` (an nn.Conv2d container, possibly spectral-normed: then
+    ``ctx.sn[conv]`` holds this forward's [1/sigma | u | v] and the weight is packed as W/sigma)."""
     if hasattr(conv, 'weight_orig'):
-        w = sn_weight(conv, training)
-        packs = None
-    else:
-        w = conv.weight
-        packs = _packs(w) if x.is_cuda else None
-    return ops.ConvFn.apply(x, w, conv.bias, res, res_up, gate, premask_dx, grad_premasked, packs)
+        return ops.ConvFn.apply(x, conv.weight_orig, conv.bias, res, res_up, gate, premask_dx, grad_premasked,
+                                None, ctx.sn[conv])
+    w = conv.weight
+    return ops.ConvFn.apply(x, w, conv.bias, res, res_up, gate, premask_dx, grad_premasked, _packs(w), None)
 
 
 def _bn_gate(x, bn, mc, ctx, training, up=False, want_raw=False):
@@ -157,10 +157,10 @@ class GenResBlock(nn.Module):
             raise ValueError('Not valid stride (the fused generator block upsamples by 2)')
         t = self.training
         a, s = _bn_gate(x, self.conv[0].module, self.mc_1, ctx, t, up=True, want_raw=True)
-        sc = _conv(s, self.shortcut[2].module, t)                        # 1x1 at low resolution
-        c1 = _conv(a, self.conv[4].module, t)
+        sc = _conv(s, self.shortcut[2].module, ctx)                      # 1x1 at low resolution
+        c1 = _conv(a, self.conv[4].module, ctx)
         h2, _ = _bn_gate(c1, self.conv[5].module, self.mc_2, ctx, t)
-        return _conv(h2, self.conv[8].module, t, res=sc, res_up=True)
+        return _conv(h2, self.conv[8].module, ctx, res=sc, res_up=True)
 
 
 class Generator(nn.Module):
@@ -205,11 +205,10 @@ class FirstDisResBlock(nn.Module):
     def fused(self, img, ctx):
         """img: fp32 NHWC [N,H,W,3] (mcgan.py:72-93).  AvgPool is linear, so conv2 + shortcut are
         summed at full resolution in conv2's epilogue and pooled once."""
-        t = self.training
         c1, c2, sc = self.conv[0].module, self.conv[3].module, self.shortcut[0].module
-        h = ops.WideFromThinFn.apply(img, sn_weight(c1, t), c1.bias, (ctx.labels, self.mc_1.packed()), True)
-        s = ops.WideFromThinFn.apply(img, sn_weight(sc, t), sc.bias, None, False)
-        y = _conv(h, c2, t, res=s, premask_dx=True)
+        h = ops.WideFromThinFn.apply(img, c1.weight_orig, c1.bias, (ctx.labels, self.mc_1.packed()), True, ctx.sn[c1])
+        s = ops.WideFromThinFn.apply(img, sc.weight_orig, sc.bias, None, False, ctx.sn[sc])
+        y = _conv(h, c2, ctx, res=s, premask_dx=True)
         return ops.Pool2Fn.apply(y)
 
 
@@ -232,12 +231,11 @@ class DisResBlock(nn.Module):
                 self.shortcut = nn.Sequential()
 
     def fused(self, x, ctx):
-        t = self.training
         has_sc = len(self.shortcut) > 0
         a, s = _relu_gate(x, self.mc_1, ctx, want_raw=has_sc)
-        h = _conv(a, self.conv[2].module, t, gate=(ctx.labels, self.mc_2.packed()), grad_premasked=True)
-        res = _conv(s, self.shortcut[1].module, t) if has_sc else x
-        y = _conv(h, self.conv[5].module, t, res=res, premask_dx=True)
+        h = _conv(a, self.conv[2].module, ctx, gate=(ctx.labels, self.mc_2.packed()), grad_premasked=True)
+        res = _conv(s, self.shortcut[1].module, ctx) if has_sc else x
+        y = _conv(h, self.conv[5].module, ctx, res=res, premask_dx=True)
         return ops.Pool2Fn.apply(y) if self.stride > 1 else y
 
 
@@ -255,11 +253,18 @@ class Discriminator(nn.Module):
         blocks += [_layer('relu'), MultimodalController(h[-1], num_mode, controller_rate),
                    _layer('sumpool'), _layer(('linear', h[-1], 1))]
         self.blocks = nn.Sequential(*blocks)
+        self._sn_batch = None       # built lazily: spectral norm is applied after construction (mcgan.py:191)
 
     def forward(self, input, indicator):
         """input image [N,C,H,W] fp32; indicator one-hot [N,M] (or int labels) -> logits [N,1]
         (src/models/mcgan.py:178-181)."""
-        ctx = _Ctx(_labels_from_indicator(indicator))
+        if self._sn_batch is None:
+            mods = [m for m in self.modules() if hasattr(m, 'weight_orig')]
+            self._sn_batch = [ops.SNBatch(mods[i:i + 16]) for i in range(0, len(mods), 16)]
+        sn = {}
+        for batch in self._sn_batch:      # one launch per <= 16 layers: power iteration + [1/sigma|u|v] snapshot
+            sn.update(batch.run(self.training))
+        ctx = _Ctx(_labels_from_indicator(indicator), sn)
         img = input.permute(0, 2, 3, 1).contiguous().float()
         n_res = len(self.blocks) - 4
         x = self.blocks[0].fused(img, ctx)
@@ -268,7 +273,8 @@ class Discriminator(nn.Module):
         g, _ = _relu_gate(x, self.blocks[n_res + 1], ctx)
         pooled = g.float().sum(dim=(1, 2))                                # global SUM pooling [N, C]
         lin = self.blocks[n_res + 3].module
-        return F.linear(pooled, sn_weight(lin, self.training), lin.bias)
+        w = ops.SNScaleFn.apply(lin.weight_orig, sn[lin]) if lin in sn else lin.weight
+        return F.linear(pooled, w, lin.bias)
 
 
 # --------------------------------------------------------------------------- MCGAN

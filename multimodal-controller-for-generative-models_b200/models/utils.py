@@ -2,7 +2,6 @@
 (src/models/utils.py:7-21)."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ..config import cfg
 
@@ -27,23 +26,3 @@ def make_SpectralNormalization(m):
     """Legacy ``torch.nn.utils.spectral_norm`` on Linear / Conv layers (src/models/utils.py:17-21):
     creates ``weight_orig``, ``weight_u``, ``weight_v`` — the state_dict keys of the reference."""
     return torch.nn.utils.spectral_norm(m) if isinstance(m, _DENSE) else m
-
-
-def sn_weight(module, training):
-    """Effective weight ``W / sigma`` of a spectral-normed layer, restating the forward
-    pre-hook of torch's legacy spectral_norm (``compute_weight``): in training one power
-    iteration updates the ``weight_u`` / ``weight_v`` buffers IN PLACE (eps 1e-12), then
-    sigma = u . (W v) is differentiated with u, v held constant.  Layers without spectral
-    norm return their plain weight."""
-    if not hasattr(module, 'weight_orig'):
-        return module.weight
-    w = module.weight_orig
-    u, v = module.weight_u, module.weight_v
-    mat = w.reshape(w.size(0), -1)
-    if training:
-        with torch.no_grad():
-            F.normalize(torch.mv(mat.t(), u), dim=0, eps=1e-12, out=v)
-            F.normalize(torch.mv(mat, v), dim=0, eps=1e-12, out=u)
-            u, v = u.clone(), v.clone()
-    sigma = torch.dot(u, torch.mv(mat, v))
-    return w / sigma

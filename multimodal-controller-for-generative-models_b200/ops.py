@@ -186,6 +186,87 @@ def pack_weight(w, inv_sigma=None, want_fwd=True, want_flip=True):
     return fwd, flip
 
 
+def pack_weight_padded(w, inv_sigma, row_stride):
+    """bf16 [K, 1, 1, row_stride] <- W * inv_sigma, columns in (r,s,c) order, zero padded."""
+    _check_cuda(w, inv_sigma)
+    K, C, R, S = w.shape
+    out = torch.empty(K, 1, 1, row_stride, dtype=torch.bfloat16, device=w.device)
+    _lib.call("mcgm_pack_weight_padded", w.data_ptr(), K, C, R, S, _ptr(inv_sigma), out.data_ptr(), row_stride, _stream())
+    return out
+
+
+class SNBatch:
+    """All spectral-normed layers of one network: ONE launch runs every layer's power iteration
+    (in place on weight_u / weight_v) and snapshots [1/sigma | u | v] per layer."""
+
+    def __init__(self, modules):
+        import ctypes
+        self.modules = list(modules)
+        n = len(self.modules)
+        if n == 0 or n > 16:
+            raise ValueError("Not valid number of spectral-normed layers (1..16 per batch)")
+        self.shapes = []
+        offs, off = [], 0
+        for m in self.modules:
+            w = m.weight_orig
+            K, CRS = w.shape[0], w.numel() // w.shape[0]
+            self.shapes.append((K, CRS))
+            offs.append(off)
+            off += (1 + K + CRS + 3) // 4 * 4
+        self.total, self.offs = off, offs
+        self._c = ctypes
+        self._key = None
+
+    def _arrays(self):
+        key = tuple((m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()) for m in self.modules)
+        if key != self._key:
+            c, n = self._c, len(self.modules)
+            self._W = (c.c_void_p * n)(*[k[0] for k in key])
+            self._u = (c.c_void_p * n)(*[k[1] for k in key])
+            self._v = (c.c_void_p * n)(*[k[2] for k in key])
+            self._K = (c.c_int * n)(*[s[0] for s in self.shapes])
+            self._CRS = (c.c_int * n)(*[s[1] for s in self.shapes])
+            self._off = (c.c_long * n)(*self.offs)
+            self._key = key
+        return self._W, self._K, self._CRS, self._u, self._v, self._off
+
+    def run(self, do_iter):
+        """-> {module: state view [1/sigma | u | v]}"""
+        dev = self.modules[0].weight_orig.device
+        for m in self.modules:
+            _check_cuda(m.weight_orig, m.weight_u, m.weight_v)
+        state = torch.empty(self.total, dtype=torch.float32, device=dev)
+        W, K, CRS, u, v, off = self._arrays()
+        _lib.call("mcgm_sn_power_iter", len(self.modules), W, K, CRS, u, v, state.data_ptr(), off, int(do_iter),
+                  1e-12, _stream())
+        return {m: state[o:o + 1 + k + crs] for m, o, (k, crs) in zip(self.modules, self.offs, self.shapes)}
+
+
+def sn_weight_bwd(dwbar, row_stride, krsc, w, state):
+    """dW (OIHW, fp32) = (dW_bar - <dW_bar, W_bar> u v^T) / sigma."""
+    _check_cuda(w, state)
+    K, C, R, S = w.shape if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1)
+    dw = torch.empty_like(w)
+    _lib.call("mcgm_sn_weight_bwd", dwbar.data_ptr(), row_stride, int(krsc), w.data_ptr(), state.data_ptr(),
+              K, C, R, S, dw.data_ptr(), _stream())
+    return dw
+
+
+class SNScaleFn(torch.autograd.Function):
+    """W_bar = W / sigma for a small (Linear) weight; backward through sigma with u, v constant."""
+
+    @staticmethod
+    def forward(ctx, w, state):
+        ctx.save_for_backward(w, state)
+        return w * state[0]
+
+    @staticmethod
+    def backward(ctx, dwbar):
+        w, state = ctx.saved_tensors
+        dwbar = dwbar.contiguous()
+        return sn_weight_bwd(dwbar, dwbar.numel() // dwbar.shape[0], 0, w, state), None
+
+
 def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None, labels=None, packed=None,
              flags=0):
     """Implicit-GEMM conv (tcgen05): x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> [N,H,W,Cout]."""
@@ -343,8 +424,12 @@ class ConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs):
-        wf, wflip = packs if packs is not None else pack_weight(w)
+    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn):
+        # sn: [1/sigma | u | v] snapshot of a spectral-normed layer (w is then weight_orig)
+        if packs is not None:
+            wf, wflip = packs
+        else:
+            wf, wflip = pack_weight(w.detach(), sn[0:1] if sn is not None else None)
         flags = 0
         labels = packed = None
         if gate is not None:
@@ -353,7 +438,7 @@ class ConvFn(torch.autograd.Function):
         if res is not None:
             flags |= EPI_RES_UP2 if res_up else EPI_RES
         out = conv_fwd(x, wf, torch.bfloat16, bias, res, None, labels, packed, flags)
-        ctx.save_for_backward(x, out if gate is not None else None)
+        ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn)
         ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
         ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
         ctx.gated, ctx.premask_dx, ctx.grad_premasked = gate is not None, premask_dx, grad_premasked
@@ -361,7 +446,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, out = ctx.saved_tensors
+        x, out, w_orig, sn = ctx.saved_tensors
         dout = dout.contiguous()
         K, C, R, S = ctx.wshape
         if ctx.gated and not ctx.grad_premasked:
@@ -375,10 +460,13 @@ class ConvFn(torch.autograd.Function):
                 dx = conv_fwd(dout, ctx.wflip, torch.bfloat16)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw_krsc, db = conv_wgrad(x, dout, R, S, want_bias=ctx.has_bias)
-            dw = dw_krsc.permute(0, 3, 1, 2)          # KRSC -> OIHW view
+            if sn is not None:
+                dw = sn_weight_bwd(dw_krsc, R * S * C, 1, w_orig, sn)
+            else:
+                dw = dw_krsc.permute(0, 3, 1, 2)      # KRSC -> OIHW view
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = pool2(dout, 1.0) if ctx.res_up else dout
-        return dx, dw, db, dres, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None
 
 
 def thin_im2col(thin, R, S, flip=False, KU=64):
@@ -425,23 +513,22 @@ class WideFromThinFn(torch.autograd.Function):
     gradient (needed in the G update) is a 1x1 GEMM to [P, 32] followed by col2im."""
 
     @staticmethod
-    def forward(ctx, thin, w, bias, gate, grad_premasked):
+    def forward(ctx, thin, w, bias, gate, grad_premasked, sn):
         K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
         U = thin_im2col(thin, R, S, False, _KU)
-        wm = _pad_cols(w.detach().permute(0, 2, 3, 1).reshape(K, R * S * C), _KU)
-        wm = wm.to(torch.bfloat16).reshape(K, 1, 1, _KU).contiguous()
+        wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
         flags, labels, packed = 0, None, None
         if gate is not None:
             labels, packed = gate
             flags = EPI_RELU | EPI_MASK
         out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags)
-        ctx.save_for_backward(U, w, out if gate is not None else None)
+        ctx.save_for_backward(U, w, out if gate is not None else None, sn)
         ctx.gated, ctx.has_bias, ctx.grad_premasked = gate is not None, bias is not None, grad_premasked
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        U, w, out = ctx.saved_tensors
+        U, w, out, sn = ctx.saved_tensors
         dout = dout.contiguous()
         K, C, R, S = w.shape
         if ctx.gated and not ctx.grad_premasked:
@@ -450,14 +537,18 @@ class WideFromThinFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dthin[q,j] = sum_t T[q + off(t')][(t',j)],  T[p][(t',j)] = sum_co dout[p,co] w[co,j,flip(t')]
             CT = 32 if R * S * C <= 32 else 64
-            wd = _pad_rows(w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(R * S * C, K), CT)
+            weff = w.detach() * sn[0] if sn is not None else w.detach()
+            wd = _pad_rows(weff.flip(2, 3).permute(2, 3, 1, 0).reshape(R * S * C, K), CT)
             wd = wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous()
             T = conv_fwd(dout, wd, torch.float32)
             dthin = thin_col2im(T, C, R, S)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)       # [K,1,1,KU]
-            dw = dwm.reshape(K, _KU)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
-        return dthin, dw, db, None, None
+            dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)       # [K,1,1,KU], columns (r,s,c)
+            if sn is not None:
+                dw = sn_weight_bwd(dwm, _KU, 1, w, sn)
+            else:
+                dw = dwm.reshape(K, _KU)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
+        return dthin, dw, db, None, None, None
 
 
 class ThinFromWideFn(torch.autograd.Function):

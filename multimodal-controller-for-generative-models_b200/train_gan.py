@@ -14,16 +14,19 @@ import torch.nn.functional as F
 from .config import GAN_HYPER, cfg
 
 
-def make_optimizer(model, lr, betas):
-    """Adam with torch defaults eps=1e-8, no amsgrad (src/train_gan.py:223-236)."""
-    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas)
+def make_optimizer(model, lr, betas, capturable=False):
+    """Adam with torch defaults eps=1e-8, no amsgrad (src/train_gan.py:223-236).
+    ``capturable`` keeps the step counter on the device so the update can live in a CUDA graph."""
+    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas,
+                            capturable=capturable)
 
 
-def make_optimizers(model):
+def make_optimizers(model, capturable=False):
     return {
-        'generator': make_optimizer(model.generator, GAN_HYPER['lr']['generator'], GAN_HYPER['betas']['generator']),
+        'generator': make_optimizer(model.generator, GAN_HYPER['lr']['generator'], GAN_HYPER['betas']['generator'],
+                                    capturable),
         'discriminator': make_optimizer(model.discriminator, GAN_HYPER['lr']['discriminator'],
-                                        GAN_HYPER['betas']['discriminator']),
+                                        GAN_HYPER['betas']['discriminator'], capturable),
     }
 
 
@@ -160,3 +163,44 @@ def train_step(model, optimizer, input, z=None, reducers=None):
         optimizer['generator'].step()
     total = (d_loss - g_loss).abs() if d_loss is not None and g_loss is not None else None
     return {'loss': total, 'loss_D': d_loss, 'loss_G': g_loss}
+
+
+class GraphedTrainStep:
+    """The whole training iteration (5 D + 1 G updates: forwards, backwards, Adam, noise draws)
+    captured ONCE into a CUDA graph and replayed per batch.
+
+    One iteration is ~6000 kernel launches of 10-400 us each; issued eagerly the host can barely
+    stay ahead of the B200.  The step has static shapes and never synchronises with the host, so
+    it is captured after a few eager warm-up iterations (which also build every lazily created
+    workspace, packed codebook and TMA descriptor) and replayed with new data copied into static
+    input buffers.  Optimisers must be built with ``capturable=True``.
+    """
+
+    def __init__(self, model, optimizer, batch_size, warmup=3):
+        dev = next(model.parameters()).device
+        shape = model.generator.data_shape
+        self.img = torch.zeros(batch_size, *shape, device=dev)
+        self.label = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.model, self.optimizer = model, optimizer
+        batch = {'img': self.img, 'label': self.label}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_step(model, optimizer, batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        c0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = train_step(model, optimizer, batch)
+        self.native_launches = _lib.launch_count - c0      # libmcgm kernels inside one replay
+
+    def __call__(self, input):
+        """input: {'img','label'} on the host (pinned) or the device; returns device loss tensors
+        that are overwritten by the next call."""
+        self.img.copy_(input['img'], non_blocking=True)
+        self.label.copy_(input['label'], non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -152,6 +152,9 @@ def check_pool():
 CONV_SHAPES = [  # N, H, W, Cin, Cout, R
     (2, 32, 32, 64, 64, 3), (4, 8, 8, 128, 128, 3), (2, 16, 16, 256, 256, 3), (8, 4, 4, 64, 128, 1),
     (3, 16, 16, 128, 256, 1), (2, 8, 8, 64, 3, 3), (1, 32, 32, 256, 128, 3), (5, 8, 8, 64, 64, 3),
+    # enough M tiles that the two-tiles-per-CTA (MT=2) forward and two-taps-per-CTA (NT=2) wgrad paths run,
+    # the second with an ODD tile count (ragged last pair)
+    (40, 32, 32, 64, 128, 3), (593, 8, 8, 64, 64, 3), (40, 32, 32, 64, 256, 1),
 ]
 
 
@@ -257,7 +260,7 @@ def check_thin():
         out_ref.backward(dy)
         imd = nhwc(img).to(DEV).requires_grad_(True)
         wd = w.to(DEV).requires_grad_(True)
-        out = ops.WideFromThinFn.apply(imd, wd, b.to(DEV), (lab, packed), False)
+        out = ops.WideFromThinFn.apply(imd, wd, b.to(DEV), (lab, packed), False, None)
         rows.append((f"wide_from_thin fwd {tag}", rel(nchw(out.float()), out_ref), BF16_OUT))
         out.backward(nhwc(dy).to(DEV).to(torch.bfloat16))
         # the GPU masks dy with its own (bf16-rounded) output sign; identical except at exact zeros
@@ -282,5 +285,66 @@ def check_thin():
     return rows
 
 
+class _SNLayer:
+    def __init__(self, w, u, v):
+        self.weight_orig, self.weight_u, self.weight_v = w, u, v
+
+
+def check_sn():
+    """Batched spectral-norm power iteration / W/sigma packing / backward vs the oracle (torch CPU)."""
+    rows = []
+    g = torch.Generator().manual_seed(3)
+    shapes = [(128, 128, 3, 3), (128, 3, 3, 3), (128, 128, 1, 1), (1, 128, 1, 1), (64, 64, 3, 3)]
+    ws = [torch.randn(*sh, generator=g) * 0.1 for sh in shapes]
+    us = [F.normalize(torch.randn(sh[0], generator=g), dim=0) for sh in shapes]
+    vs = [F.normalize(torch.randn(sh[1] * sh[2] * sh[3], generator=g), dim=0) for sh in shapes]
+    layers = [_SNLayer(w.to(DEV), u.to(DEV), v.to(DEV)) for w, u, v in zip(ws, us, vs)]
+    batch = ops.SNBatch(layers)
+    for it in range(2):                      # two consecutive training forwards (u, v carried in place)
+        states = batch.run(True)
+        for i, (sh, L) in enumerate(zip(shapes, layers)):
+            sd = {"weight_orig": ws[i].clone().requires_grad_(True), "weight_u": us[i], "weight_v": vs[i]}
+            wbar = O.sn_weight(sd, "", True)          # updates us[i], vs[i] in place like the reference
+            st = states[L]
+            K, CRS = sh[0], sh[1] * sh[2] * sh[3]
+            tag = f"iter{it} {sh}"
+            rows.append((f"sn u {tag}", rel(st[1:1 + K], us[i]), F32_TOL))
+            rows.append((f"sn v {tag}", rel(st[1 + K:1 + K + CRS], vs[i]), F32_TOL))
+            rows.append((f"sn buffers in place {tag}", rel(L.weight_u, us[i]) + rel(L.weight_v, vs[i]), 2 * F32_TOL))
+            rows.append((f"sn wbar {tag}", rel(L.weight_orig * st[0], wbar.detach()), F32_TOL))
+            dwbar = torch.randn(*sh, generator=g)
+            wbar.backward(dwbar)
+            # backward from a KRSC-ordered gradient (conv_wgrad layout) and from an OIHW-ordered one
+            dk = dwbar.permute(0, 2, 3, 1).contiguous().to(DEV)
+            got = ops.sn_weight_bwd(dk, CRS, 1, L.weight_orig, st)
+            rows.append((f"sn bwd krsc {tag}", rel(got, sd["weight_orig"].grad), 1e-4))
+            got = ops.sn_weight_bwd(dwbar.to(DEV).contiguous(), CRS, 0, L.weight_orig, st)
+            rows.append((f"sn bwd oihw {tag}", rel(got, sd["weight_orig"].grad), 1e-4))
+            if sh[1] <= 4:
+                pk = ops.pack_weight_padded(L.weight_orig, st[0:1], 64).float().cpu().reshape(K, 64)
+                want = torch.zeros(K, 64)
+                want[:, :CRS] = wbar.detach().permute(0, 2, 3, 1).reshape(K, CRS)
+                rows.append((f"pack_weight_padded {tag}", rel(pk, want.to(torch.bfloat16).float()), 1e-6))
+    # eval mode: no power iteration, sigma from the stored u, v
+    states = batch.run(False)
+    sd = {"weight_orig": ws[0], "weight_u": us[0], "weight_v": vs[0]}
+    rows.append(("sn eval wbar", rel(layers[0].weight_orig * states[layers[0]][0], O.sn_weight(sd, "", False)), F32_TOL))
+    return rows
+
+
+def check_conv_variants():
+    """The same parity rows with the alternative tilings forced on / off through mcgm_debug_set."""
+    rows = []
+    big = [sh for sh in CONV_SHAPES if sh[0] >= 40]
+    for key, val, tag in [(7, 1, "BN256/MT2"), (6, 0, "MT1 only"), (8, 0, "NT1 only")]:
+        _lib.call("mcgm_debug_set", key, val)
+        try:
+            rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_fwd(big) if n.startswith("conv")]
+            rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_wgrad(big)]
+        finally:
+            _lib.call("mcgm_debug_set", key, {7: 0, 6: 1, 8: 1}[key])
+    return rows
+
+
 ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
-                     check_conv_wgrad, check_thin]
+                     check_conv_wgrad, check_thin, check_conv_variants, check_sn]

@@ -1,0 +1,83 @@
+"""Kernel microbenchmarks (CUDA events, L2 flushed between launches): conv fwd / wgrad / gate."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__ as entry  # noqa: E402
+entry.build()
+from mcgm_b200 import ops  # noqa: E402
+from mcgm_b200._lib import GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2  # noqa: E402
+
+from mcgm_b200 import _lib  # noqa: E402
+for kv in filter(None, os.environ.get("MCGM_DEBUG_SET", "").split(",")):
+    k, v = kv.split("=")
+    _lib.call("mcgm_debug_set", int(k), int(v))
+    print("debug_set", k, v)
+dev = "cuda"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+which = sys.argv[1:] or ["conv", "wgrad", "gate"]
+N = 512
+if "conv" in which:
+    for (H, Cin, Cout, R) in [(32, 256, 256, 3), (16, 256, 256, 3), (8, 256, 256, 3), (32, 128, 128, 3), (16, 128, 128, 3),
+                              (8, 128, 128, 3), (16, 256, 256, 1), (16, 128, 128, 1), (32, 64, 128, 1), (32, 256, 32, 1)]:
+        x = torch.randn(N, H, H, Cin, device=dev).to(torch.bfloat16)
+        w = torch.randn(Cout, R, R, Cin, device=dev).to(torch.bfloat16)
+        t = timeit(lambda: ops.conv_fwd(x, w, torch.bfloat16 if Cout != 32 else torch.float32))
+        fl = 2.0 * N * H * H * Cin * Cout * R * R
+        print(f"conv_fwd N{N} {H}x{H} {Cin}->{Cout} k{R}: {t * 1e6:8.1f} us  {fl / t / 1e12:7.1f} TFLOP/s", flush=True)
+if "wgrad" in which:
+    for (H, Cin, Cout, R) in [(32, 256, 256, 3), (16, 256, 256, 3), (8, 256, 256, 3), (32, 128, 128, 3), (16, 128, 128, 3),
+                              (8, 128, 128, 3), (16, 256, 256, 1), (32, 64, 128, 1), (32, 256, 64, 1)]:
+        x = torch.randn(N, H, H, Cin, device=dev).to(torch.bfloat16)
+        dy = torch.randn(N, H, H, Cout, device=dev).to(torch.bfloat16)
+        t = timeit(lambda: ops.conv_wgrad(x, dy, R, R, want_bias=False))
+        fl = 2.0 * N * H * H * Cin * Cout * R * R
+        print(f"conv_wgrad N{N} {H}x{H} {Cin}->{Cout} k{R}: {t * 1e6:8.1f} us  {fl / t / 1e12:7.1f} TFLOP/s", flush=True)
+if "gate" in which:
+    M = 10
+    cb = (torch.rand(M, 256) > 0.5).float().to(dev)
+    packed = ops.PackedCodebook(cb)
+    labels = torch.randint(0, M, (N,), device=dev).to(torch.int32)
+    gamma, beta = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    for (H, up) in [(32, False), (16, True), (16, False), (8, True)]:
+        x = torch.randn(N, H, H, 256, device=dev).to(torch.bfloat16)
+        T = x.numel() * 2
+        t = timeit(lambda: ops.bn_stats(x))
+        print(f"bn_stats {H}x{H}: {t * 1e6:7.1f} us {T / t / 1e9:7.0f} GB/s", flush=True)
+        mean, rstd = ops.bn_stats(x)
+        fl = GATE_BN | GATE_RELU | GATE_MASK | (GATE_UP2 if up else 0)
+        t = timeit(lambda: ops.gate_fwd(x, fl, labels, packed, mean, rstd, gamma, beta, up))
+        by = T * ((1 + 4 + 1) if up else 2)
+        print(f"gate_fwd {H}x{H} up{int(up)} raw{int(up)}: {t * 1e6:7.1f} us {by / t / 1e9:7.0f} GB/s", flush=True)
+        f = 2 if up else 1
+        dy = torch.randn(N, H * f, H * f, 256, device=dev).to(torch.bfloat16)
+        draw = torch.randn_like(x) if up else None
+        t = timeit(lambda: ops.gate_bwd(dy, draw, x, fl, labels, packed, mean, rstd, gamma, beta))
+        by = 2 * (dy.numel() * 2 + T) + T + (T if up else 0)
+        print(f"gate_bwd {H}x{H} up{int(up)} (reduce+apply): {t * 1e6:7.1f} us {by / t / 1e9:7.0f} GB/s", flush=True)
+    x = torch.randn(N, 16, 16, 128, device=dev).to(torch.bfloat16)
+    cb = (torch.rand(M, 128) > 0.5).float().to(dev)
+    packed = ops.PackedCodebook(cb)
+    t = timeit(lambda: ops.gate_fwd(x, GATE_RELU | GATE_MASK, labels, packed, None, None, None, None, True))
+    print(f"relu_gate 16x16 C128 +raw: {t * 1e6:7.1f} us {x.numel() * 2 * 3 / t / 1e9:7.0f} GB/s", flush=True)
