@@ -131,8 +131,10 @@ int mcgm_sn_power_iter(int n_layers, const float* const* W_host, const int* K_ho
                        const long* state_off_host, int do_iter, float eps, void* stream);
 /* dW = (dW_bar - <dW_bar, W_bar> u v^T) / sigma.  dW_bar is [K][row_stride] fp32 whose rows hold
  * R*S*C entries in (r,s,c) order (krsc = 1, the layout of mcgm_conv_wgrad) or (c,r,s) order. */
+size_t mcgm_sn_weight_bwd_workspace_bytes(void);
 int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const float* W_oihw,
-                       const float* sn_state, int K, int C, int R, int S, float* dW_oihw, void* stream);
+                       const float* sn_state, int K, int C, int R, int S, float* dW_oihw,
+                       void* workspace, void* stream);
 /* bf16 [K][row_stride] <- W[k,c,r,s] * inv_sigma with columns in (r,s,c) order, zero padded: the
  * weight matrix of the im2col'd thin convolution (row_stride = 64). */
 int mcgm_pack_weight_padded(const float* w_oihw, int K, int C, int R, int S, const float* inv_sigma,
@@ -155,7 +157,8 @@ int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype,
  * NHWC tensors: dw[k,r,s,c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-pad,w+s-pad,c].
  * x [N,H,W,Cin] bf16, dy [N,H,W,Cout] bf16 (Cin,Cout % 64 == 0), dw fp32 KRSC.
  * Deterministic split-K: partials in workspace, fixed-order reduction.
- * dbias (optional) = sum over pixels of dy. */
+ * dbias (optional) = sum over pixels of dy, accumulated on the tensor cores in the same
+ * kernel (dY^T x ones) — dy is read from HBM once. */
 size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S);
 int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias,
                     int N, int H, int W, int Cin, int Cout, int R, int S,

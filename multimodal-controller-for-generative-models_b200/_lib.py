@@ -36,8 +36,9 @@ SIGNATURES = {
     "mcgm_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mcgm_sn_power_iter": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_float, c_void_p]),
+    "mcgm_sn_weight_bwd_workspace_bytes": (c_size_t, []),
     "mcgm_sn_weight_bwd": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p]),
     "mcgm_pack_weight_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mcgm_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

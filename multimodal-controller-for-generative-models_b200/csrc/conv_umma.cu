@@ -378,8 +378,9 @@ struct WgradParams {
   int total_kb, splits, kb_per_split;
   int cout_tiles, cin_tiles, taps, tap_groups;
   uint64_t desc_templ;
-  uint32_t idesc;
+  uint32_t idesc, idesc_bias;
   float* partial;                       // [splits][Cout*R*S*Cin]
+  float* bias_partial;                  // [splits][Cout] or nullptr
 };
 
 // NT = number of filter taps one CTA accumulates against the SAME dY tile (A operand):
@@ -388,10 +389,12 @@ template <int BN, int NT>
 struct WgCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + NT * kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
-  static constexpr int kTmemRaw = NT * BN;
+  static constexpr int kBiasCol = NT * BN;             // 16 extra accumulator columns: dY^T x ones = bias gradient
+  static constexpr int kTmemRaw = NT * BN + 16;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kOnesBytes = 8192;              // an all-ones [64 k][64 mn] bf16 operand tile
+  static constexpr int kStages = ((196608 - kOnesBytes) / kStageBytes) > 8 ? 8 : ((196608 - kOnesBytes) / kStageBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 256;
 };
 
 template <int BN, int NT>
@@ -401,7 +404,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   using Cfg = WgCfg<BN, NT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t ones_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = ones_base + Cfg::kOnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::kStages);
@@ -418,6 +422,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
   const int ntaps = min(NT, p.taps - tap0);          // the last group of a 3x3 kernel holds one tap
   const int co0 = cout_t * kTileM, ci0 = cin_t * BN;
+  // the CTAs of tap group 0 / cin tile 0 also accumulate dbias = dY^T x ones (one extra N=16 MMA per k step)
+  const bool do_bias = p.bias_partial != nullptr && tap0 == 0 && cin_t == 0;
+  if (do_bias && warp >= 2) {
+    const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
+    for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_base + 16u * i), "r"(ones2) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_dy);
@@ -485,6 +497,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                        acc_on | (uint32_t)(k != 0));
           }
         }
+        if (do_bias) {
+          const uint64_t odesc = smem_desc(p.desc_templ, ones_base);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * 128), odesc, p.idesc_bias,
+                     acc_on | (uint32_t)(k != 0));
+        }
         umma_commit(empty_bar(stage));
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -496,6 +515,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const size_t per_split = (size_t)p.Cout * p.taps * p.Cin;
+    if (do_bias) {
+      uint32_t acc[32];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kBiasCol, acc);
+      tmem_ld_wait();
+      if (co < p.Cout) p.bias_partial[(size_t)split * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
+    }
     for (int q = 0; q < ntaps; ++q) {
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + q * BN;
       float* dst = p.partial + (size_t)split * per_split + ((size_t)co * p.taps + tap0 + q) * p.Cin + ci0;
@@ -526,7 +551,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/,
-                                    float* __restrict__ dw) {
+                                    float* __restrict__ dw, const float* __restrict__ bias_partial, int Cout,
+                                    float* __restrict__ dbias) {
+  if (dbias && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+      float a = 0.0f;
+      for (int s = 0; s < splits; ++s) a += bias_partial[(size_t)s * Cout + c];
+      dbias[c] = a;
+    }
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<const float4*>(partial)[i];
     for (int s = 1; s < splits; ++s) {
@@ -535,39 +568,6 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
     }
     reinterpret_cast<float4*>(dw)[i] = a;
   }
-}
-
-// column sums of a bf16 [P, C] matrix (bias gradient): partial per block, then fixed-order finish
-__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long P, int C, float* __restrict__ partial) {
-  const int CG = C / 8;
-  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, PL = blockDim.x / CG;
-  float s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = 0.f;
-  for (long q = (long)blockIdx.x * PL + pl; q < P; q += (long)gridDim.x * PL) {
-    Vec<__nv_bfloat16> v;
-    v.load(x + q * C + cg * 8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] += v.v[i];
-  }
-  extern __shared__ float sm[];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sm[pl * C + cg * 8 + i] = s[i];
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int l = 0; l < PL; ++l) a += sm[l * C + c];
-    partial[(size_t)blockIdx.x * C + c] = a;
-  }
-}
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= C) return;
-  double S = 0.0;
-  for (int b = lane; b < nblocks; b += 32) S += (double)partial[(size_t)b * C + warp];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
-  if (lane == 0) out[warp] = (float)S;
 }
 
 // ---------------------------------------------------------------------------
@@ -787,11 +787,11 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = out_dtype == MCGM_F32;
-  // two M tiles per CTA when there is enough work to keep every SM busy with pairs
+  // two M tiles per CTA (halves the weight bytes per MMA) whenever single tiles would need > 1 wave
   const int m_tiles = p.total_tiles / p.n_tiles;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const bool pair = g_knobs.mt2 && (((m_tiles + 1) / 2) * p.n_tiles >= sms);
+  const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles > sms);   // more than one wave of single tiles
   switch (BN) {
     case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(mx, mw, p, f32, st) : launch_fwd_t<256, 1>(mx, mw, p, f32, st);
     case 128: return pair ? launch_fwd_t<128, 2>(mx, mw, p, f32, st) : launch_fwd_t<128, 1>(mx, mw, p, f32, st);
@@ -805,7 +805,7 @@ extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, 
   WgradPlan pl;
   if (plan_wgrad(N, H, W, Cin, Cout, R, S, &pl)) return 0;
   size_t bytes = (size_t)pl.splits * pl.per_split * sizeof(float);
-  bytes += (size_t)148 * 4 * Cout * sizeof(float);  // bias-gradient partials
+  bytes += (size_t)pl.splits * Cout * sizeof(float);  // bias-gradient partials
   return bytes;
 }
 
@@ -821,7 +821,9 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
   p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
   p.desc_templ = make_smem_desc_hi_lbo(g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1);
+  p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1);
   p.partial = (float*)workspace;
+  p.bias_partial = dbias ? p.partial + (size_t)pl.splits * pl.per_split : nullptr;
 
   CUtensorMap mdy, mx;
   const uint32_t box[4] = {64u, (uint32_t)pl.KW, (uint32_t)pl.KH, (uint32_t)pl.KN};
@@ -845,20 +847,7 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
   const size_t n4 = pl.per_split / 4;
   long blocks = (long)((n4 + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw);
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial, Cout, dbias);
   MCGM_LAUNCH_CHECK();
-  if (dbias) {
-    if (Cout % 8 || (Cout / 8) > 256 || 256 % (Cout / 8))
-      return fail(MCGM_E_UNSUPPORTED, "conv_wgrad: dbias needs Cout/8 dividing 256");
-    float* bpart = p.partial + (size_t)pl.splits * pl.per_split;
-    const int CG = Cout / 8, PL = 256 / CG;
-    const long P = (long)N * H * W;
-    long nb = (P + PL - 1) / PL;
-    if (nb > 148 * 4) nb = 148 * 4;
-    colsum_partial_kernel<<<(int)nb, 256, (size_t)PL * Cout * sizeof(float), st>>>((const __nv_bfloat16*)dy, P, Cout, bpart);
-    MCGM_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(bpart, (int)nb, Cout, dbias);
-    MCGM_LAUNCH_CHECK();
-  }
   return 0;
 }

@@ -106,29 +106,45 @@ sn_power_iter_kernel(const SnBatch b, float* __restrict__ state, int do_iter, fl
 
 // dW[k,c,r,s] = (dWbar[k,(r,s,c)] - s * u[k] * v[(c,r,s)]) * inv_sigma,  s = <dWbar, W> * inv_sigma
 // dWbar is [K][row_stride] with the first R*S*C entries of a row in (r,s,c) order (KRSC), or in
-// (c,r,s) order when krsc == 0.  One CTA per layer call.
-__global__ void __launch_bounds__(kSnThreads)
-sn_weight_bwd_kernel(const float* __restrict__ dwbar, long row_stride, int krsc, const float* __restrict__ W,
-                     const float* __restrict__ st /*[inv_sigma | u | v]*/, int K, int C, int R, int S,
-                     float* __restrict__ dW) {
+// (c,r,s) order when krsc == 0.  Two launches of kSnBwdBlocks CTAs: per-block partial dot products,
+// then every block re-sums the partials in a fixed order (deterministic) and applies its slice.
+static constexpr int kSnBwdBlocks = 64;
+static constexpr int kSnBwdThreads = 256;
+
+__device__ __forceinline__ long sn_src_index(long o, int CRS, int C, int RS, long row_stride, int krsc) {
+  const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);   // o indexes OIHW
+  if (!krsc) return (long)k * row_stride + rem;
+  const int c = rem / RS, rs = rem - c * RS;
+  return (long)k * row_stride + (long)rs * C + c;
+}
+
+__global__ void __launch_bounds__(kSnBwdThreads)
+sn_bwd_dot_kernel(const float* __restrict__ dwbar, long row_stride, int krsc, const float* __restrict__ W,
+                  int K, int C, int RS, float* __restrict__ partial) {
   __shared__ float red[40];
-  const int CRS = C * R * S;
+  const int CRS = C * RS;
+  const long total = (long)K * CRS;
+  float acc = 0.0f;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x)
+    acc = fmaf(dwbar[sn_src_index(o, CRS, C, RS, row_stride, krsc)], W[o], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kSnBwdThreads)
+sn_bwd_apply_kernel(const float* __restrict__ dwbar, long row_stride, int krsc, const float* __restrict__ st,
+                    const float* __restrict__ partial, int nparts, int K, int C, int RS, float* __restrict__ dW) {
+  const int CRS = C * RS;
   const long total = (long)K * CRS;
   const float inv_sigma = st[0];
   const float* u = st + 1;
   const float* v = st + 1 + K;
-  auto src_index = [&](long o) -> long {   // o indexes OIHW: ((k*C + c)*R + r)*S + s
+  float s = 0.0f;
+  for (int i = 0; i < nparts; ++i) s += partial[i];
+  s *= inv_sigma;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
     const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);
-    if (!krsc) return (long)k * row_stride + rem;
-    const int c = rem / (R * S), rs = rem - c * (R * S);
-    return (long)k * row_stride + (long)rs * C + c;
-  };
-  float acc = 0.0f;
-  for (long o = threadIdx.x; o < total; o += blockDim.x) acc = fmaf(dwbar[src_index(o)], W[o], acc);
-  const float s = block_sum(acc, red) * inv_sigma;
-  for (long o = threadIdx.x; o < total; o += blockDim.x) {
-    const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);
-    dW[o] = (dwbar[src_index(o)] - s * u[k] * v[rem]) * inv_sigma;
+    dW[o] = (dwbar[sn_src_index(o, CRS, C, RS, row_stride, krsc)] - s * u[k] * v[rem]) * inv_sigma;
   }
 }
 
@@ -180,11 +196,22 @@ extern "C" int mcgm_sn_power_iter(int n_layers, const float* const* W_host, cons
   return 0;
 }
 
+extern "C" size_t mcgm_sn_weight_bwd_workspace_bytes(void) { return kSnBwdBlocks * sizeof(float); }
+
 extern "C" int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const float* W_oihw,
-                                  const float* sn_state, int K, int C, int R, int S, float* dW_oihw, void* stream) {
+                                  const float* sn_state, int K, int C, int R, int S, float* dW_oihw,
+                                  void* workspace, void* stream) {
   MCGM_CHECK_ARG(dwbar && W_oihw && sn_state && dW_oihw && K > 0 && C > 0 && R > 0 && S > 0 && row_stride >= (long)C * R * S,
                  "sn_weight_bwd: bad arguments");
-  sn_weight_bwd_kernel<<<1, kSnThreads, 0, (cudaStream_t)stream>>>(dwbar, row_stride, krsc, W_oihw, sn_state, K, C, R, S, dW_oihw);
+  MCGM_CHECK_ARG(workspace, "sn_weight_bwd: needs a workspace of mcgm_sn_weight_bwd_workspace_bytes()");
+  const long total = (long)K * C * R * S;
+  int blocks = (int)((total + kSnBwdThreads - 1) / kSnBwdThreads);
+  if (blocks > kSnBwdBlocks) blocks = kSnBwdBlocks;
+  float* partial = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  sn_bwd_dot_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, W_oihw, K, C, R * S, partial);
+  MCGM_LAUNCH_CHECK();
+  sn_bwd_apply_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, sn_state, partial, blocks, K, C, R * S, dW_oihw);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -216,29 +216,42 @@ __global__ void kern_grad_finalize_kernel(const float* __restrict__ partial, int
 //   kernel grads   : dWmat = dY^T x U             (conv_wgrad 1x1)
 //   thin_from_wide : T = wide x Wmat^T (fp32 [P, CT]);  thin[p, j] = sum_t T[p + off(t), t*Ct + j]
 // ---------------------------------------------------------------------------
-__global__ void thin_im2col_kernel(const float* __restrict__ thin, __nv_bfloat16* __restrict__ U, int N, int H,
-                                   int W, int Ct, int R, int S, int sgn, int KU) {
+__global__ void __launch_bounds__(256)
+thin_im2col_kernel(const float* __restrict__ thin, __nv_bfloat16* __restrict__ U, int N, int H,
+                   int W, int Ct, int R, int S, int sgn, int KU, PixDiv dw, PixDiv dhw) {
+  // column -> (row offset, column offset, channel) tables: no division in the hot loop
+  __shared__ signed char tdr[128], tds[128], tj[128];
   const int pad = (R - 1) / 2, T = R * S;
-  const int groups = KU / 8;
-  const long total = (long)N * H * W * groups;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int gidx = (int)(e % groups);
-    const long p = e / groups;
-    const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
+  for (int col = threadIdx.x; col < KU; col += blockDim.x) {
+    if (col < T * Ct) {
+      const int t = col / Ct, r = t / S;
+      tdr[col] = (signed char)(sgn * (r - pad));
+      tds[col] = (signed char)(sgn * (t - r * S - pad));
+      tj[col] = (signed char)(col - t * Ct);
+    } else {
+      tj[col] = -1;
+    }
+  }
+  __syncthreads();
+  const uint32_t groups = KU / 8, used = (T * Ct + 7) / 8;
+  const uint32_t HW = (uint32_t)H * W;
+  const uint32_t total = (uint32_t)N * HW * groups;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const uint32_t p = e / groups, gidx = e - p * groups;
     Vec<__nv_bfloat16> o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int col = gidx * 8 + i;
-      float v = 0.0f;
-      if (col < T * Ct) {
-        const int t = col / Ct, j = col - t * Ct;
-        const int r = t / S, s = t - r * S;
-        const int hh = h + sgn * (r - pad), ww = w + sgn * (s - pad);
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(thin + (((long)n * H + hh) * W + ww) * Ct + j);
+    for (int i = 0; i < 8; ++i) o.v[i] = 0.0f;
+    if (gidx < used) {
+      const uint32_t n = dhw.div(p), hw = p - n * HW, h = dw.div(hw), w = hw - h * W;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = gidx * 8 + i, j = tj[col];
+        const int hh = (int)h + tdr[col], ww = (int)w + tds[col];
+        if (j >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W)
+          o.v[i] = __ldg(thin + ((size_t)(n * H + hh) * W + ww) * Ct + j);
       }
-      o.v[i] = v;
     }
-    o.store(U + p * KU + gidx * 8);
+    o.store(U + (size_t)p * KU + gidx * 8);
   }
 }
 
@@ -361,12 +374,14 @@ extern "C" int mcgm_thin_kern_grad(const float* thin, const void* wide, float* d
 extern "C" int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, int W, int Ct, int R, int S,
                                 int flip, int KU, void* stream) {
   MCGM_CHECK_ARG(thin && U_bf16 && N > 0 && H > 0 && W > 0, "thin_im2col: bad arguments");
-  MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && KU % 8 == 0 && R * S * Ct <= KU, "thin_im2col: Ct=%d R=%d S=%d do not fit KU=%d", Ct, R, S, KU);
+  MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && KU % 8 == 0 && KU <= 128 && R * S * Ct <= KU, "thin_im2col: Ct=%d R=%d S=%d do not fit KU=%d", Ct, R, S, KU);
   const long total = (long)N * H * W * (KU / 8);
+  MCGM_CHECK_ARG(total < (1L << 32), "thin_im2col: tensor too large");
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   thin_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(thin, (__nv_bfloat16*)U_bf16, N, H, W, Ct, R, S,
-                                                                   flip ? -1 : 1, KU);
+                                                                   flip ? -1 : 1, KU, PixDiv::make((uint32_t)W),
+                                                                   PixDiv::make((uint32_t)(H * W)));
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -247,8 +247,10 @@ def sn_weight_bwd(dwbar, row_stride, krsc, w, state):
     _check_cuda(w, state)
     K, C, R, S = w.shape if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1)
     dw = torch.empty_like(w)
+    ws = _workspace("sn_bwd", _lib.query("mcgm_sn_weight_bwd_workspace_bytes"), w.device)
     _lib.call("mcgm_sn_weight_bwd", dwbar.data_ptr(), row_stride, int(krsc), w.data_ptr(), state.data_ptr(),
-              K, C, R, S, dw.data_ptr(), _stream())
+              K, C, R, S, dw.data_ptr(), ws.data_ptr(), _stream())
+    _lib.launch_count += 1
     return dw
 
 
@@ -303,7 +305,7 @@ def conv_wgrad(x, dy, R, S, want_bias=True):
     ev = _prof_begin()
     _lib.call("mcgm_conv_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, R, S,
               ws.data_ptr(), _stream())
-    _lib.launch_count += 3 if want_bias else 1
+    _lib.launch_count += 1                       # wgrad + split-K / bias reduce
     _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S)
     return dw, db
 
