@@ -162,12 +162,12 @@ def run_native(args):
     torch.manual_seed(0)                      # identical weights / codebooks / SN vectors on every rank
     model = models.mcgan().to(dev)
     model.train(True)
-    use_graph = world == 1 and not args.no_graph     # multi-GPU: eager step, all-reduce overlapped with backward
-    opt = train_gan.make_optimizers(model, capturable=use_graph)
+    use_graph = not args.no_graph                    # --no-graph: eager step, all-reduce overlapped with backward
+    opt = train_gan.make_optimizers(model, capturable=use_graph and world == 1)
     reducers = None
     if world > 1:
-        reducers = {"generator": train_gan.GradAllReduce(model.generator),
-                    "discriminator": train_gan.GradAllReduce(model.discriminator)}
+        reducers = {"generator": train_gan.GradAllReduce(model.generator, overlap=not use_graph),
+                    "discriminator": train_gan.GradAllReduce(model.discriminator, overlap=not use_graph)}
     B = args.batch
     g = torch.Generator().manual_seed(1 + rank)            # per-rank data shard
     n_host = 4
@@ -178,7 +178,10 @@ def run_native(args):
     host_loss = torch.zeros(3, dtype=torch.float32).pin_memory()
     torch.manual_seed(100 + rank)                          # z stream
 
-    graphed = train_gan.GraphedTrainStep(model, opt, B) if use_graph else None
+    graphed = None
+    if use_graph:
+        graphed = (train_gan.GraphedTrainStep(model, opt, B) if world == 1
+                   else train_gan.GraphedDDPTrainStep(model, opt, reducers, B))
 
     def run_step(batch):
         if graphed is not None:
@@ -222,10 +225,10 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        for i in range(2):                  # nvidia-smi needs ~0.3 s before its first sample
-            step_resident(i)
-        torch.cuda.synchronize()
-        sampler.rows.clear()
+    for i in range(2):                      # every rank (the step holds collectives); gives nvidia-smi
+        step_resident(i)                    # the ~0.3 s it needs before its first sample
+    torch.cuda.synchronize()
+    sampler.rows.clear()
     ms, launches = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e(0)
@@ -287,7 +290,9 @@ def run_native(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B,
                            "parallelism": f"dp{world}", "schedule": "5D+1G per step",
-                           "launch": "one CUDA graph per iteration" if use_graph else "eager, all-reduce overlapped",
+                           "launch": (("one CUDA graph per iteration" if world == 1 else
+                                       "CUDA graph per D/G forward+backward, NCCL all-reduce + Adam between graphs")
+                                      if use_graph else "eager, bucketed all-reduce overlapped with backward"),
                            "l2": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
                            "kernel_profile": "one extra iteration after the timed region, CUDA events per native call"},
                 "e2e": {"value": B * world / (ms_e2e / args.steps * 1e-3), "unit": "img/s",

@@ -93,13 +93,14 @@ def _labels_from_indicator(indicator):
 
 
 _pack_cache = {}
+_packs_force = False      # set while capturing re-playable graph segments: the cache check is capture-time only
 
 
 def _packs(weight):
     """bf16 (KRSC, flipped CRSK) copies of a parameter, cached until the parameter changes."""
     key = id(weight)
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1] is weight:
+    if hit is not None and hit[0] == weight._version and hit[1] is weight and not _packs_force:
         return hit[2]
     packs = ops.pack_weight(weight.detach())
     _pack_cache[key] = (weight._version, weight, packs)

@@ -41,8 +41,12 @@ class GradAllReduce:
     BatchNorm statistics stay per-rank, as with the reference's DataParallel replicas.
     """
 
-    def __init__(self, module, bucket_bytes=8 << 20, group=None):
+    def __init__(self, module, bucket_bytes=8 << 20, group=None, overlap=True):
+        """overlap=True: hook-driven bucketed all-reduce during backward (eager mode).
+        overlap=False: one all-reduce of the whole flat buffer in ``finish()`` — the form that is
+        captured inside a CUDA graph (the payload is 4-17 MB, i.e. tens of microseconds on NVLink)."""
         self.group = group
+        self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
         total = sum(p.numel() for p in self.params)
@@ -72,7 +76,7 @@ class GradAllReduce:
         self.pending = [0] * len(self.buckets)
         self.handles = []
         self.enabled = True
-        if self.world > 1:
+        if self.world > 1 and overlap:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
 
@@ -96,6 +100,10 @@ class GradAllReduce:
     def finish(self):
         if self.world == 1:
             return
+        if not self.overlap:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(self.world)
+            return
         # parameters that received no gradient this step (unused) still need their bucket reduced
         for b, (s, e, n) in enumerate(self.buckets):
             if self.pending[b] != n:
@@ -109,6 +117,24 @@ class GradAllReduce:
 def hinge_d(d_real, d_fake):
     """relu(1 - D(x)).mean() + relu(1 + D(G(z))).mean()   (src/train_gan.py:154)."""
     return F.relu(1.0 - d_real).mean() + F.relu(1.0 + d_fake).mean()
+
+
+def d_forward_backward(model, img, label, z):
+    """Forward + backward of one D update (src/train_gan.py:143-157); returns the hinge loss."""
+    d_x = model.discriminate(img, label)
+    generated = model.generate(label, z)
+    d_g = model.discriminate(generated.detach(), label)
+    d_loss = hinge_d(d_x, d_g)
+    d_loss.backward()
+    return d_loss
+
+
+def g_forward_backward(model, label, z):
+    """Forward + backward of one G update (src/train_gan.py:165-175); returns -D(G(z)).mean()."""
+    generated = model.generate(label, z)
+    g_loss = -model.discriminate(generated, label).mean()
+    g_loss.backward()
+    return g_loss
 
 
 def train_step(model, optimizer, input, z=None, reducers=None):
@@ -141,11 +167,7 @@ def train_step(model, optimizer, input, z=None, reducers=None):
         zero()
         if reducers is not None:
             reducers['generator'].enabled = False              # G receives no gradient in the D step
-        d_x = model.discriminate(img, label)
-        generated = model.generate(label, draw())
-        d_g = model.discriminate(generated.detach(), label)
-        d_loss = hinge_d(d_x, d_g)
-        d_loss.backward()
+        d_loss = d_forward_backward(model, img, label, draw())
         if reducers is not None:
             reducers['discriminator'].finish()
             reducers['generator'].enabled = True
@@ -154,9 +176,7 @@ def train_step(model, optimizer, input, z=None, reducers=None):
         zero()
         if reducers is not None:
             reducers['discriminator'].enabled = False          # D's grads are discarded by the next zero_grad
-        generated = model.generate(label, draw())
-        g_loss = -model.discriminate(generated, label).mean()
-        g_loss.backward()
+        g_loss = g_forward_backward(model, label, draw())
         if reducers is not None:
             reducers['generator'].finish()
             reducers['discriminator'].enabled = True
@@ -176,25 +196,29 @@ class GraphedTrainStep:
     input buffers.  Optimisers must be built with ``capturable=True``.
     """
 
-    def __init__(self, model, optimizer, batch_size, warmup=3):
+    def __init__(self, model, optimizer, batch_size, warmup=3, reducers=None, inject_noise=False):
         dev = next(model.parameters()).device
         shape = model.generator.data_shape
         self.img = torch.zeros(batch_size, *shape, device=dev)
         self.label = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.model, self.optimizer = model, optimizer
         batch = {'img': self.img, 'label': self.label}
+        # inject_noise: latent draws come from static buffers the caller fills (parity tests)
+        n_z = GAN_HYPER['iter']['discriminator'] + GAN_HYPER['iter']['generator']
+        self.z = ([torch.zeros(batch_size, model.latent_size, device=dev) for _ in range(n_z)]
+                  if inject_noise else None)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                train_step(model, optimizer, batch)
+                train_step(model, optimizer, batch, z=self.z, reducers=reducers)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
         c0 = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = train_step(model, optimizer, batch)
+            self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
         self.native_launches = _lib.launch_count - c0      # libmcgm kernels inside one replay
 
     def __call__(self, input):
@@ -202,5 +226,78 @@ class GraphedTrainStep:
         that are overwritten by the next call."""
         self.img.copy_(input['img'], non_blocking=True)
         self.label.copy_(input['label'], non_blocking=True)
+        if self.z is not None:
+            for dst, src in zip(self.z, input['z']):
+                dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        return self.out
+
+
+class GraphedDDPTrainStep:
+    """Data-parallel variant: the forward+backward of a D update and of a G update are captured
+    as two CUDA graphs (no collective inside a graph); after each replay the flat gradient buffer
+    is all-reduced over NCCL/NVLink and Adam steps eagerly.  Per iteration the host issues
+    6 graph launches + 6 all-reduces + 6 optimiser steps instead of ~6000 kernel launches.
+    Weight packing of G is forced inside the graphs (its cache check happens at capture time)."""
+
+    def __init__(self, model, optimizer, reducers, batch_size, warmup=2):
+        from .models import mcgan as _m
+        dev = next(model.parameters()).device
+        shape = model.generator.data_shape
+        self.img = torch.zeros(batch_size, *shape, device=dev)
+        self.label = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.model, self.optimizer, self.reducers = model, optimizer, reducers
+        self.n_d, self.n_g = GAN_HYPER['iter']['discriminator'], GAN_HYPER['iter']['generator']
+        latent = model.latent_size
+
+        def d_part():
+            reducers['discriminator'].zero_grad()
+            reducers['generator'].zero_grad()
+            return d_forward_backward(model, self.img, self.label, torch.randn(batch_size, latent, device=dev))
+
+        def g_part():
+            reducers['discriminator'].zero_grad()
+            reducers['generator'].zero_grad()
+            return g_forward_backward(model, self.label, torch.randn(batch_size, latent, device=dev))
+
+        for r in reducers.values():
+            if r.overlap:
+                raise ValueError('Not valid reducer: graph mode needs GradAllReduce(overlap=False)')
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                d_part()
+                g_part()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        _m._packs_force = True
+        try:
+            c0 = _lib.launch_count
+            self.graph_d = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_d):
+                self.d_loss = d_part()
+            c1 = _lib.launch_count
+            self.graph_g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_g, pool=self.graph_d.pool()):
+                self.g_loss = g_part()
+            c2 = _lib.launch_count
+        finally:
+            _m._packs_force = False
+        self.native_launches = (c1 - c0) * self.n_d + (c2 - c1) * self.n_g
+        self.out = {'loss_D': self.d_loss, 'loss_G': self.g_loss, 'loss': None}
+
+    def __call__(self, input):
+        self.img.copy_(input['img'], non_blocking=True)
+        self.label.copy_(input['label'], non_blocking=True)
+        for _ in range(self.n_d):
+            self.graph_d.replay()
+            self.reducers['discriminator'].finish()
+            self.optimizer['discriminator'].step()
+        for _ in range(self.n_g):
+            self.graph_g.replay()
+            self.reducers['generator'].finish()
+            self.optimizer['generator'].step()
+        self.out['loss'] = (self.d_loss - self.g_loss).abs()
         return self.out

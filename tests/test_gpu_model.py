@@ -156,3 +156,33 @@ def test_config1_full_width_gradients_vs_oracle():
     print("config1 median gradient error:", errs[len(errs) // 2])
     assert errs[0][0] < GRAD_TOL, errs[:6]
     assert errs[len(errs) // 2][0] < GRAD_MEDIAN_TOL
+
+
+def test_graph_replay_equals_eager(golden):
+    """The CUDA-graph captured iteration is the same computation as the eager one: from identical
+    weights, optimiser state, data and injected noise both must land on the same parameters."""
+    import copy
+    from mcgm_b200 import train_gan
+    case = golden["cases"]["tiny_cifar"]
+    arr = load_arrays("tiny_cifar")
+    m_eager = build_model(case, device="cuda").to("cuda")
+    m_graph = copy.deepcopy(m_eager)
+    m_eager.train(True)
+    m_graph.train(True)
+    batch = {"img": arr["img"].cuda(), "label": arr["label"].cuda(), "z": [z.cuda() for z in arr["zs"]]}
+    opt_g = train_gan.make_optimizers(m_graph, capturable=True)
+    graphed = train_gan.GraphedTrainStep(m_graph, opt_g, case["batch"], warmup=1, inject_noise=True)
+    # the warm-up + capture iterations already trained m_graph on zeros: restart both from one state
+    m_graph.load_state_dict(m_eager.state_dict())
+    opt_e = train_gan.make_optimizers(m_eager, capturable=True)
+    for o in opt_g.values():
+        for st in o.state.values():
+            st["step"].zero_(); st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+    for _ in range(2):
+        out_e = train_gan.train_step(m_eager, opt_e, batch, z=batch["z"])
+        out_g = graphed(batch)
+    assert abs(float(out_e["loss_D"]) - float(out_g["loss_D"])) < 1e-4
+    assert abs(float(out_e["loss_G"]) - float(out_g["loss_G"])) < 1e-4
+    sd_e, sd_g = m_eager.state_dict(), m_graph.state_dict()
+    worst = max(rel_err(sd_g[k].float().cpu(), sd_e[k].float().cpu()) for k in sd_e if sd_e[k].is_floating_point())
+    assert worst < 1e-4, worst
