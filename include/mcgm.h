@@ -33,6 +33,12 @@ extern "C" {
 #define MCGM_F32 0
 #define MCGM_BF16 1
 
+/* convolution kinds of the *_ex entry points */
+#define MCGM_CONV_S1 0        /* stride 1, R x S in {1x1, 3x3}, pad (R-1)/2                         */
+#define MCGM_CONV_S2K4 1      /* 4x4 kernel, stride 2, pad 1: output = input / 2  (mcvae.py:41-49)   */
+#define MCGM_CONV_PHASE2 2    /* 4 output phases x 2x2 taps: output = 2 x input.  Nearest-up2 -> Conv3x3
+                                 (mcgan.py:17-19) and ConvTranspose2d(4,2,1) (mcvae.py:87-92)          */
+
 #define MCGM_E_ARG (-1)      /* bad argument / unsupported shape */
 #define MCGM_E_CUDA (-2)     /* CUDA runtime / driver error */
 #define MCGM_E_UNSUPPORTED (-3)
@@ -153,6 +159,18 @@ int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype,
                   const int32_t* labels, const uint32_t* bits, int M,
                   int flags, void* stream);
 
+/* Generalised geometry on the same kernel (H, W are INPUT dims):
+ *   MCGM_CONV_S2K4  : w bf16 [Cout,4,4,Cin]; out[n,i,j] = sum_{p,q} x[n,2i+p-1,2j+q-1] . w[:,p,q,:]
+ *                     (TMA traversal stride 2 gathers the strided pixels; no im2col, no space-to-depth)
+ *   MCGM_CONV_PHASE2: w bf16 [4 phases (ph*2+pw)][Cout][2][2][Cin];
+ *                     out[n,2i+ph,2j+pw] = sum_{a,b} x[n,i+a-1+ph,j+b-1+pw] . w[ph*2+pw,:,a,b,:]
+ *                     — 2.25x fewer MACs than convolving the materialised upsampled tensor. */
+int mcgm_conv_fwd_ex(int kind, const void* x, const void* w, void* out, int out_dtype,
+                     int N, int H, int W, int Cin, int Cout,
+                     const float* bias, const void* res, const void* aux,
+                     const int32_t* labels, const uint32_t* bits, int M,
+                     int flags, void* stream);
+
 /* ---- weight gradient, tcgen05 + TMA with MN-major operands straight from the
  * NHWC tensors: dw[k,r,s,c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-pad,w+s-pad,c].
  * x [N,H,W,Cin] bf16, dy [N,H,W,Cout] bf16 (Cin,Cout % 64 == 0), dw fp32 KRSC.
@@ -163,6 +181,14 @@ size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, i
 int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias,
                     int N, int H, int W, int Cin, int Cout, int R, int S,
                     void* workspace, void* stream);
+
+/* Generalised geometry (H, W = dims of X; dw is fp32 [Cout][16 taps (p*4+q)][Cin]):
+ *   MCGM_CONV_S2K4  : dy [N,H/2,W/2,Cout]; dw[k,p,q,c] = sum dy[n,i,j,k] * x[n,2i+p-1,2j+q-1,c]
+ *   MCGM_CONV_PHASE2: dy [N,2H,2W,Cout];   dw[k,p,q,c] = sum dy[n,2i+p-1,2j+q-1,k] * x[n,i,j,c]
+ *                     (phase ph, tap a of the forward weight is p = 3 - 2a - ph; same for q). */
+size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int N, int H, int W, int Cin, int Cout);
+int mcgm_conv_wgrad_ex(int kind, const void* x, const void* dy, float* dw, float* dbias,
+                       int N, int H, int W, int Cin, int Cout, void* workspace, void* stream);
 
 /* ---- thin convolutions: one side has <= 4 channels (RGB image side of
  * Conv2d(3,128,...) mcgan.py:77,87 and Conv2d(256,3,3,1,1) mcgan.py:59).

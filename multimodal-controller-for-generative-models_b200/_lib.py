@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmcgm.so")
 F32, BF16 = 0, 1
 GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK = 1, 2, 4, 8
 EPI_BIAS, EPI_RES, EPI_RES_UP2, EPI_RELU, EPI_MASK, EPI_TANH, EPI_POSMASK = 1, 2, 4, 8, 16, 32, 64
+CONV_S1, CONV_S2K4, CONV_PHASE2 = 0, 1, 2
 
 # name -> (restype, argtypes); every symbol of include/mcgm.h
 SIGNATURES = {
@@ -42,6 +43,11 @@ SIGNATURES = {
     "mcgm_pack_weight_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mcgm_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcgm_conv_fwd_ex": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcgm_conv_wgrad_ex_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mcgm_conv_wgrad_ex": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p]),
     "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mcgm_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p]),

@@ -52,9 +52,9 @@ struct MapKey {
   const void* ptr;
   uint64_t d[4];
   uint32_t b[4];
-  int rank;
+  int rank, estride;
   bool operator==(const MapKey& o) const {
-    if (ptr != o.ptr || rank != o.rank) return false;
+    if (ptr != o.ptr || rank != o.rank || estride != o.estride) return false;
     for (int i = 0; i < 4; ++i)
       if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
     return true;
@@ -62,19 +62,23 @@ struct MapKey {
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)k.rank * 0x9e3779b97f4a7c15ull;
+    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride) * 0x9e3779b97f4a7c15ull;
     for (int i = 0; i < 4; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
     return h;
   }
 };
 
-// bf16 tensor, dims innermost-first, dense strides, 128B swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+// bf16 tensor, dims innermost-first, dense strides, 128B swizzle, zero OOB fill.  `estride` is the
+// TMA traversal stride of the two spatial dims of a 4-D NHWC map (1, or 2 for stride-2 gathers): a
+// box of b elements then lands b/estride elements in shared memory.
+static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box,
+                     int estride = 1) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{};
   key.ptr = ptr;
   key.rank = rank;
+  key.estride = estride;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   {
     std::lock_guard<std::mutex> lock(mu);
@@ -83,13 +87,25 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
   }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // The encode is a DRIVER call and needs a current context on the calling thread.  An autograd
+  // worker thread may reach this point before any runtime call bound one: bind the context of the
+  // device that owns `ptr` once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+      MCGM_CUDA(cudaSetDevice(attr.device));
+      MCGM_CUDA(cudaFree(0));
+    }
+    ctx_bound = true;
+  }
   cuuint64_t gdim[4], gstride[3];
   cuuint32_t bdim[4], estr[4];
   uint64_t stride = 2;  // bytes
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = (rank == 4 && (i == 1 || i == 2)) ? (cuuint32_t)estride : 1u;
     stride *= dims[i];
     if (i < rank - 1) gstride[i] = stride;
   }
@@ -129,10 +145,19 @@ static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                       // bf16 elements = 128 B rows
 static constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
 
+static constexpr int kMaxTaps = 16;
+
+// Geometry of the generalised forward conv.  M tiles are laid on a TILE GRID (Hg x Wg per image):
+//   plain stride-1 conv   : grid = output = input, taps = R*S with offsets (r-pad, s-pad)
+//   stride-2 conv (IS = 2): grid = output; input pixel of tap t = 2*grid + (dh,dw)   (TMA traversal stride 2)
+//   phase conv  (PH = 4, OS = 2): grid = input; output pixel = 2*grid + (ph,pw); each phase has its own
+//       2x2 taps and weight rows — nearest-up2 followed by conv3x3, and ConvTranspose2d(4,2,1).
 struct ConvFwdParams {
-  int N, H, W, Cin, Cout, R, S, pad;
+  int N, Hg, Wg, Ho, Wo, Cin, Cout;
+  int IS, OS, PH, T;                         // input traversal stride, output scale, phases, taps per phase
+  signed char tap_dh[4 * kMaxTaps], tap_dw[4 * kMaxTaps];   // [phase][tap]
   int TW, TH, TN, tiles_w, tiles_h;
-  int n_tiles, total_tiles;
+  int n_tiles, m_super, total_tiles;
   int kpt, num_kb;
   uint64_t desc_templ;
   uint32_t idesc;
@@ -175,7 +200,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   }
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
     long rpix = pix;
-    if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+    if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
     const __nv_bfloat16* rp = p.res + rpix * p.Cout + col0;
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
@@ -274,27 +299,29 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // ===== TMA producer =====
       int stage = 0, phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt0 = (t / p.n_tiles) * MT;
-        const int cout0 = nt * BN;
+        const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
+        const int mt0 = ms * MT;
+        const int wrow0 = ph * p.Cout + nt * BN;             // weight rows of this phase / channel slab
         int w0[MT], h0[MT], n0[MT];
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
           const int mt = mt0 + j;
-          w0[j] = (mt % p.tiles_w) * p.TW;
-          h0[j] = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+          w0[j] = (mt % p.tiles_w) * p.TW * p.IS;
+          h0[j] = ((mt / p.tiles_w) % p.tiles_h) * p.TH * p.IS;
           n0[j] = (mt / tiles_per_img_block) * p.TN;       // past the batch for a ragged last pair: TMA zero-fills
         }
-        int tap = 0, cb = 0, r = 0, s = 0;
+        int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int dh = p.tap_dh[ph * kMaxTaps + tap], dw = p.tap_dw[ph * kMaxTaps + tap];
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int j = 0; j < MT; ++j)
-            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kBlockK, w0[j] + s - p.pad, h0[j] + r - p.pad, n0[j]);
-          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, cout0);
+            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kBlockK, w0[j] + dw, h0[j] + dh, n0[j]);
+          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, wrow0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-          if (++cb == p.kpt) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+          if (++cb == p.kpt) { cb = 0; ++tap; }
         }
       }
     }
@@ -333,18 +360,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
-      const int nt = t % p.n_tiles, mt0 = (t / p.n_tiles) * MT;
+      const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
+      const int mt0 = ms * MT;
       const int cout0 = nt * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
         const int mt = mt0 + j;
-        const int w = (mt % p.tiles_w) * p.TW + tw;
-        const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+        const int wg = (mt % p.tiles_w) * p.TW + tw;
+        const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
         const int n = (mt / tiles_per_img_block) * p.TN + tn;
-        const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-        const long pix = ((long)n * p.H + h) * p.W + w;
+        const bool valid = (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
+        const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
+        const long pix = ((long)n * p.Ho + h) * p.Wo + w;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + j * BN;
         constexpr int CW = BN < 32 ? BN : 32;
 #pragma unroll 1
@@ -372,15 +401,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // ---------------------------------------------------------------------------
 // wgrad kernel: one (cout tile, cin tile, tap, k-split) work item per CTA
 // ---------------------------------------------------------------------------
+// Generalised weight gradient: k-blocks are 64-pixel boxes of a GRID (Hg x Wg per image);
+//   dY pixel of tap t = AS*grid + (a_dh,a_dw)[t],  X pixel of tap t = BS*grid + (b_dh,b_dw)[t]
+//   stride-1 conv : AS = BS = 1, a = 0, b = (r-pad, s-pad)
+//   4x4 stride-2  : grid = dY grid, AS = 1, a = 0; BS = 2, b = (p-1, q-1)            (16 taps)
+//   phase conv    : grid = X grid,  AS = 2, a = (p-1, q-1); BS = 1, b = 0            (16 taps)
 struct WgradParams {
-  int N, H, W, Cin, Cout, R, S, pad;
-  int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 pixels
+  int N, Cin, Cout;
+  int AS, BS;
+  signed char a_dh[kMaxTaps], a_dw[kMaxTaps], b_dh[kMaxTaps], b_dw[kMaxTaps];
+  int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 grid pixels
   int total_kb, splits, kb_per_split;
   int cout_tiles, cin_tiles, taps, tap_groups;
   uint64_t desc_templ;
   uint32_t idesc, idesc_bias;
   float* partial;                       // [splits][Cout*R*S*Cin]
-  float* bias_partial;                  // [splits][Cout] or nullptr
+  float* bias_partial;                  // [splits][bias_slots][Cout] or nullptr
+  int bias_taps[4], bias_slots;         // taps whose dY pixels tile dY exactly once (stride-2 dY: 4 parity classes)
 };
 
 // NT = number of filter taps one CTA accumulates against the SAME dY tile (A operand):
@@ -423,7 +460,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const int ntaps = min(NT, p.taps - tap0);          // the last group of a 3x3 kernel holds one tap
   const int co0 = cout_t * kTileM, ci0 = cin_t * BN;
   // the CTAs of tap group 0 / cin tile 0 also accumulate dbias = dY^T x ones (one extra N=16 MMA per k step)
-  const bool do_bias = p.bias_partial != nullptr && tap0 == 0 && cin_t == 0;
+  int bias_slot = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < p.bias_slots && p.bias_taps[i] == tap0) bias_slot = i;
+  const bool do_bias = p.bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
   if (do_bias && warp >= 2) {
     const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
     for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
@@ -448,13 +489,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
-      int dr[NT], ds[NT];                        // tap offsets of this CTA's taps (registers: loops are unrolled)
+      int dr[NT], ds[NT];                        // X-side tap offsets of this CTA's taps (registers: loops are unrolled)
 #pragma unroll
       for (int q = 0; q < NT; ++q) {
         const int tap = min(tap0 + q, p.taps - 1);
-        dr[q] = tap / p.S - p.pad;
-        ds[q] = tap % p.S - p.pad;
+        dr[q] = p.b_dh[tap];
+        ds[q] = p.b_dw[tap];
       }
+      const int ar = p.a_dh[tap0], ac = p.a_dw[tap0];   // dY-side offset (non-zero only when NT == 1)
       int bw = kb0 % p.kb_w, bh = (kb0 / p.kb_w) % p.kb_h, bn = kb0 / (p.kb_w * p.kb_h);
       const uint32_t tx_bytes = kABytes + ntaps * Cfg::kBBytes;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -464,14 +506,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int j = 0; j < kTileM / 64; ++j)
-          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0, h0, n0);
+          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           if (q < ntaps) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j,
-                          w0 + ds[q], h0 + dr[q], n0);
+                          w0 * p.BS + ds[q], h0 * p.BS + dr[q], n0);
           }
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -519,7 +561,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       uint32_t acc[32];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kBiasCol, acc);
       tmem_ld_wait();
-      if (co < p.Cout) p.bias_partial[(size_t)split * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
+      if (co < p.Cout)
+        p.bias_partial[((size_t)split * p.bias_slots + bias_slot) * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
     }
     for (int q = 0; q < ntaps; ++q) {
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + q * BN;
@@ -551,12 +594,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/,
-                                    float* __restrict__ dw, const float* __restrict__ bias_partial, int Cout,
-                                    float* __restrict__ dbias) {
+                                    float* __restrict__ dw, const float* __restrict__ bias_partial, int bias_rows,
+                                    int Cout, float* __restrict__ dbias) {
   if (dbias && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
       float a = 0.0f;
-      for (int s = 0; s < splits; ++s) a += bias_partial[(size_t)s * Cout + c];
+      for (int s = 0; s < bias_rows; ++s) a += bias_partial[(size_t)s * Cout + c];
       dbias[c] = a;
     }
   }
@@ -633,8 +676,8 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParam
   }
   int sms = sm_count();
   if (sms <= 0) return fail(MCGM_E_CUDA, "cannot query SM count");
-  const int m_tiles = p.total_tiles / p.n_tiles;
-  p.total_tiles = ((m_tiles + MT - 1) / MT) * p.n_tiles;
+  p.m_super = (p.m_super + MT - 1) / MT;           // in: M tiles per phase; out: CTA tiles per phase
+  p.total_tiles = p.m_super * p.n_tiles * p.PH;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mx, mw, p);
   MCGM_LAUNCH_CHECK();
@@ -663,21 +706,35 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
 
 struct WgradPlan {
   int BN, NT, tap_groups, cout_tiles, cin_tiles, taps, splits, kb_per_split, total_kb, KW, KH, KN;
+  int Hg, Wg, AS, BS;           // grid dims and traversal strides of dY / X
+  bool a_shift;                 // dY offsets differ per tap (phase conv): no tap pairing
   size_t per_split;  // floats
 };
 
-static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
+// H, W are the dims of X
+static int plan_wgrad(int kind, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
   if (Cin % 64 || Cout % 64) return fail(MCGM_E_UNSUPPORTED, "wgrad: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
-  if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "wgrad: only 1x1 and 3x3 kernels");
-  if (!pick_pixel_box(H, W, 64, &pl->KW, &pl->KH, &pl->KN))
-    return fail(MCGM_E_UNSUPPORTED, "wgrad: H=%d W=%d cannot be tiled into 64-pixel boxes", H, W);
+  pl->AS = pl->BS = 1;
+  pl->a_shift = false;
+  if (kind == MCGM_CONV_S1) {
+    if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "wgrad: only 1x1 and 3x3 stride-1 kernels");
+    pl->Hg = H; pl->Wg = W; pl->taps = R * S;
+  } else if (kind == MCGM_CONV_S2K4) {
+    if (H % 2 || W % 2) return fail(MCGM_E_ARG, "wgrad: stride-2 conv needs even H, W");
+    pl->Hg = H / 2; pl->Wg = W / 2; pl->taps = 16; pl->BS = 2;
+  } else if (kind == MCGM_CONV_PHASE2) {
+    pl->Hg = H; pl->Wg = W; pl->taps = 16; pl->AS = 2; pl->a_shift = true;
+  } else {
+    return fail(MCGM_E_ARG, "wgrad: unknown kind %d", kind);
+  }
+  if (!pick_pixel_box(pl->Hg, pl->Wg, 64, &pl->KW, &pl->KH, &pl->KN))
+    return fail(MCGM_E_UNSUPPORTED, "wgrad: grid H=%d W=%d cannot be tiled into 64-pixel boxes", pl->Hg, pl->Wg);
   pl->BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
   pl->cin_tiles = Cin / pl->BN;
   pl->cout_tiles = (Cout + kTileM - 1) / kTileM;
-  pl->taps = R * S;
   const int n_boxes = (N + pl->KN - 1) / pl->KN;
-  pl->total_kb = n_boxes * (H / pl->KH) * (W / pl->KW);
-  pl->NT = (g_knobs.nt2 && pl->taps > 1 && pl->BN <= 128) ? 2 : 1;
+  pl->total_kb = n_boxes * (pl->Hg / pl->KH) * (pl->Wg / pl->KW);
+  pl->NT = (g_knobs.nt2 && pl->taps > 1 && pl->BN <= 128 && !pl->a_shift) ? 2 : 1;
   pl->tap_groups = (pl->taps + pl->NT - 1) / pl->NT;
   const int tiles = pl->cout_tiles * pl->cin_tiles * pl->tap_groups;
   int sms = sm_count();
@@ -738,25 +795,46 @@ extern "C" int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int 
   return 0;
 }
 
-extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin,
-                             int Cout, int R, int S, const float* bias, const void* res, const void* aux,
-                             const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
+// kind: MCGM_CONV_S1 (stride-1 RxS, R=S in {1,3}), MCGM_CONV_S2K4 (4x4 stride 2 pad 1: out = in/2),
+// MCGM_CONV_PHASE2 (4 output phases x 2x2 taps: out = 2*in).  H, W are the INPUT dims.
+static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
+                         int Cin, int Cout, int R, int S, const float* bias, const void* res, const void* aux,
+                         const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
   MCGM_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv_fwd: bad arguments");
   MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "conv_fwd: out_dtype %d unsupported", out_dtype);
   if (Cin % kBlockK) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cin=%d must be a multiple of 64 (use the thin kernels)", Cin);
-  if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: only 1x1 and 3x3 kernels (got %dx%d)", R, S);
   if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "conv_fwd: BIAS flag without bias");
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) MCGM_CHECK_ARG(res && (Cout % 8 == 0), "conv_fwd: RES flag needs res and Cout %% 8 == 0");
-  if (flags & MCGM_EPI_RES_UP2) MCGM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv_fwd: RES_UP2 needs even H, W");
   if (flags & MCGM_EPI_MASK) MCGM_CHECK_ARG(labels && bits && M > 0 && Cout % 32 == 0, "conv_fwd: MASK needs labels, bits and Cout %% 32 == 0");
   if (flags & MCGM_EPI_POSMASK) MCGM_CHECK_ARG(aux && (Cout % 8 == 0), "conv_fwd: POSMASK needs aux and Cout %% 8 == 0");
 
   ConvFwdParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = (R - 1) / 2;
-  if (!pick_pixel_box(H, W, kTileM, &p.TW, &p.TH, &p.TN))
-    return fail(MCGM_E_UNSUPPORTED, "conv_fwd: H=%d W=%d cannot be tiled into 128-pixel boxes", H, W);
-  p.tiles_w = W / p.TW;
-  p.tiles_h = H / p.TH;
+  p.N = N; p.Cin = Cin; p.Cout = Cout;
+  p.IS = 1; p.OS = 1; p.PH = 1;
+  if (kind == MCGM_CONV_S1) {
+    if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: only 1x1 and 3x3 stride-1 kernels (got %dx%d)", R, S);
+    p.Hg = H; p.Wg = W; p.Ho = H; p.Wo = W; p.T = R * S;
+    for (int t = 0; t < p.T; ++t) { p.tap_dh[t] = (signed char)(t / S - (R - 1) / 2); p.tap_dw[t] = (signed char)(t % S - (S - 1) / 2); }
+  } else if (kind == MCGM_CONV_S2K4) {
+    MCGM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv_fwd: stride-2 conv needs even H, W");
+    p.Hg = H / 2; p.Wg = W / 2; p.Ho = H / 2; p.Wo = W / 2; p.T = 16; p.IS = 2;
+    for (int t = 0; t < 16; ++t) { p.tap_dh[t] = (signed char)(t / 4 - 1); p.tap_dw[t] = (signed char)(t % 4 - 1); }
+  } else if (kind == MCGM_CONV_PHASE2) {
+    p.Hg = H; p.Wg = W; p.Ho = 2 * H; p.Wo = 2 * W; p.T = 4; p.OS = 2; p.PH = 4;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 4; ++t) {
+        p.tap_dh[ph * kMaxTaps + t] = (signed char)(t / 2 - 1 + (ph >> 1));
+        p.tap_dw[ph * kMaxTaps + t] = (signed char)(t % 2 - 1 + (ph & 1));
+      }
+  } else {
+    return fail(MCGM_E_ARG, "conv_fwd: unknown kind %d", kind);
+  }
+  if (flags & MCGM_EPI_RES_UP2) MCGM_CHECK_ARG(p.Ho % 2 == 0 && p.Wo % 2 == 0, "conv_fwd: RES_UP2 needs even output H, W");
+  if (!pick_pixel_box(p.Hg, p.Wg, kTileM, &p.TW, &p.TH, &p.TN))
+    return fail(MCGM_E_UNSUPPORTED, "conv_fwd: tile grid H=%d W=%d cannot be tiled into 128-pixel boxes", p.Hg, p.Wg);
+  if (p.TW * p.IS > 256 || p.TH * p.IS > 256) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: TMA box too large for stride %d", p.IS);
+  p.tiles_w = p.Wg / p.TW;
+  p.tiles_h = p.Hg / p.TH;
   const int tiles_nb = (N + p.TN - 1) / p.TN;
   int BN;
   if (Cout % 256 == 0) BN = 256;
@@ -765,10 +843,11 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   else if (Cout == 32) BN = 32;
   else if (Cout <= 16) BN = 16;
   else return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d unsupported (multiple of 64, 32, or <= 16)", Cout);
+  if (p.PH > 1 && Cout % BN) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: phase conv needs Cout %% %d == 0", BN);
   p.n_tiles = (Cout + BN - 1) / BN;
-  p.total_tiles = p.tiles_w * p.tiles_h * tiles_nb * p.n_tiles;
+  const int m_tiles = p.tiles_w * p.tiles_h * tiles_nb;
   p.kpt = Cin / kBlockK;
-  p.num_kb = R * S * p.kpt;
+  p.num_kb = p.T * p.kpt;
   p.desc_templ = make_smem_desc_hi_lbo(g_knobs.k_lbo, g_knobs.k_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, BN, 0, 0);
   p.bias = bias; p.res = (const __nv_bfloat16*)res; p.aux = (const __nv_bfloat16*)aux;
@@ -777,21 +856,21 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   CUtensorMap mx, mw;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    if (int e = make_tmap(&mx, x, 4, dims, box)) return e;
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
+    if (int e = make_tmap(&mx, x, 4, dims, box, p.IS)) return e;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)R * S * Cin, (uint64_t)Cout};
+    const uint64_t dims[2] = {(uint64_t)p.T * Cin, (uint64_t)p.PH * Cout};
     const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
     if (int e = make_tmap(&mw, w, 2, dims, box)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = out_dtype == MCGM_F32;
   // two M tiles per CTA (halves the weight bytes per MMA) whenever single tiles would need > 1 wave
-  const int m_tiles = p.total_tiles / p.n_tiles;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles > sms);   // more than one wave of single tiles
+  const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles * p.PH > sms);
+  p.m_super = m_tiles;           // launch_fwd turns this into ceil(m_tiles / MT)
   switch (BN) {
     case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(mx, mw, p, f32, st) : launch_fwd_t<256, 1>(mx, mw, p, f32, st);
     case 128: return pair ? launch_fwd_t<128, 2>(mx, mw, p, f32, st) : launch_fwd_t<128, 1>(mx, mw, p, f32, st);
@@ -801,22 +880,40 @@ extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dt
   }
 }
 
-extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {
+extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin,
+                             int Cout, int R, int S, const float* bias, const void* res, const void* aux,
+                             const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
+  return conv_fwd_impl(MCGM_CONV_S1, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
+}
+
+extern "C" int mcgm_conv_fwd_ex(int kind, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
+                                int Cin, int Cout, const float* bias, const void* res, const void* aux,
+                                const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
+  MCGM_CHECK_ARG(kind == MCGM_CONV_S2K4 || kind == MCGM_CONV_PHASE2, "conv_fwd_ex: kind must be S2K4 or PHASE2 (use mcgm_conv_fwd for stride-1)");
+  return conv_fwd_impl(kind, x, w, out, out_dtype, N, H, W, Cin, Cout, 0, 0, bias, res, aux, labels, bits, M, flags, stream);
+}
+
+static size_t wgrad_ws_bytes(int kind, int N, int H, int W, int Cin, int Cout, int R, int S) {
   WgradPlan pl;
-  if (plan_wgrad(N, H, W, Cin, Cout, R, S, &pl)) return 0;
+  if (plan_wgrad(kind, N, H, W, Cin, Cout, R, S, &pl)) return 0;
   size_t bytes = (size_t)pl.splits * pl.per_split * sizeof(float);
-  bytes += (size_t)pl.splits * Cout * sizeof(float);  // bias-gradient partials
+  bytes += (size_t)pl.splits * 4 * Cout * sizeof(float);  // bias-gradient partials (up to 4 slots)
   return bytes;
 }
 
-extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
-                               int Cout, int R, int S, void* workspace, void* stream) {
+static int conv_wgrad_impl(int kind, const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W,
+                           int Cin, int Cout, int R, int S, void* workspace, void* stream) {
   MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
   WgradPlan pl;
-  if (int e = plan_wgrad(N, H, W, Cin, Cout, R, S, &pl)) return e;
+  if (int e = plan_wgrad(kind, N, H, W, Cin, Cout, R, S, &pl)) return e;
   WgradParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad = (R - 1) / 2;
-  p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = W / pl.KW; p.kb_h = H / pl.KH;
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.AS = pl.AS; p.BS = pl.BS;
+  for (int t = 0; t < pl.taps; ++t) {
+    if (kind == MCGM_CONV_S1) { p.b_dh[t] = (signed char)(t / S - (R - 1) / 2); p.b_dw[t] = (signed char)(t % S - (S - 1) / 2); }
+    else if (kind == MCGM_CONV_S2K4) { p.b_dh[t] = (signed char)(t / 4 - 1); p.b_dw[t] = (signed char)(t % 4 - 1); }
+    else { p.a_dh[t] = (signed char)(t / 4 - 1); p.a_dw[t] = (signed char)(t % 4 - 1); }
+  }
+  p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = pl.Wg / pl.KW; p.kb_h = pl.Hg / pl.KH;
   p.total_kb = pl.total_kb; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
   p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
   p.desc_templ = make_smem_desc_hi_lbo(g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
@@ -824,16 +921,23 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
   p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1);
   p.partial = (float*)workspace;
   p.bias_partial = dbias ? p.partial + (size_t)pl.splits * pl.per_split : nullptr;
+  p.bias_slots = 1; p.bias_taps[0] = 0;
+  if (kind == MCGM_CONV_PHASE2) {          // dY is read with stride 2: the four offsets in {0,1}^2 cover it once
+    p.bias_slots = 4; p.bias_taps[0] = 5; p.bias_taps[1] = 6; p.bias_taps[2] = 9; p.bias_taps[3] = 10;
+  }
 
+  // dims of dY and X: the grid scaled by the traversal strides
+  const int Hdy = pl.Hg * pl.AS, Wdy = pl.Wg * pl.AS;
   CUtensorMap mdy, mx;
-  const uint32_t box[4] = {64u, (uint32_t)pl.KW, (uint32_t)pl.KH, (uint32_t)pl.KN};
   {
-    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    if (int e = make_tmap(&mdy, dy, 4, dims, box)) return e;
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
+    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
+    if (int e = make_tmap(&mdy, dy, 4, dims, box, pl.AS)) return e;
   }
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    if (int e = make_tmap(&mx, x, 4, dims, box)) return e;
+    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
+    if (int e = make_tmap(&mx, x, 4, dims, box, pl.BS)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = pl.cout_tiles * pl.cin_tiles * pl.tap_groups * pl.splits;
@@ -847,7 +951,23 @@ extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* 
   const size_t n4 = pl.per_split / 4;
   long blocks = (long)((n4 + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial, Cout, dbias);
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial, pl.splits * p.bias_slots, Cout, dbias);
   MCGM_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {
+  return wgrad_ws_bytes(MCGM_CONV_S1, N, H, W, Cin, Cout, R, S);
+}
+extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
+                               int Cout, int R, int S, void* workspace, void* stream) {
+  return conv_wgrad_impl(MCGM_CONV_S1, x, dy, dw, dbias, N, H, W, Cin, Cout, R, S, workspace, stream);
+}
+extern "C" size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int N, int H, int W, int Cin, int Cout) {
+  return wgrad_ws_bytes(kind, N, H, W, Cin, Cout, 0, 0);
+}
+extern "C" int mcgm_conv_wgrad_ex(int kind, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
+                                  int W, int Cin, int Cout, void* workspace, void* stream) {
+  MCGM_CHECK_ARG(kind == MCGM_CONV_S2K4 || kind == MCGM_CONV_PHASE2, "conv_wgrad_ex: kind must be S2K4 or PHASE2");
+  return conv_wgrad_impl(kind, x, dy, dw, dbias, N, H, W, Cin, Cout, 0, 0, workspace, stream);
 }

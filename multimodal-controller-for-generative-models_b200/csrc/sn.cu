@@ -62,8 +62,17 @@ sn_power_iter_kernel(const SnBatch b, float* __restrict__ state, int do_iter, fl
     // v = normalize(W^T u): thread j walks a column (coalesced across threads for every row k)
     float nrm = 0.0f;
     for (int j = tid; j < CRS; j += blockDim.x) {
-      float a = 0.0f;
-      for (int k = 0; k < K; ++k) a = fmaf(W[(size_t)k * CRS + j], su[k], a);
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;      // 4 independent chains x unroll 2: loads in flight
+      int k = 0;
+#pragma unroll 2
+      for (; k + 3 < K; k += 4) {
+        a0 = fmaf(__ldg(W + (size_t)k * CRS + j), su[k], a0);
+        a1 = fmaf(__ldg(W + (size_t)(k + 1) * CRS + j), su[k + 1], a1);
+        a2 = fmaf(__ldg(W + (size_t)(k + 2) * CRS + j), su[k + 2], a2);
+        a3 = fmaf(__ldg(W + (size_t)(k + 3) * CRS + j), su[k + 3], a3);
+      }
+      for (; k < K; ++k) a0 = fmaf(__ldg(W + (size_t)k * CRS + j), su[k], a0);
+      const float a = (a0 + a1) + (a2 + a3);
       sv[j] = a;
       nrm = fmaf(a, a, nrm);
     }
@@ -74,9 +83,17 @@ sn_power_iter_kernel(const SnBatch b, float* __restrict__ state, int do_iter, fl
   }
   // W v: one warp per row
   for (int k = warp; k < K; k += nw) {
-    float a = 0.0f;
-    for (int j = lane; j < CRS; j += 32) a = fmaf(W[(size_t)k * CRS + j], sv[j], a);
-    a = warp_sum(a);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int j = lane;
+#pragma unroll 2
+    for (; j + 96 < CRS; j += 128) {
+      a0 = fmaf(__ldg(W + (size_t)k * CRS + j), sv[j], a0);
+      a1 = fmaf(__ldg(W + (size_t)k * CRS + j + 32), sv[j + 32], a1);
+      a2 = fmaf(__ldg(W + (size_t)k * CRS + j + 64), sv[j + 64], a2);
+      a3 = fmaf(__ldg(W + (size_t)k * CRS + j + 96), sv[j + 96], a3);
+    }
+    for (; j < CRS; j += 32) a0 = fmaf(__ldg(W + (size_t)k * CRS + j), sv[j], a0);
+    const float a = warp_sum((a0 + a1) + (a2 + a3));
     if (lane == 0) swv[k] = a;
   }
   __syncthreads();

@@ -9,7 +9,7 @@ style, e.g. src/utils.py:126); a failing native call raises ``RuntimeError``.
 import torch
 
 from . import _lib
-from ._lib import (BF16, EPI_BIAS, EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_TANH, F32,
+from ._lib import (BF16, CONV_PHASE2, CONV_S1, CONV_S2K4, EPI_BIAS, EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_TANH, F32,
                    GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2)
 
 
@@ -291,6 +291,60 @@ def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None,
     return out
 
 
+def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=None, labels=None, packed=None,
+                flags=0):
+    """Generalised geometry on the tcgen05 conv kernel (include/mcgm.h):
+    CONV_S2K4  : w [Cout,4,4,Cin]        x [N,H,W,Cin] -> [N,H/2,W/2,Cout]   (4x4, stride 2, pad 1)
+    CONV_PHASE2: w [4,Cout,2,2,Cin]      x [N,H,W,Cin] -> [N,2H,2W,Cout]     (4 phases x 2x2 taps)"""
+    _check_cuda(x, w, bias, res, aux, labels)
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise ValueError("Not valid dtype: conv operands must be bfloat16")
+    N, H, W, Cin = x.shape
+    if kind == CONV_S2K4:
+        Cout, Ho, Wo = w.shape[0], H // 2, W // 2
+        ok = tuple(w.shape) == (Cout, 4, 4, Cin)
+    elif kind == CONV_PHASE2:
+        Cout, Ho, Wo = w.shape[1], 2 * H, 2 * W
+        ok = tuple(w.shape) == (4, Cout, 2, 2, Cin)
+    else:
+        raise ValueError("Not valid conv kind")
+    if not ok:
+        raise ValueError(f"Not valid weight shape {tuple(w.shape)} for conv kind {kind}")
+    out = torch.empty(N, Ho, Wo, Cout, dtype=out_dtype, device=x.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    ev = _prof_begin()
+    _lib.call("mcgm_conv_fwd_ex", kind, x.data_ptr(), w.data_ptr(), out.data_ptr(),
+              F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout,
+              _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
+              packed.M if packed else 0, flags, _stream())
+    # algorithmic flops of the REFERENCE op (3x3 on the upsampled tensor / 4x4 strided), not the executed MACs
+    ref_taps = 9 if kind == CONV_PHASE2 else 16
+    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ref_taps)
+    return out
+
+
+def conv_wgrad_ex(kind, x, dy, want_bias=True):
+    """dw fp32 [Cout, 4, 4, Cin] (tap index p*4+q, see include/mcgm.h) and dbias; x dims are [N,H,W,Cin]."""
+    _check_cuda(x, dy)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    nbytes = _lib.query("mcgm_conv_wgrad_ex_workspace_bytes", kind, N, H, W, Cin, Cout)
+    if nbytes == 0:
+        raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} kind={kind}")
+    ws = _workspace("wgrad", nbytes, x.device)
+    dw = torch.empty(Cout, 4, 4, Cin, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    ev = _prof_begin()
+    _lib.call("mcgm_conv_wgrad_ex", kind, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout,
+              ws.data_ptr(), _stream())
+    _lib.launch_count += 1
+    ref_taps = 9 if kind == CONV_PHASE2 else 16
+    _prof_end(ev, "wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * ref_taps
+              if kind == CONV_PHASE2 else 2.0 * N * (H // 2) * (W // 2) * Cout * Cin * 16)
+    return dw, db
+
+
 def conv_wgrad(x, dy, R, S, want_bias=True):
     """dw (fp32 KRSC [Cout,R,S,Cin]) and dbias from NHWC bf16 x and dy."""
     _check_cuda(x, dy)
@@ -506,6 +560,62 @@ def _pad_cols(m, cols):
 
 
 _KU = 64          # im2col width of the thin tensor (R*S*Ct <= 36 taps*channels, padded to one 64-wide K block)
+
+
+# Nearest-up2 followed by a 3x3 conv collapses, per output phase (ph, pw), to a 2x2 conv over the
+# LOW-resolution input with pre-summed taps: rows {r} of the 3x3 kernel that read the same input row
+# are added.  _RM[ph, a, r] = 1 if kernel row r reads input row (i + a - 1 + ph) for output row 2i+ph.
+_RM = torch.tensor([[[1., 0., 0.], [0., 1., 1.]], [[1., 1., 0.], [0., 0., 1.]]])
+# The adjoint is a 4x4 stride-2 conv over the output gradient; _QM[x, r] = 1 if kernel row r
+# contributes at offset x - 1 (x = 3 - 2a - ph).
+_QM = torch.tensor([[0., 0., 1.], [0., 1., 1.], [1., 1., 0.], [1., 0., 0.]])
+_mats = {}
+
+
+def _up2_mats(device):
+    m = _mats.get(device)
+    if m is None:
+        m = _mats[device] = (_RM.to(device), _QM.to(device))
+    return m
+
+
+def up2_conv_packs(w):
+    """fp32 OIHW 3x3 weight -> (phase weights bf16 [4,Cout,2,2,Cin], adjoint 4x4/s2 weights bf16 [Cin,4,4,Cout])."""
+    rm, qm = _up2_mats(w.device)
+    wp = torch.einsum('par,qbs,kcrs->pqkabc', rm, rm, w)
+    K, C = w.shape[0], w.shape[1]
+    wp = wp.reshape(4, K, 2, 2, C).to(torch.bfloat16).contiguous()
+    kd = torch.einsum('xr,ys,kcrs->cxyk', qm, qm, w).to(torch.bfloat16).contiguous()
+    return wp, kd
+
+
+class ConvUp2Fn(torch.autograd.Function):
+    """nn.Upsample(2, 'nearest') -> Conv2d(C, K, 3, 1, 1) (src/models/mcgan.py:17-19) WITHOUT
+    materialising the upsampled tensor: 4 output phases x 2x2 taps on the low-resolution input
+    (2.25x fewer MACs, and the gate kernel writes T instead of 4T).  Backward: the data gradient is a
+    4x4 stride-2 conv of dout (TMA traversal stride 2), the weight gradient a 16-tap strided wgrad
+    folded back onto the 3x3 kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, packs):
+        wp, kd = packs if packs is not None else up2_conv_packs(w.detach())
+        out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
+        ctx.save_for_backward(x)
+        ctx.kd, ctx.has_bias, ctx.dev = kd, bias is not None, w.device
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_fwd_ex(CONV_S2K4, dout, ctx.kd, torch.bfloat16)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dk, db = conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias)     # [K,4,4,C]
+            _, qm = _up2_mats(ctx.dev)
+            dw = torch.einsum('xr,ys,kxyc->kcrs', qm, qm, dk)
+        return dx, dw, db, None
 
 
 class WideFromThinFn(torch.autograd.Function):

@@ -285,6 +285,64 @@ def check_thin():
     return rows
 
 
+def check_conv_ex():
+    """Generalised geometries: nearest-up2+conv3x3 as a phase conv, 4x4 stride-2 conv, ConvTranspose2d(4,2,1)."""
+    from mcgm_b200._lib import CONV_PHASE2, CONV_S2K4
+    rows = []
+    for (N, H, Cin, Cout) in [(4, 8, 64, 64), (40, 16, 64, 128), (3, 4, 128, 256), (2, 16, 256, 64)]:
+        g = torch.Generator().manual_seed(N + H + Cin)
+        x = torch.randn(N, Cin, H, H, generator=g).to(torch.bfloat16).float()
+        tag = f"N{N} {H}x{H} {Cin}->{Cout}"
+        # --- up2 + conv3x3 (mcgan.py:17-19).  Integer-valued weights: their phase sums stay bf16-exact.
+        w = torch.randint(-2, 3, (Cout, Cin, 3, 3), generator=g).float() * 0.125
+        b = torch.randn(Cout, generator=g)
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), wr, br, padding=1)
+        dy = torch.randn(N, Cout, 2 * H, 2 * H, generator=g).to(torch.bfloat16).float()
+        ref.backward(dy)
+        xd = nhwc(x).to(DEV).to(torch.bfloat16).requires_grad_(True)
+        wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        wp, _ = ops.up2_conv_packs(wd.detach())
+        out32 = ops.conv_fwd_ex(CONV_PHASE2, xd.detach(), wp, torch.float32, bd.detach())
+        rows.append((f"up2conv fwd f32 {tag}", rel(nchw(out32), ref), F32_TOL))
+        out = ops.ConvUp2Fn.apply(xd, wd, bd, None)
+        rows.append((f"up2conv fwd bf16 {tag}", rel(nchw(out.float()), ref), BF16_OUT))
+        out.backward(nhwc(dy).to(DEV).to(torch.bfloat16))
+        rows.append((f"up2conv dgrad {tag}", rel(nchw(xd.grad.float()), xr.grad), BF16_OUT))
+        rows.append((f"up2conv wgrad {tag}", rel(wd.grad, wr.grad), 5e-5))
+        rows.append((f"up2conv dbias {tag}", rel(bd.grad, br.grad), F32_TOL))
+        # --- Conv2d(Cin, Cout, 4, 2, 1) (mcvae.py:41-49) and its gradients
+        w4 = (torch.randn(Cout, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5).to(torch.bfloat16).float()
+        xr, w4r = x.clone().requires_grad_(True), w4.clone().requires_grad_(True)
+        ref = F.conv2d(xr, w4r, None, stride=2, padding=1)
+        dy = torch.randn(N, Cout, H // 2, H // 2, generator=g).to(torch.bfloat16).float()
+        ref.backward(dy)
+        w4k = w4.permute(0, 2, 3, 1).contiguous().to(DEV).to(torch.bfloat16)            # KRSC
+        xdd = nhwc(x).to(DEV).to(torch.bfloat16)
+        dyd = nhwc(dy).to(DEV).to(torch.bfloat16)
+        if H >= 16 or (H // 2) * (H // 2) * N >= 128:
+            y = ops.conv_fwd_ex(CONV_S2K4, xdd, w4k, torch.float32)
+            rows.append((f"conv4x4s2 fwd {tag}", rel(nchw(y), ref), F32_TOL))
+            dw4, _ = ops.conv_wgrad_ex(CONV_S2K4, xdd, dyd, want_bias=False)             # [Cout,4,4,Cin]
+            rows.append((f"conv4x4s2 wgrad {tag}", rel(dw4.permute(0, 3, 1, 2), w4r.grad), 5e-5))
+            # data gradient = phase conv with W'[ph,pw][cin][a,b][cout] = w4[cout, cin, 3-2a-ph, 3-2b-pw]
+            idx = torch.tensor([[3, 1], [2, 0]])
+            wt = w4.permute(1, 0, 2, 3)                                                   # [Cin, Cout, 4, 4]
+            wph = torch.stack([wt[:, :, idx[ph]][:, :, :, idx[pw]] for ph in range(2) for pw in range(2)])
+            wph = wph.permute(0, 1, 3, 4, 2).contiguous().to(DEV).to(torch.bfloat16)      # [4, Cin, 2, 2, Cout]
+            dx = ops.conv_fwd_ex(CONV_PHASE2, dyd, wph, torch.float32)
+            rows.append((f"conv4x4s2 dgrad (phase conv) {tag}", rel(nchw(dx), xr.grad), F32_TOL))
+        # --- ConvTranspose2d(Cin, Cout, 4, 2, 1) forward (mcvae.py:87-92) as a phase conv
+        wt4 = (torch.randn(Cin, Cout, 4, 4, generator=g) / (Cin * 4) ** 0.5).to(torch.bfloat16).float()
+        ref = F.conv_transpose2d(x, wt4, None, stride=2, padding=1)
+        idx = torch.tensor([[3, 1], [2, 0]])
+        wph = torch.stack([wt4[:, :, idx[ph]][:, :, :, idx[pw]] for ph in range(2) for pw in range(2)])  # [4,Cin,Cout,2,2]
+        wph = wph.permute(0, 2, 3, 4, 1).contiguous().to(DEV).to(torch.bfloat16)          # [4, Cout, 2, 2, Cin]
+        y = ops.conv_fwd_ex(CONV_PHASE2, xdd, wph, torch.float32)
+        rows.append((f"convT4x4s2 fwd (phase conv) {tag}", rel(nchw(y), ref), F32_TOL))
+    return rows
+
+
 class _SNLayer:
     def __init__(self, w, u, v):
         self.weight_orig, self.weight_u, self.weight_v = w, u, v
@@ -347,4 +405,4 @@ def check_conv_variants():
 
 
 ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
-                     check_conv_wgrad, check_thin, check_conv_variants, check_sn]
+                     check_conv_wgrad, check_thin, check_conv_variants, check_sn, check_conv_ex]

@@ -7,7 +7,7 @@ import torch
 from util import GOLDEN, build_model, sd_hash
 
 
-@pytest.mark.parametrize("name", ["tiny_cifar", "tiny_omni", "cifar10_full"])
+@pytest.mark.parametrize("name", ["tiny_cifar", "tiny_omni", "cifar10_full", "omniglot_full"])
 def test_state_dict_bit_identical_to_reference(golden, name):
     case = golden["cases"][name]
     model = build_model(case)
