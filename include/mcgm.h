@@ -211,13 +211,15 @@ int mcgm_thin_kern_grad(const float* thin, const void* wide, float* dkern,
                         void* workspace, void* stream);
 
 /* ---- thin convolutions on the tensor cores: im2col / col2im of the THIN tensor only.
- *   im2col : U[p, t*Ct + j] = thin[p +/- off(t), j]   bf16 [N,H,W,KU], zero padded (flip: -off)
+ *   im2col : U[p, t*Ct + j] = thin[stride*p +/- off(t), j]  bf16 [N,Ho,Wo,KU], zero padded; off(t) =
+ *            (r - pad, s - pad); flip: -off (stride 1 only).  stride 2 / 4x4 / pad 1 serves
+ *            Conv2d(3,64,4,2,1) (mcvae.py:41) and the data gradient of ConvTranspose2d(64,3,4,2,1).
  *   col2im : thin[p, j] = bias[j] + sum_t T[p + off(t), t*Ct + j]  (T fp32 [N,H,W,CT]) -> tanh
  * With U, Conv2d(3,Cw) forward is mcgm_conv_fwd 1x1 (Cin = KU), its weight gradient is
  * mcgm_conv_wgrad 1x1; Conv2d(Cw,3) forward is a 1x1 mcgm_conv_fwd to T followed by col2im.
  * The wide tensor is read exactly once in every direction. */
 int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, int W, int Ct, int R, int S,
-                     int flip, int KU, void* stream);
+                     int stride, int pad, int flip, int KU, void* stream);
 int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, int Ct, int R, int S,
                      const float* bias, int flags, void* stream);
 

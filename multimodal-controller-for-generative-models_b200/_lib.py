@@ -58,7 +58,8 @@ SIGNATURES = {
     "mcgm_thin_kern_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mcgm_thin_kern_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
-    "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
     "mcgm_thin_col2im": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p]),
     "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

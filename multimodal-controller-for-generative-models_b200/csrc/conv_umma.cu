@@ -843,7 +843,10 @@ static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int 
   else if (Cout == 32) BN = 32;
   else if (Cout <= 16) BN = 16;
   else return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d unsupported (multiple of 64, 32, or <= 16)", Cout);
-  if (p.PH > 1 && Cout % BN) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: phase conv needs Cout %% %d == 0", BN);
+  // phase conv: the weight rows of phase ph start at ph*Cout.  With Cout < 16 (RGB output of a
+  // ConvTranspose2d) the 16-row box also covers the next phases' rows; those accumulator columns are
+  // never stored (the epilogue stops at Cout).
+  if (p.PH > 1 && Cout % BN && Cout > 16) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: phase conv needs Cout %% %d == 0", BN);
   p.n_tiles = (Cout + BN - 1) / BN;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_nb;
   p.kpt = Cin / kBlockK;

@@ -525,14 +525,17 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, db, dres, None, None, None, None, None, None
 
 
-def thin_im2col(thin, R, S, flip=False, KU=64):
-    """U[p, t*Ct + j] = thin[p +/- off(t), j] as bf16 [N,H,W,KU] (zero padded)."""
+def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None):
+    """U[p, t*Ct + j] = thin[stride*p +/- off(t), j] as bf16 [N,Ho,Wo,KU] (zero padded)."""
     _check_cuda(thin)
     if thin.dtype != torch.float32:
         raise ValueError("Not valid dtype: thin tensors are float32")
     N, H, W, Ct = thin.shape
-    U = torch.empty(N, H, W, KU, dtype=torch.bfloat16, device=thin.device)
-    _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), N, H, W, Ct, R, S, int(flip), KU, _stream())
+    pad = (R - 1) // 2 if pad is None else pad
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    U = torch.empty(N, Ho, Wo, KU, dtype=torch.bfloat16, device=thin.device)
+    _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), N, H, W, Ct, R, S, stride, pad, int(flip), KU,
+              _stream())
     return U
 
 
@@ -618,6 +621,85 @@ class ConvUp2Fn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+_PIDX = ((3, 1), (2, 0))     # kernel index of (phase ph, tap a): p = 3 - 2a - ph
+
+
+def _phase_weights(w_oc_ic_44):
+    """[O, I, 4, 4] (O = output channels of the PHASE conv) -> [4, O, 2, 2, I] with
+    out[ph*2+pw, o, a, b, i] = w[o, i, 3-2a-ph, 3-2b-pw]."""
+    idx = torch.tensor(_PIDX, device=w_oc_ic_44.device)
+    parts = [w_oc_ic_44[:, :, idx[ph]][:, :, :, idx[pw]] for ph in range(2) for pw in range(2)]   # [O,I,2,2] each
+    return torch.stack(parts).permute(0, 1, 3, 4, 2).contiguous()
+
+
+class ConvS2Fn(torch.autograd.Function):
+    """Conv2d(C, K, 4, 2, 1) (src/models/mcvae.py:41-49) on the tensor cores: the strided input pixels
+    are gathered by TMA with traversal stride 2.  Backward: data gradient = 4-phase 2x2 conv of dout,
+    weight gradient = 16-tap strided wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        wk = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()                 # KRSC
+        out = conv_fwd_ex(CONV_S2K4, x, wk, torch.bfloat16, bias)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wph = _phase_weights(w.detach().permute(1, 0, 2, 3)).to(torch.bfloat16)          # [4, Cin, 2, 2, Cout]
+            dx = conv_fwd_ex(CONV_PHASE2, dout, wph, torch.bfloat16)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dk, db = conv_wgrad_ex(CONV_S2K4, x, dout, want_bias=ctx.has_bias)             # [K,4,4,C]
+            dw = dk.permute(0, 3, 1, 2)
+        return dx, dw, db
+
+
+class ConvT4Fn(torch.autograd.Function):
+    """ConvTranspose2d(C, K, 4, 2, 1) (src/models/mcvae.py:87-92; weight layout [C, K, 4, 4]) as a
+    4-phase 2x2 conv.  K <= 4 (the RGB output layer) produces an fp32 image; its gradients go
+    through the stride-2 im2col of the (thin) output gradient and 1x1 GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        C, K = w.shape[0], w.shape[1]
+        wph = _phase_weights(w.detach().permute(1, 0, 2, 3)).to(torch.bfloat16)              # [4, K, 2, 2, C]
+        thin = K <= 4
+        out = conv_fwd_ex(CONV_PHASE2, x, wph, torch.float32 if thin else torch.bfloat16, bias)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias, ctx.thin = bias is not None, thin
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        C, K = w.shape[0], w.shape[1]
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.thin:
+            U = thin_im2col(dout, 4, 4, False, _KU, 2, 1)                                   # [N,H,W,64], cols (p,q,j)
+            if ctx.needs_input_grad[0]:
+                wm = _pad_cols(w.detach().permute(0, 2, 3, 1).reshape(C, 16 * K), _KU)
+                dx = conv_fwd(U, wm.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16)
+            if ctx.needs_input_grad[1]:
+                dwm, _ = conv_wgrad(x, U, 1, 1, want_bias=False)                            # [KU,1,1,C]
+                dw = dwm.reshape(_KU, C)[:16 * K].reshape(4, 4, K, C).permute(3, 2, 0, 1)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = dout.sum(dim=(0, 1, 2))
+            return dx, dw, db
+        if ctx.needs_input_grad[0]:
+            kd = w.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()             # [C,4,4,K]
+            dx = conv_fwd_ex(CONV_S2K4, dout, kd, torch.bfloat16)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dk, db = conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias)           # [K,4,4,C]
+            dw = dk.permute(3, 0, 1, 2)
+        return dx, dw, db
+
+
 class WideFromThinFn(torch.autograd.Function):
     """Conv2d(Ct<=4 -> Cw) on an fp32 NHWC image, optional ReLU+mask epilogue
     (src/models/mcgan.py:77-79, 87).  im2col of the 3-channel image (tiny) turns it into a
@@ -625,9 +707,11 @@ class WideFromThinFn(torch.autograd.Function):
     gradient (needed in the G update) is a 1x1 GEMM to [P, 32] followed by col2im."""
 
     @staticmethod
-    def forward(ctx, thin, w, bias, gate, grad_premasked, sn):
+    def forward(ctx, thin, w, bias, gate, grad_premasked, sn, stride=1, pad=None):
         K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
-        U = thin_im2col(thin, R, S, False, _KU)
+        if stride != 1 and thin.requires_grad:
+            raise ValueError("Not valid: the strided thin conv has no image gradient (first encoder layer only)")
+        U = thin_im2col(thin, R, S, False, _KU, stride, pad)
         wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
         flags, labels, packed = 0, None, None
         if gate is not None:
@@ -660,7 +744,7 @@ class WideFromThinFn(torch.autograd.Function):
                 dw = sn_weight_bwd(dwm, _KU, 1, w, sn)
             else:
                 dw = dwm.reshape(K, _KU)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
-        return dthin, dw, db, None, None, None
+        return dthin, dw, db, None, None, None, None, None
 
 
 class ThinFromWideFn(torch.autograd.Function):

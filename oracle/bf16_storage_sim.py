@@ -22,30 +22,38 @@ class _Round(torch.autograd.Function):
         return g.bfloat16().float()
 
 
-def _wide(w):
-    return w.shape[0] > 4 and w.shape[1] > 4
-
-
 class _Patched:
-    """Context manager that makes the oracle round like the bf16 pipeline."""
+    """Context manager that makes the oracles (MCGAN and MCVAE) round like the bf16 pipeline:
+    conv weights, conv inputs coming from an fp32 image (<= 4 channels: the im2col buffer is bf16),
+    conv / conv-transpose outputs with more than 4 channels (RGB outputs stay fp32), and every
+    4-D masked activation."""
 
     def __enter__(self):
-        self.conv2d, self.mask = F.conv2d, O.mc_mask
+        from . import mcvae_oracle as V
+        self.V = V
+        self.conv2d, self.convt, self.mask_o, self.mask_v = F.conv2d, F.conv_transpose2d, O.mc_mask, V.mc_mask
 
-        def conv2d(x, w, b=None, padding=0):
-            w = _Round.apply(w)
-            return _Round.apply(self.conv2d(x, w, b, padding=padding)) if _wide(w) or w.shape[0] > 4 \
-                else self.conv2d(x, w, b, padding=padding)
+        def conv2d(x, w, b=None, stride=1, padding=0):
+            if w.shape[1] <= 4:
+                x = _Round.apply(x)
+            y = self.conv2d(x, _Round.apply(w), b, stride=stride, padding=padding)
+            return _Round.apply(y) if w.shape[0] > 4 else y
+
+        def conv_transpose2d(x, w, b=None, stride=1, padding=0):
+            y = self.convt(x, _Round.apply(w), b, stride=stride, padding=padding)
+            return _Round.apply(y) if w.shape[1] > 4 else y
 
         ns = type("FPatched", (), {k: getattr(F, k) for k in dir(F) if not k.startswith("__")})
         ns.conv2d = staticmethod(conv2d)
-        O.F = ns
-        O.mc_mask = lambda x, i, c: _Round.apply(self.mask(x, i, c))
+        ns.conv_transpose2d = staticmethod(conv_transpose2d)
+        mask = lambda x, i, c: _Round.apply(self.mask_o(x, i, c)) if x.dim() > 2 else self.mask_o(x, i, c)  # noqa: E731
+        O.F = V.F = ns
+        O.mc_mask = V.mc_mask = mask
         return self
 
     def __exit__(self, *a):
-        O.F = F
-        O.mc_mask = self.mask
+        O.F = self.V.F = F
+        O.mc_mask, self.V.mc_mask = self.mask_o, self.mask_v
 
 
 def gradients(sd, z, label, num_mode, strides, simulate):
@@ -60,3 +68,17 @@ def gradients(sd, z, label, num_mode, strides, simulate):
         loss = -O.discriminator(O.generator(z, ind, sd), ind, sd, strides).mean()
         loss.backward()
     return float(loss.detach()), {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+
+def vae_gradients(sd, img, label, num_mode, eps, simulate):
+    """MCVAE loss and parameter gradients, with or without simulated bf16 storage."""
+    from . import mcvae_oracle as V
+    sd = V.make_trainable(sd)
+    if simulate:
+        with _Patched():
+            out = V.forward(img, label, sd, num_mode, eps)
+            out["loss"].backward()
+    else:
+        out = V.forward(img, label, sd, num_mode, eps)
+        out["loss"].backward()
+    return float(out["loss"].detach()), {k: v.grad for k, v in sd.items() if v.grad is not None}

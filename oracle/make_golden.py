@@ -154,6 +154,52 @@ def main():
         meta['cases'][name] = case
         print(name, 'loss_D', d_loss, 'loss_G', g_loss)
 
+    # --- MCVAE (COIL100-shaped, 100 modes): forward, gradients and one train step through the reference
+    from utils import process_control
+    cfg.update(device='cpu', data_name='COIL100', model_name='mcvae', control={'controller_rate': '0.5'})
+    process_control()
+    cfg['classes_size'] = 100
+    torch.manual_seed(0)
+    m = models.mcvae()
+    meta['cases']['vae_full'] = {'data_name': 'COIL100', 'classes': 100, 'seed': 0, 'model': 'mcvae',
+                                 'state_dict_sha256': sd_hash(m.state_dict()),
+                                 'keys': [[k, list(v.shape)] for k, v in m.state_dict().items()]}
+    batch = 16
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    label = torch.randint(0, 100, (batch,), generator=g)
+    eps = torch.randn(batch, cfg['vae']['latent_size'], generator=g)
+    _randn_like = torch.randn_like
+    torch.randn_like = lambda t: eps.clone()                  # inject the reparameterisation noise (mcvae.py:60)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    import copy
+    scratch = copy.deepcopy(m)
+    scratch.train(True)
+    out = scratch({'img': img.clone(), 'label': label})
+    out['loss'].backward()
+    case = {'data_name': 'COIL100', 'classes': 100, 'seed': 0, 'input_seed': 1, 'batch': batch, 'model': 'mcvae',
+            'state_dict_sha256': sd_hash(sd0), 'loss_fwd': float(out['loss'].detach()),
+            'grad_norms': {k: float(p.grad.norm()) for k, p in scratch.named_parameters() if p.grad is not None}}
+    arrays = {'img': img.numpy(), 'label': label.numpy(), 'eps': eps.numpy(),
+              'recon': out['img'].detach().numpy(), 'mu': out['mu'].detach().numpy(),
+              'logvar': out['logvar'].detach().numpy()}
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4, weight_decay=0)
+    m.train(True)
+    opt.zero_grad()
+    out = m({'img': img.clone(), 'label': label})
+    out['loss'].backward()
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1)
+    opt.step()
+    out2 = m({'img': img.clone(), 'label': label})
+    sd1 = m.state_dict()
+    case['loss_step1'] = float(out['loss'].detach())
+    case['loss_step2'] = float(out2['loss'].detach())
+    case['delta_norms'] = {k: float((sd1[k].float() - sd0[k].float()).norm()) for k in sd0 if sd0[k].is_floating_point()}
+    np.savez_compressed(os.path.join(OUT, 'vae_full.npz'), **arrays)
+    meta['cases']['vae_step'] = case
+    torch.randn_like = _randn_like
+    print('vae loss', case['loss_fwd'], case['loss_step2'])
+
     with open(os.path.join(OUT, 'mcgan_golden.json'), 'w') as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print('wrote', OUT)
