@@ -165,11 +165,15 @@ int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype,
  *   MCGM_CONV_PHASE2: w bf16 [4 phases (ph*2+pw)][Cout][2][2][Cin];
  *                     out[n,2i+ph,2j+pw] = sum_{a,b} x[n,i+a-1+ph,j+b-1+pw] . w[ph*2+pw,:,a,b,:]
  *                     — 2.25x fewer MACs than convolving the materialised upsampled tensor. */
-int mcgm_conv_fwd_ex(int kind, const void* x, const void* w, void* out, int out_dtype,
-                     int N, int H, int W, int Cin, int Cout,
+int mcgm_conv_fwd_ex(int kind, int in_dtype, const void* x, const void* w, void* out, int out_dtype,
+                     int N, int H, int W, int Cin, int Cout, int R, int S,
                      const float* bias, const void* res, const void* aux,
                      const int32_t* labels, const uint32_t* bits, int M,
                      int flags, void* stream);
+/* in_dtype = MCGM_F32 is the fp32 PARITY pipeline: x, w (KRSC), res, aux and out are fp32 and the
+ * tensor cores read the operands as TF32 (kind::tf32).  Feeding it tf32-split operands three times
+ * (big*big + big*small + small*big, accumulated through the fp32 residual input) gives fp32-accurate
+ * convolutions ("3xTF32"); see mcgm_split_tf32.  R, S are used by MCGM_CONV_S1 only. */
 
 /* ---- weight gradient, tcgen05 + TMA with MN-major operands straight from the
  * NHWC tensors: dw[k,r,s,c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-pad,w+s-pad,c].
@@ -186,9 +190,10 @@ int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias,
  *   MCGM_CONV_S2K4  : dy [N,H/2,W/2,Cout]; dw[k,p,q,c] = sum dy[n,i,j,k] * x[n,2i+p-1,2j+q-1,c]
  *   MCGM_CONV_PHASE2: dy [N,2H,2W,Cout];   dw[k,p,q,c] = sum dy[n,2i+p-1,2j+q-1,k] * x[n,i,j,c]
  *                     (phase ph, tap a of the forward weight is p = 3 - 2a - ph; same for q). */
-size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int N, int H, int W, int Cin, int Cout);
-int mcgm_conv_wgrad_ex(int kind, const void* x, const void* dy, float* dw, float* dbias,
-                       int N, int H, int W, int Cin, int Cout, void* workspace, void* stream);
+size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int in_dtype, int N, int H, int W, int Cin, int Cout,
+                                          int R, int S);
+int mcgm_conv_wgrad_ex(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias,
+                       int N, int H, int W, int Cin, int Cout, int R, int S, void* workspace, void* stream);
 
 /* ---- thin convolutions: one side has <= 4 channels (RGB image side of
  * Conv2d(3,128,...) mcgan.py:77,87 and Conv2d(256,3,3,1,1) mcgan.py:59).
@@ -218,10 +223,17 @@ int mcgm_thin_kern_grad(const float* thin, const void* wide, float* dkern,
  * With U, Conv2d(3,Cw) forward is mcgm_conv_fwd 1x1 (Cin = KU), its weight gradient is
  * mcgm_conv_wgrad 1x1; Conv2d(Cw,3) forward is a 1x1 mcgm_conv_fwd to T followed by col2im.
  * The wide tensor is read exactly once in every direction. */
-int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, int W, int Ct, int R, int S,
+int mcgm_thin_im2col(const float* thin, void* U, int out_dtype, int N, int H, int W, int Ct, int R, int S,
                      int stride, int pad, int flip, int KU, void* stream);
 int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, int Ct, int R, int S,
                      const float* bias, int flags, void* stream);
+
+/* ---- operand splitting for the fp32 parity pipeline (cfg['compute_dtype'] = 'fp32'):
+ *   split_tf32   : x = big + small (+ O(2^-21 |x|)), both exactly TF32-representable — three
+ *                  kind::tf32 convolutions big*big + big*small + small*big recover an fp32 product
+ *   split_bf16x3 : x = p1 + p2 + p3, bf16 pieces — six bf16 weight-gradient GEMMs do the same. */
+int mcgm_split_tf32(const float* x, float* big, float* small, long n, void* stream);
+int mcgm_split_bf16x3(const float* x, void* p1, void* p2, void* p3, long n, void* stream);
 
 /* ---- pooling / resampling helpers on bf16 NHWC (AvgPool2d(2) mcgan.py:81,88;
  * Upsample backward = 2x2 sum).  avgpool2: y[n,h,w,c] = scale * sum_{2x2} x;

@@ -43,11 +43,11 @@ SIGNATURES = {
     "mcgm_pack_weight_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mcgm_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "mcgm_conv_fwd_ex": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "mcgm_conv_wgrad_ex_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
-    "mcgm_conv_wgrad_ex": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_void_p]),
+    "mcgm_conv_fwd_ex": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcgm_conv_wgrad_ex_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mcgm_conv_wgrad_ex": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_void_p]),
     "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mcgm_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p]),
@@ -59,7 +59,9 @@ SIGNATURES = {
     "mcgm_thin_kern_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p]),
     "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_int, c_void_p]),
+                                 c_int, c_int, c_void_p]),
+    "mcgm_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
+    "mcgm_split_bf16x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "mcgm_thin_col2im": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p]),
     "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -52,9 +52,9 @@ struct MapKey {
   const void* ptr;
   uint64_t d[4];
   uint32_t b[4];
-  int rank, estride;
+  int rank, estride, f32;
   bool operator==(const MapKey& o) const {
-    if (ptr != o.ptr || rank != o.rank || estride != o.estride) return false;
+    if (ptr != o.ptr || rank != o.rank || estride != o.estride || f32 != o.f32) return false;
     for (int i = 0; i < 4; ++i)
       if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
     return true;
@@ -62,7 +62,7 @@ struct MapKey {
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride) * 0x9e3779b97f4a7c15ull;
+    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride + 64 * k.f32) * 0x9e3779b97f4a7c15ull;
     for (int i = 0; i < 4; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
     return h;
   }
@@ -72,13 +72,14 @@ struct MapKeyHash {
 // TMA traversal stride of the two spatial dims of a 4-D NHWC map (1, or 2 for stride-2 gathers): a
 // box of b elements then lands b/estride elements in shared memory.
 static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box,
-                     int estride = 1) {
+                     int estride = 1, int f32 = 0) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{};
   key.ptr = ptr;
   key.rank = rank;
   key.estride = estride;
+  key.f32 = f32;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   {
     std::lock_guard<std::mutex> lock(mu);
@@ -101,7 +102,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
   }
   cuuint64_t gdim[4], gstride[3];
   cuuint32_t bdim[4], estr[4];
-  uint64_t stride = 2;  // bytes
+  uint64_t stride = f32 ? 4 : 2;  // bytes
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
@@ -109,7 +110,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
     stride *= dims[i];
     if (i < rank - 1) gstride[i] = stride;
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride,
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride,
                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -155,6 +156,7 @@ static constexpr int kMaxTaps = 16;
 struct ConvFwdParams {
   int N, Hg, Wg, Ho, Wo, Cin, Cout;
   int IS, OS, PH, T;                         // input traversal stride, output scale, phases, taps per phase
+  int tf32, kblk;                            // fp32 operands read as TF32; elements per 128-byte k-block row (32 / 64)
   signed char tap_dh[4 * kMaxTaps], tap_dw[4 * kMaxTaps];   // [phase][tap]
   int TW, TH, TN, tiles_w, tiles_h;
   int n_tiles, m_super, total_tiles;
@@ -201,14 +203,27 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
     long rpix = pix;
     if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
-    const __nv_bfloat16* rp = p.res + rpix * p.Cout + col0;
+    if (p.tf32) {                                          // fp32 pipeline: residual is fp32
+      const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.Cout + col0;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (i < ncols) {
-        Vec<__nv_bfloat16> r;
-        r.load(rp + i);
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncols) {
+          Vec<float> r;
+          r.load(rp + i);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i + j] += r.v[j];
+          for (int j = 0; j < 4; ++j) v[i + j] += r.v[j];
+        }
+      }
+    } else {
+      const __nv_bfloat16* rp = p.res + rpix * p.Cout + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          Vec<__nv_bfloat16> r;
+          r.load(rp + i);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i + j] += r.v[j];
+        }
       }
     }
   }
@@ -222,14 +237,27 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
     for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.0f;
   }
   if (flags & MCGM_EPI_POSMASK) {
-    const __nv_bfloat16* ap = p.aux + pix * p.Cout + col0;
+    if (p.tf32) {
+      const float* ap = reinterpret_cast<const float*>(p.aux) + pix * p.Cout + col0;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (i < ncols) {
-        Vec<__nv_bfloat16> r;
-        r.load(ap + i);
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncols) {
+          Vec<float> r;
+          r.load(ap + i);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+          for (int j = 0; j < 4; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+        }
+      }
+    } else {
+      const __nv_bfloat16* ap = p.aux + pix * p.Cout + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncols) {
+          Vec<__nv_bfloat16> r;
+          r.load(ap + i);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+        }
       }
     }
   }
@@ -318,8 +346,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int j = 0; j < MT; ++j)
-            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kBlockK, w0[j] + dw, h0[j] + dh, n0[j]);
-          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kBlockK, wrow0);
+            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * p.kblk, w0[j] + dw, h0[j] + dh, n0[j]);
+          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * p.kblk, wrow0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           if (++cb == p.kpt) { cb = 0; ++tap; }
         }
@@ -344,7 +372,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             const uint64_t adesc = smem_desc(p.desc_templ, sa + j * kABytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16(d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+              umma_any(p.tf32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -408,6 +436,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 //   phase conv    : grid = X grid,  AS = 2, a = (p-1, q-1); BS = 1, b = 0            (16 taps)
 struct WgradParams {
   int N, Cin, Cout;
+  int tf32, chb, boxb, kadv;            // fp32/TF32 operands; channels per 128-byte box row (64 bf16 / 32 fp32);
+                                        // bytes of one TMA box (64 px x 128 B = 8192 / 32 px x 128 B = 4096); descriptor
+                                        // advance per MMA in 16-byte units (16 rows = 128 / 8 rows = 64).  A k-block is
+                                        // 64 pixels (bf16) or 32 pixels (fp32): always 4 MMAs of K = 16 / 8.
   int AS, BS;
   signed char a_dh[kMaxTaps], a_dw[kMaxTaps], b_dh[kMaxTaps], b_dw[kMaxTaps];
   int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 grid pixels
@@ -466,7 +498,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     if (i < p.bias_slots && p.bias_taps[i] == tap0) bias_slot = i;
   const bool do_bias = p.bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
   if (do_bias && warp >= 2) {
-    const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
+    const uint32_t ones2 = p.tf32 ? 0x3f800000u : 0x3f803f80u;   // fp32 1.0 / two bf16 1.0
     for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_base + 16u * i), "r"(ones2) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
@@ -504,15 +536,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int j = 0; j < kTileM / 64; ++j)
-          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
+        for (int j = 0; j < kTileM / p.chb; ++j)
+          tma_load_4d(sa + j * p.boxb, &tmap_dy, full_bar(stage), co0 + p.chb * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           if (q < ntaps) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j,
+            for (int j = 0; j < BN / p.chb; ++j)
+              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * p.boxb, &tmap_x, full_bar(stage), ci0 + p.chb * j,
                           w0 * p.BS + ds[q], h0 * p.BS + dr[q], n0);
           }
         }
@@ -534,16 +564,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
           if (q < ntaps) {
             const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes + q * Cfg::kBBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
-              umma_f16(tmem_base + q * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
-                       acc_on | (uint32_t)(k != 0));
+            for (int k = 0; k < 4; ++k)              // 16 (bf16) / 8 (tf32) pixel rows of 128 B per MMA
+              umma_any(p.tf32, tmem_base + q * BN, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv),
+                       p.idesc, acc_on | (uint32_t)(k != 0));
           }
         }
         if (do_bias) {
           const uint64_t odesc = smem_desc(p.desc_templ, ones_base);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * 128), odesc, p.idesc_bias,
+          for (int k = 0; k < 4; ++k)
+            umma_any(p.tf32, tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * p.kadv), odesc, p.idesc_bias,
                      acc_on | (uint32_t)(k != 0));
         }
         umma_commit(empty_bar(stage));
@@ -712,7 +742,7 @@ struct WgradPlan {
 };
 
 // H, W are the dims of X
-static int plan_wgrad(int kind, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
+static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
   if (Cin % 64 || Cout % 64) return fail(MCGM_E_UNSUPPORTED, "wgrad: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
   pl->AS = pl->BS = 1;
   pl->a_shift = false;
@@ -727,8 +757,9 @@ static int plan_wgrad(int kind, int N, int H, int W, int Cin, int Cout, int R, i
   } else {
     return fail(MCGM_E_ARG, "wgrad: unknown kind %d", kind);
   }
-  if (!pick_pixel_box(pl->Hg, pl->Wg, 64, &pl->KW, &pl->KH, &pl->KN))
-    return fail(MCGM_E_UNSUPPORTED, "wgrad: grid H=%d W=%d cannot be tiled into 64-pixel boxes", pl->Hg, pl->Wg);
+  // k-block = 64 grid pixels of bf16 or 32 of fp32: its operand tiles are the same bytes either way
+  if (!pick_pixel_box(pl->Hg, pl->Wg, tf32 ? 32 : 64, &pl->KW, &pl->KH, &pl->KN))
+    return fail(MCGM_E_UNSUPPORTED, "wgrad: grid H=%d W=%d cannot be tiled into k-block boxes", pl->Hg, pl->Wg);
   pl->BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
   pl->cin_tiles = Cin / pl->BN;
   pl->cout_tiles = (Cout + kTileM - 1) / kTileM;
@@ -797,12 +828,18 @@ extern "C" int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int 
 
 // kind: MCGM_CONV_S1 (stride-1 RxS, R=S in {1,3}), MCGM_CONV_S2K4 (4x4 stride 2 pad 1: out = in/2),
 // MCGM_CONV_PHASE2 (4 output phases x 2x2 taps: out = 2*in).  H, W are the INPUT dims.
-static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
+// in_dtype MCGM_BF16: x, w, res, aux bf16.  MCGM_F32: all fp32, operands read by the tensor cores as
+// TF32 (kind::tf32, K = 8 per instruction) — the fp32 parity pipeline; out_dtype must be fp32.
+static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
                          int Cin, int Cout, int R, int S, const float* bias, const void* res, const void* aux,
                          const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
   MCGM_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv_fwd: bad arguments");
   MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "conv_fwd: out_dtype %d unsupported", out_dtype);
-  if (Cin % kBlockK) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cin=%d must be a multiple of 64 (use the thin kernels)", Cin);
+  MCGM_CHECK_ARG(in_dtype == MCGM_BF16 || in_dtype == MCGM_F32, "conv_fwd: in_dtype %d unsupported", in_dtype);
+  const int tf32 = in_dtype == MCGM_F32;
+  const int kblk = tf32 ? 32 : 64;
+  if (tf32) MCGM_CHECK_ARG(out_dtype == MCGM_F32, "conv_fwd: fp32 operands need an fp32 output");
+  if (Cin % kblk) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cin=%d must be a multiple of %d (use the thin kernels)", Cin, kblk);
   if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "conv_fwd: BIAS flag without bias");
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) MCGM_CHECK_ARG(res && (Cout % 8 == 0), "conv_fwd: RES flag needs res and Cout %% 8 == 0");
   if (flags & MCGM_EPI_MASK) MCGM_CHECK_ARG(labels && bits && M > 0 && Cout % 32 == 0, "conv_fwd: MASK needs labels, bits and Cout %% 32 == 0");
@@ -811,6 +848,7 @@ static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int 
   ConvFwdParams p{};
   p.N = N; p.Cin = Cin; p.Cout = Cout;
   p.IS = 1; p.OS = 1; p.PH = 1;
+  p.tf32 = tf32; p.kblk = kblk;
   if (kind == MCGM_CONV_S1) {
     if (!((R == 1 && S == 1) || (R == 3 && S == 3))) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: only 1x1 and 3x3 stride-1 kernels (got %dx%d)", R, S);
     p.Hg = H; p.Wg = W; p.Ho = H; p.Wo = W; p.T = R * S;
@@ -849,23 +887,23 @@ static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int 
   if (p.PH > 1 && Cout % BN && Cout > 16) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: phase conv needs Cout %% %d == 0", BN);
   p.n_tiles = (Cout + BN - 1) / BN;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_nb;
-  p.kpt = Cin / kBlockK;
+  p.kpt = Cin / kblk;
   p.num_kb = p.T * p.kpt;
   p.desc_templ = make_smem_desc_hi_lbo(g_knobs.k_lbo, g_knobs.k_sbo, g_knobs.version, g_knobs.layout);
-  p.idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+  p.idesc = make_idesc_bf16(kTileM, BN, 0, 0, tf32);
   p.bias = bias; p.res = (const __nv_bfloat16*)res; p.aux = (const __nv_bfloat16*)aux;
   p.labels = labels; p.bits = bits; p.words = (Cout + 31) / 32; p.flags = flags; p.out = out;
 
   CUtensorMap mx, mw;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
-    if (int e = make_tmap(&mx, x, 4, dims, box, p.IS)) return e;
+    const uint32_t box[4] = {(uint32_t)kblk, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
+    if (int e = make_tmap(&mx, x, 4, dims, box, p.IS, tf32)) return e;
   }
   {
     const uint64_t dims[2] = {(uint64_t)p.T * Cin, (uint64_t)p.PH * Cout};
-    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)BN};
-    if (int e = make_tmap(&mw, w, 2, dims, box)) return e;
+    const uint32_t box[2] = {(uint32_t)kblk, (uint32_t)BN};
+    if (int e = make_tmap(&mw, w, 2, dims, box, 1, tf32)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = out_dtype == MCGM_F32;
@@ -886,31 +924,34 @@ static int conv_fwd_impl(int kind, const void* x, const void* w, void* out, int 
 extern "C" int mcgm_conv_fwd(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin,
                              int Cout, int R, int S, const float* bias, const void* res, const void* aux,
                              const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
-  return conv_fwd_impl(MCGM_CONV_S1, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
+  return conv_fwd_impl(MCGM_CONV_S1, MCGM_BF16, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
 }
 
-extern "C" int mcgm_conv_fwd_ex(int kind, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
-                                int Cin, int Cout, const float* bias, const void* res, const void* aux,
-                                const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
-  MCGM_CHECK_ARG(kind == MCGM_CONV_S2K4 || kind == MCGM_CONV_PHASE2, "conv_fwd_ex: kind must be S2K4 or PHASE2 (use mcgm_conv_fwd for stride-1)");
-  return conv_fwd_impl(kind, x, w, out, out_dtype, N, H, W, Cin, Cout, 0, 0, bias, res, aux, labels, bits, M, flags, stream);
+extern "C" int mcgm_conv_fwd_ex(int kind, int in_dtype, const void* x, const void* w, void* out, int out_dtype,
+                                int N, int H, int W, int Cin, int Cout, int R, int S, const float* bias,
+                                const void* res, const void* aux, const int32_t* labels, const uint32_t* bits,
+                                int M, int flags, void* stream) {
+  return conv_fwd_impl(kind, in_dtype, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
 }
 
-static size_t wgrad_ws_bytes(int kind, int N, int H, int W, int Cin, int Cout, int R, int S) {
+static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Cin, int Cout, int R, int S) {
   WgradPlan pl;
-  if (plan_wgrad(kind, N, H, W, Cin, Cout, R, S, &pl)) return 0;
+  if (plan_wgrad(kind, in_dtype == MCGM_F32, N, H, W, Cin, Cout, R, S, &pl)) return 0;
   size_t bytes = (size_t)pl.splits * pl.per_split * sizeof(float);
   bytes += (size_t)pl.splits * 4 * Cout * sizeof(float);  // bias-gradient partials (up to 4 slots)
   return bytes;
 }
 
-static int conv_wgrad_impl(int kind, const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W,
-                           int Cin, int Cout, int R, int S, void* workspace, void* stream) {
+static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
+                           int W, int Cin, int Cout, int R, int S, void* workspace, void* stream) {
   MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
+  MCGM_CHECK_ARG(in_dtype == MCGM_BF16 || in_dtype == MCGM_F32, "conv_wgrad: in_dtype %d unsupported", in_dtype);
+  const int tf32 = in_dtype == MCGM_F32;
   WgradPlan pl;
-  if (int e = plan_wgrad(kind, N, H, W, Cin, Cout, R, S, &pl)) return e;
+  if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl)) return e;
   WgradParams p{};
   p.N = N; p.Cin = Cin; p.Cout = Cout; p.AS = pl.AS; p.BS = pl.BS;
+  p.tf32 = tf32; p.chb = tf32 ? 32 : 64; p.boxb = tf32 ? 4096 : 8192; p.kadv = tf32 ? 64 : 128;
   for (int t = 0; t < pl.taps; ++t) {
     if (kind == MCGM_CONV_S1) { p.b_dh[t] = (signed char)(t / S - (R - 1) / 2); p.b_dw[t] = (signed char)(t % S - (S - 1) / 2); }
     else if (kind == MCGM_CONV_S2K4) { p.b_dh[t] = (signed char)(t / 4 - 1); p.b_dw[t] = (signed char)(t % 4 - 1); }
@@ -919,9 +960,9 @@ static int conv_wgrad_impl(int kind, const void* x, const void* dy, float* dw, f
   p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = pl.Wg / pl.KW; p.kb_h = pl.Hg / pl.KH;
   p.total_kb = pl.total_kb; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
   p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
-  p.desc_templ = make_smem_desc_hi_lbo(g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
-  p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1);
-  p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1);
+  p.desc_templ = make_smem_desc_hi_lbo(tf32 ? 4096 : g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
+  p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1, tf32);
+  p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1, tf32);
   p.partial = (float*)workspace;
   p.bias_partial = dbias ? p.partial + (size_t)pl.splits * pl.per_split : nullptr;
   p.bias_slots = 1; p.bias_taps[0] = 0;
@@ -934,13 +975,13 @@ static int conv_wgrad_impl(int kind, const void* x, const void* dy, float* dw, f
   CUtensorMap mdy, mx;
   {
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
-    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
-    if (int e = make_tmap(&mdy, dy, 4, dims, box, pl.AS)) return e;
+    const uint32_t box[4] = {(uint32_t)p.chb, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
+    if (int e = make_tmap(&mdy, dy, 4, dims, box, pl.AS, tf32)) return e;
   }
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
-    if (int e = make_tmap(&mx, x, 4, dims, box, pl.BS)) return e;
+    const uint32_t box[4] = {(uint32_t)p.chb, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
+    if (int e = make_tmap(&mx, x, 4, dims, box, pl.BS, tf32)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = pl.cout_tiles * pl.cin_tiles * pl.tap_groups * pl.splits;
@@ -960,17 +1001,18 @@ static int conv_wgrad_impl(int kind, const void* x, const void* dy, float* dw, f
 }
 
 extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {
-  return wgrad_ws_bytes(MCGM_CONV_S1, N, H, W, Cin, Cout, R, S);
+  return wgrad_ws_bytes(MCGM_CONV_S1, MCGM_BF16, N, H, W, Cin, Cout, R, S);
 }
 extern "C" int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
                                int Cout, int R, int S, void* workspace, void* stream) {
-  return conv_wgrad_impl(MCGM_CONV_S1, x, dy, dw, dbias, N, H, W, Cin, Cout, R, S, workspace, stream);
+  return conv_wgrad_impl(MCGM_CONV_S1, MCGM_BF16, x, dy, dw, dbias, N, H, W, Cin, Cout, R, S, workspace, stream);
 }
-extern "C" size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int N, int H, int W, int Cin, int Cout) {
-  return wgrad_ws_bytes(kind, N, H, W, Cin, Cout, 0, 0);
+extern "C" size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int in_dtype, int N, int H, int W, int Cin, int Cout,
+                                                     int R, int S) {
+  return wgrad_ws_bytes(kind, in_dtype, N, H, W, Cin, Cout, R, S);
 }
-extern "C" int mcgm_conv_wgrad_ex(int kind, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
-                                  int W, int Cin, int Cout, void* workspace, void* stream) {
-  MCGM_CHECK_ARG(kind == MCGM_CONV_S2K4 || kind == MCGM_CONV_PHASE2, "conv_wgrad_ex: kind must be S2K4 or PHASE2");
-  return conv_wgrad_impl(kind, x, dy, dw, dbias, N, H, W, Cin, Cout, 0, 0, workspace, stream);
+extern "C" int mcgm_conv_wgrad_ex(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias,
+                                  int N, int H, int W, int Cin, int Cout, int R, int S, void* workspace,
+                                  void* stream) {
+  return conv_wgrad_impl(kind, in_dtype, x, dy, dw, dbias, N, H, W, Cin, Cout, R, S, workspace, stream);
 }

