@@ -195,26 +195,6 @@ size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int in_dtype, int N, int H, 
 int mcgm_conv_wgrad_ex(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias,
                        int N, int H, int W, int Cin, int Cout, int R, int S, void* workspace, void* stream);
 
-/* ---- thin convolutions: one side has <= 4 channels (RGB image side of
- * Conv2d(3,128,...) mcgan.py:77,87 and Conv2d(256,3,3,1,1) mcgan.py:59).
- * HBM-bound CUDA-core kernels.  `thin` is fp32 NHWC [N,H,W,Ct] (Ct <= 4),
- * `wide` is bf16 NHWC [N,H,W,Cw] (Cw % 8 == 0), kern is fp32 [R*S][Ct][Cw].
- *   wide_from_thin : wide[p,c]  = sum_{t,j} thin[p+off(t), j] * kern[t][j][c]  (+bias, ReLU, mask)
- *   thin_from_wide : thin[p,j]  = sum_{t,c} wide[p+off(t), c] * kern[t][j][c]  (+bias, tanh)
- *   kern_grad      : dkern[t][j][c] = sum_p thin[p+off(t), j] * wide[p, c]
- * off(t) = (r - pad, s - pad), t = r*S + s. */
-int mcgm_thin_wide_from_thin(const float* thin, const float* kern, void* wide,
-                             int N, int H, int W, int Ct, int Cw, int R, int S,
-                             const float* bias, const int32_t* labels, const uint32_t* bits, int M,
-                             const void* aux, int flags, void* stream);
-int mcgm_thin_thin_from_wide(const void* wide, const float* kern, float* thin,
-                             int N, int H, int W, int Ct, int Cw, int R, int S,
-                             const float* bias, int flags, void* stream);
-size_t mcgm_thin_kern_grad_workspace_bytes(int Ct, int Cw, int R, int S);
-int mcgm_thin_kern_grad(const float* thin, const void* wide, float* dkern,
-                        int N, int H, int W, int Ct, int Cw, int R, int S,
-                        void* workspace, void* stream);
-
 /* ---- thin convolutions on the tensor cores: im2col / col2im of the THIN tensor only.
  *   im2col : U[p, t*Ct + j] = thin[stride*p +/- off(t), j]  bf16 [N,Ho,Wo,KU], zero padded; off(t) =
  *            (r - pad, s - pad); flip: -off (stride 1 only).  stride 2 / 4x4 / pad 1 serves

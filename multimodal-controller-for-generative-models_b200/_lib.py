@@ -51,13 +51,6 @@ SIGNATURES = {
     "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mcgm_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p]),
-    "mcgm_thin_wide_from_thin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                         c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
-    "mcgm_thin_thin_from_wide": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                         c_int, c_void_p, c_int, c_void_p]),
-    "mcgm_thin_kern_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "mcgm_thin_kern_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                    c_void_p, c_void_p]),
     "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "mcgm_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p]),

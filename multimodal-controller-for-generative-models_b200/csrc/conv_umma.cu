@@ -186,7 +186,7 @@ struct FwdCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool TF32>
 __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uint32_t (&acc)[32], int ncols,
                                                      long pix, int n, int h, int w, int col0, bool valid) {
   // acc: fp32 bit patterns of `ncols` consecutive output channels starting at col0
@@ -203,7 +203,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
     long rpix = pix;
     if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
-    if (p.tf32) {                                          // fp32 pipeline: residual is fp32
+    if constexpr (TF32) {                                  // fp32 pipeline: residual is fp32
       const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.Cout + col0;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
     for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.0f;
   }
   if (flags & MCGM_EPI_POSMASK) {
-    if (p.tf32) {
+    if constexpr (TF32) {
       const float* ap = reinterpret_cast<const float*>(p.aux) + pix * p.Cout + col0;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -288,11 +288,12 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   }
 }
 
-template <int BN, int MT, typename OutT>
+template <int BN, int MT, typename OutT, bool TF32>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const ConvFwdParams p) {
   using Cfg = FwdCfg<BN, MT>;
+  constexpr int kElems = TF32 ? 32 : 64;                 // operand elements per 128-byte k-block row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -346,8 +347,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int j = 0; j < MT; ++j)
-            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * p.kblk, w0[j] + dw, h0[j] + dh, n0[j]);
-          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * p.kblk, wrow0);
+            tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kElems, w0[j] + dw, h0[j] + dh, n0[j]);
+          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kElems, wrow0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           if (++cb == p.kpt) { cb = 0; ++tap; }
         }
@@ -372,7 +373,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             const uint64_t adesc = smem_desc(p.desc_templ, sa + j * kABytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_any(p.tf32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+              umma_any(TF32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -410,7 +411,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if constexpr (CW == 32) tmem_ld32(t_row + c, acc);
           else tmem_ld16(t_row + c, acc);
           tmem_ld_wait();
-          epilogue_store_chunk<BN, OutT>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
+          epilogue_store_chunk<BN, OutT, TF32>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
         }
       }
       tc_fence_before();
@@ -436,10 +437,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 //   phase conv    : grid = X grid,  AS = 2, a = (p-1, q-1); BS = 1, b = 0            (16 taps)
 struct WgradParams {
   int N, Cin, Cout;
-  int tf32, chb, boxb, kadv;            // fp32/TF32 operands; channels per 128-byte box row (64 bf16 / 32 fp32);
-                                        // bytes of one TMA box (64 px x 128 B = 8192 / 32 px x 128 B = 4096); descriptor
-                                        // advance per MMA in 16-byte units (16 rows = 128 / 8 rows = 64).  A k-block is
-                                        // 64 pixels (bf16) or 32 pixels (fp32): always 4 MMAs of K = 16 / 8.
   int AS, BS;
   signed char a_dh[kMaxTaps], a_dw[kMaxTaps], b_dh[kMaxTaps], b_dw[kMaxTaps];
   int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 grid pixels
@@ -498,7 +495,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     if (i < p.bias_slots && p.bias_taps[i] == tap0) bias_slot = i;
   const bool do_bias = p.bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
   if (do_bias && warp >= 2) {
-    const uint32_t ones2 = p.tf32 ? 0x3f800000u : 0x3f803f80u;   // fp32 1.0 / two bf16 1.0
+    const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
     for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones_base + 16u * i), "r"(ones2) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
@@ -536,13 +533,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        for (int j = 0; j < kTileM / p.chb; ++j)
-          tma_load_4d(sa + j * p.boxb, &tmap_dy, full_bar(stage), co0 + p.chb * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
+#pragma unroll
+        for (int j = 0; j < kTileM / 64; ++j)
+          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           if (q < ntaps) {
-            for (int j = 0; j < BN / p.chb; ++j)
-              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * p.boxb, &tmap_x, full_bar(stage), ci0 + p.chb * j,
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j,
                           w0 * p.BS + ds[q], h0 * p.BS + dr[q], n0);
           }
         }
@@ -564,16 +563,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
           if (q < ntaps) {
             const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes + q * Cfg::kBBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)              // 16 (bf16) / 8 (tf32) pixel rows of 128 B per MMA
-              umma_any(p.tf32, tmem_base + q * BN, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv),
-                       p.idesc, acc_on | (uint32_t)(k != 0));
+            for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
+              umma_f16(tmem_base + q * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
+                       acc_on | (uint32_t)(k != 0));
           }
         }
         if (do_bias) {
           const uint64_t odesc = smem_desc(p.desc_templ, ones_base);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_any(p.tf32, tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * p.kadv), odesc, p.idesc_bias,
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * 128), odesc, p.idesc_bias,
                      acc_on | (uint32_t)(k != 0));
         }
         umma_commit(empty_bar(stage));
@@ -695,10 +694,10 @@ static bool pick_pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return true;
 }
 
-template <int BN, int MT, typename OutT>
+template <int BN, int MT, typename OutT, bool TF32 = false>
 static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParams p, cudaStream_t st) {
   using Cfg = FwdCfg<BN, MT>;
-  auto kern = conv_fwd_kernel<BN, MT, OutT>;
+  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32>;
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -716,6 +715,7 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParam
 
 template <int BN, int MT>
 static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFwdParams& p, bool f32, cudaStream_t st) {
+  if (p.tf32) return launch_fwd<BN, MT, float, true>(mx, mw, p, st);      // fp32 parity pipeline
   return f32 ? launch_fwd<BN, MT, float>(mx, mw, p, st) : launch_fwd<BN, MT, __nv_bfloat16>(mx, mw, p, st);
 }
 
@@ -945,13 +945,15 @@ static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Ci
 static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
                            int W, int Cin, int Cout, int R, int S, void* workspace, void* stream) {
   MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
-  MCGM_CHECK_ARG(in_dtype == MCGM_BF16 || in_dtype == MCGM_F32, "conv_wgrad: in_dtype %d unsupported", in_dtype);
-  const int tf32 = in_dtype == MCGM_F32;
+  // MN-major TF32 operands need the 128B/32B-atom swizzle on both the TMA and the UMMA side; with the plain
+  // 128B swizzle used here the tensor cores return zeros (measured).  The fp32 parity pipeline therefore
+  // computes weight gradients from bf16x3 operand pieces on this (bf16) kernel instead.
+  if (in_dtype != MCGM_BF16) return fail(MCGM_E_UNSUPPORTED, "conv_wgrad: only bf16 operands (fp32 parity mode uses bf16x3 pieces)");
+  const int tf32 = 0;
   WgradPlan pl;
   if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl)) return e;
   WgradParams p{};
   p.N = N; p.Cin = Cin; p.Cout = Cout; p.AS = pl.AS; p.BS = pl.BS;
-  p.tf32 = tf32; p.chb = tf32 ? 32 : 64; p.boxb = tf32 ? 4096 : 8192; p.kadv = tf32 ? 64 : 128;
   for (int t = 0; t < pl.taps; ++t) {
     if (kind == MCGM_CONV_S1) { p.b_dh[t] = (signed char)(t / S - (R - 1) / 2); p.b_dw[t] = (signed char)(t % S - (S - 1) / 2); }
     else if (kind == MCGM_CONV_S2K4) { p.b_dh[t] = (signed char)(t / 4 - 1); p.b_dw[t] = (signed char)(t % 4 - 1); }
@@ -975,12 +977,12 @@ static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy
   CUtensorMap mdy, mx;
   {
     const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
-    const uint32_t box[4] = {(uint32_t)p.chb, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
+    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
     if (int e = make_tmap(&mdy, dy, 4, dims, box, pl.AS, tf32)) return e;
   }
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {(uint32_t)p.chb, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
+    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
     if (int e = make_tmap(&mx, x, 4, dims, box, pl.BS, tf32)) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;

@@ -345,24 +345,6 @@ def conv_fwd_tf32(kind, x, w, R=0, S=0, bias=None, res=None, aux=None, labels=No
     return out
 
 
-def conv_wgrad_tf32(kind, x, dy, R=0, S=0, want_bias=True):
-    """fp32 operands, TF32 tensor cores: dw fp32 [Cout, taps, Cin] (taps = R*S or 16) and dbias."""
-    _check_cuda(x, dy)
-    N, H, W, Cin = x.shape
-    Cout = dy.shape[-1]
-    nbytes = _lib.query("mcgm_conv_wgrad_ex_workspace_bytes", kind, F32, N, H, W, Cin, Cout, R, S)
-    if nbytes == 0:
-        raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} kind={kind}")
-    ws = _workspace("wgrad", nbytes, x.device)
-    taps = R * S if kind == CONV_S1 else 16
-    dw = torch.empty(Cout, taps, Cin, dtype=torch.float32, device=x.device)
-    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
-    _lib.call("mcgm_conv_wgrad_ex", kind, F32, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin,
-              Cout, R, S, ws.data_ptr(), _stream())
-    _lib.launch_count += 1
-    return dw, db
-
-
 def split_tf32(x):
     """x (fp32) -> (big, small), both exactly TF32-representable, big + small = x up to 2^-21."""
     _check_cuda(x)
@@ -468,40 +450,6 @@ def unpool2(dy, scale):
     dx = torch.empty(N, 2 * H, 2 * W, C, dtype=dy.dtype, device=dy.device)
     _lib.call("mcgm_unpool2", dy.data_ptr(), dx.data_ptr(), _dtype_code(dy), N, H, W, C, float(scale), _stream())
     return dx
-
-
-def wide_from_thin(thin, kern, Cw, R, S, bias=None, labels=None, packed=None, aux=None, flags=0):
-    _check_cuda(thin, kern, bias, labels, aux)
-    N, H, W, Ct = thin.shape
-    wide = torch.empty(N, H, W, Cw, dtype=torch.bfloat16, device=thin.device)
-    if bias is not None:
-        flags |= EPI_BIAS
-    _lib.call("mcgm_thin_wide_from_thin", thin.data_ptr(), kern.data_ptr(), wide.data_ptr(), N, H, W, Ct, Cw, R, S,
-              _ptr(bias), _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
-              _ptr(aux), flags, _stream())
-    return wide
-
-
-def thin_from_wide(wide, kern, Ct, R, S, bias=None, flags=0):
-    _check_cuda(wide, kern, bias)
-    N, H, W, Cw = wide.shape
-    thin = torch.empty(N, H, W, Ct, dtype=torch.float32, device=wide.device)
-    if bias is not None:
-        flags |= EPI_BIAS
-    _lib.call("mcgm_thin_thin_from_wide", wide.data_ptr(), kern.data_ptr(), thin.data_ptr(), N, H, W, Ct, Cw, R, S,
-              _ptr(bias), flags, _stream())
-    return thin
-
-
-def kern_grad(thin, wide, R, S):
-    _check_cuda(thin, wide)
-    N, H, W, Ct = thin.shape
-    Cw = wide.shape[-1]
-    ws = _workspace("kgrad", _lib.query("mcgm_thin_kern_grad_workspace_bytes", Ct, Cw, R, S), thin.device)
-    dk = torch.empty(R * S, Ct, Cw, dtype=torch.float32, device=thin.device)
-    _lib.call("mcgm_thin_kern_grad", thin.data_ptr(), wide.data_ptr(), dk.data_ptr(), N, H, W, Ct, Cw, R, S,
-              ws.data_ptr(), _stream())
-    return dk
 
 
 # --------------------------------------------------------------------------- autograd Functions
