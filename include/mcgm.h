@@ -48,6 +48,9 @@ extern "C" {
 #define MCGM_GATE_RELU 2      /* ReLU before the mask */
 #define MCGM_GATE_UP2 4       /* nearest 2x upsample on write (fwd) / 2x2 sum on read (bwd) */
 #define MCGM_GATE_MASK 8      /* multiply by codebook[label[n], c] */
+#define MCGM_GATE_AFFINE 16   /* with GATE_BN: (mean, rstd, gamma, beta) are fixed parameters (Glow's ActNorm,
+                                 mcglow.py:24-55: y = scale*(x+loc) -> mean=-loc, rstd=1, gamma=scale, beta=0);
+                                 backward returns dgamma = sum g*(x-mean)*rstd, dbeta = sum g, dx = gamma*rstd*g */
 
 /* conv epilogue flags */
 #define MCGM_EPI_BIAS 1

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcgm.so")
 
 F32, BF16 = 0, 1
-GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK = 1, 2, 4, 8
+GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK, GATE_AFFINE = 1, 2, 4, 8, 16
 EPI_BIAS, EPI_RES, EPI_RES_UP2, EPI_RELU, EPI_MASK, EPI_TANH, EPI_POSMASK = 1, 2, 4, 8, 16, 32, 64
 CONV_S1, CONV_S2K4, CONV_PHASE2 = 0, 1, 2
 

@@ -399,8 +399,12 @@ gate_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ d_raw, con
       const float mu = mean[c], rs = rstd[c];
       a[i] = gamma[c] * rs;
       b[i] = fmaf(-mu, a[i], beta[c]);
-      c1[i] = -a[i] * rs * (dgamma[c] * invP);
-      c0[i] = -a[i] * (dbeta[c] * invP) - c1[i] * mu;
+      if (flags & MCGM_GATE_AFFINE) {            // ActNorm: (mean, rstd) are parameters, not batch statistics
+        c0[i] = c1[i] = 0.0f;
+      } else {
+        c1[i] = -a[i] * rs * (dgamma[c] * invP);
+        c0[i] = -a[i] * (dbeta[c] * invP) - c1[i] * mu;
+      }
     } else {
       a[i] = 1.f; b[i] = 0.f; c0[i] = c1[i] = 0.f;
     }

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (BF16, CONV_PHASE2, CONV_S1, CONV_S2K4, EPI_BIAS, EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_TANH, F32,
-                   GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2)
+                   GATE_AFFINE, GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2)
 
 
 # --------------------------------------------------------------------------- helpers
@@ -501,6 +501,29 @@ class GateFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
+class ActNormGateFn(torch.autograd.Function):
+    """Glow coupling-net gate: ActNorm(logdet=False) -> ReLU -> MC mask (src/models/mcglow.py:139-146)
+    in one kernel pair: y = mask * relu(scale * (x + loc)); dx = mask*relu' * scale * dy,
+    dscale = sum g*(x+loc), dloc = scale * sum g."""
+
+    @staticmethod
+    def forward(ctx, x, scale, loc, labels, packed):
+        C = x.shape[-1]
+        sc, lc = scale.detach().reshape(C).contiguous(), loc.detach().reshape(C).contiguous()
+        mean, rstd, beta = -lc, torch.ones_like(sc), torch.zeros_like(sc)
+        flags = GATE_BN | GATE_AFFINE | GATE_RELU | GATE_MASK
+        y, _ = gate_fwd(x, flags, labels, packed, mean, rstd, sc, beta, False)
+        ctx.save_for_backward(x, sc, mean, rstd, beta)
+        ctx.labels, ctx.packed, ctx.flags, ctx.pshape = labels, packed, flags, scale.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, sc, mean, rstd, beta = ctx.saved_tensors
+        dx, dgamma, dbeta = gate_bwd(dy.contiguous(), None, x, ctx.flags, ctx.labels, ctx.packed, mean, rstd, sc, beta)
+        return dx, dgamma.reshape(ctx.pshape), (sc * dbeta).reshape(ctx.pshape), None, None
+
+
 class ConvFn(torch.autograd.Function):
     """3x3 / 1x1 stride-1 conv on tensor cores with fused epilogue.
 
@@ -514,7 +537,7 @@ class ConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn):
+    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn, out_f32=False):
         # sn: [1/sigma | u | v] snapshot of a spectral-normed layer (w is then weight_orig)
         f32 = x.dtype == torch.float32           # fp32 parity pipeline (cfg['compute_dtype'] = 'fp32')
         if f32:
@@ -535,7 +558,7 @@ class ConvFn(torch.autograd.Function):
         else:
             if res is not None:
                 flags |= EPI_RES_UP2 if res_up else EPI_RES
-            out = conv_fwd(x, wf, torch.bfloat16, bias, res, None, labels, packed, flags)
+            out = conv_fwd(x, wf, torch.float32 if out_f32 else torch.bfloat16, bias, res, None, labels, packed, flags)
         ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn)
         ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
         ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
@@ -546,6 +569,8 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dout):
         x, out, w_orig, sn = ctx.saved_tensors
         dout = dout.contiguous()
+        if dout.dtype != x.dtype:
+            dout = dout.to(x.dtype)                 # fp32-output convs: gradients re-enter the bf16 pipeline
         K, C, R, S = ctx.wshape
         if ctx.gated and not ctx.grad_premasked:
             # d(pre) = dout * 1[out > 0]   (mask already folded: out == 0 where masked)
@@ -572,7 +597,7 @@ class ConvFn(torch.autograd.Function):
                 dw = dw_krsc.permute(0, 3, 1, 2)      # KRSC -> OIHW view
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = pool2(dout, 1.0) if ctx.res_up else dout
-        return dx, dw, db, dres, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None
 
 
 def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None, dtype=torch.bfloat16):

@@ -200,6 +200,55 @@ def main():
     torch.randn_like = _randn_like
     print('vae loss', case['loss_fwd'], case['loss_step2'])
 
+    # --- MCGlow (CIFAR10-shaped; K=2 flows per level and hidden 128 keep the fixture small — the full
+    #     K=16 / hidden 512 model is the same code path): data-dependent ActNorm init, loss, gradients, one step
+    cfg.update(device='cpu', data_name='CIFAR10', model_name='mcglow', control={'controller_rate': '0.5'})
+    process_control()
+    cfg['classes_size'] = 10
+    cfg['glow']['K'] = 2
+    cfg['glow']['hidden_size'] = 128
+    torch.manual_seed(0)
+    np.random.seed(0)
+    m = models.mcglow()
+    batch = 16
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    label = torch.randint(0, 10, (batch,), generator=g)
+    noise = torch.rand(batch, 3, 32, 32, generator=g)
+    _rand_like = torch.rand_like
+    torch.rand_like = lambda t: noise.clone()                 # inject the dequantisation noise (mcglow.py:299)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    case = {'data_name': 'CIFAR10', 'classes': 10, 'seed': 0, 'np_seed': 0, 'input_seed': 1, 'batch': batch,
+            'model': 'mcglow', 'K': 2, 'hidden_size': 128, 'state_dict_sha256': sd_hash(sd0),
+            'keys': [[k, list(v.shape)] for k, v in sd0.items()]}
+    m.train(True)
+    with torch.no_grad():                                     # train_glow.py:60-67: the init pass
+        out_init = m({'img': img, 'label': label})
+    case['loss_init'] = float(out_init['loss'])
+    sd_init = {k: v.clone() for k, v in m.state_dict().items()}
+    out = m({'img': img, 'label': label})
+    out['loss'].backward()
+    case['loss_fwd'] = float(out['loss'].detach())
+    case['grad_norms'] = {k: float(p.grad.norm()) for k, p in m.named_parameters() if p.grad is not None}
+    arrays = {'img': img.numpy(), 'label': label.numpy(), 'noise': noise.numpy()}
+    for i, zt in enumerate(out['z']):
+        arrays[f'z{i}'] = zt.detach().numpy()
+    for k in ('blocks.0.flows.0.actnorm.loc', 'blocks.0.flows.0.coupling.net.1.module.scale',
+              'blocks.2.flows.1.coupling.net.5.module.loc'):
+        arrays['init/' + k] = sd_init[k].numpy()
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4, weight_decay=0)
+    opt.zero_grad()
+    out = m({'img': img, 'label': label})
+    out['loss'].backward()
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1)
+    opt.step()
+    out2 = m({'img': img, 'label': label})
+    case['loss_step2'] = float(out2['loss'].detach())
+    torch.rand_like = _rand_like
+    np.savez_compressed(os.path.join(OUT, 'glow_small.npz'), **arrays)
+    meta['cases']['glow_small'] = case
+    print('glow loss', case['loss_init'], case['loss_fwd'], case['loss_step2'])
+
     with open(os.path.join(OUT, 'mcgan_golden.json'), 'w') as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print('wrote', OUT)
