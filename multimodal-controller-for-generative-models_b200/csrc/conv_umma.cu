@@ -141,7 +141,8 @@ static DescKnobs g_knobs;
 // ---------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------
-static constexpr int kConvThreads = 192;
+static constexpr int kConvThreads = 320;     // forward: TMA warp + MMA warp + 8 epilogue warps (2 per TMEM lane quadrant)
+static constexpr int kWgradThreads = 192;    // wgrad: TMA warp + MMA warp + 4 epilogue warps
 static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                       // bf16 elements = 128 B rows
 static constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
@@ -196,9 +197,19 @@ __device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uin
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   const int flags = p.flags;
   if (flags & MCGM_EPI_BIAS) {
+    if ((p.Cout & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols && col0 + i < p.Cout) v[i] += __ldg(p.bias + col0 + i);
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncols && col0 + i < p.Cout) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols && col0 + i < p.Cout) v[i] += __ldg(p.bias + col0 + i);
+    }
   }
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
     long rpix = pix;
@@ -310,7 +321,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kConvThreads - 64); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -382,36 +393,50 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quadrant = warp % 4) =====
-    const int quad = warp & 3;
+    // ===== epilogue: 8 warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); the two warps of a
+    // quadrant split the accumulator columns.  The epilogue used to be latency-bound (one warp per SM
+    // sub-partition, TMEM load -> wait -> math -> store serialised): two warps per sub-partition plus
+    // a software pipeline (the TMEM load of chunk c+1 is in flight while chunk c is processed) keep it
+    // shorter than the main loop even for K = 4..18 k-blocks (1x1, phase and 128-wide convs).
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
+    constexpr int CW = BN < 32 ? BN : 32;                    // columns per TMEM load
+    constexpr int HALF = (BN / 2 >= CW) ? BN / 2 : BN;       // columns per warp (narrow tiles: warp half 0 only)
+    constexpr int NCH = HALF / CW;
+    const bool works = half * HALF < BN;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
       const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
       const int mt0 = ms * MT;
-      const int cout0 = nt * BN;
+      const int cout0 = nt * BN + half * HALF;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (works) {
 #pragma unroll 1
-      for (int j = 0; j < MT; ++j) {
-        const int mt = mt0 + j;
-        const int wg = (mt % p.tiles_w) * p.TW + tw;
-        const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
-        const int n = (mt / tiles_per_img_block) * p.TN + tn;
-        const bool valid = (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
-        const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
-        const long pix = ((long)n * p.Ho + h) * p.Wo + w;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + j * BN;
-        constexpr int CW = BN < 32 ? BN : 32;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += CW) {
-          uint32_t acc[32];
-          if constexpr (CW == 32) tmem_ld32(t_row + c, acc);
-          else tmem_ld16(t_row + c, acc);
-          tmem_ld_wait();
-          epilogue_store_chunk<BN, OutT, TF32>(p, acc, CW, pix, n, h, w, cout0 + c, valid && (cout0 + c < p.Cout));
+        for (int j = 0; j < MT; ++j) {
+          const int mt = mt0 + j;
+          const int wg = (mt % p.tiles_w) * p.TW + tw;
+          const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+          const int n = (mt / tiles_per_img_block) * p.TN + tn;
+          const bool valid = (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
+          const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
+          const long pix = ((long)n * p.Ho + h) * p.Wo + w;
+          const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + j * BN + half * HALF;
+          uint32_t acc[2][32];
+          if constexpr (CW == 32) tmem_ld32(t_row, acc[0]);
+          else tmem_ld16(t_row, acc[0]);
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            tmem_ld_wait();
+            if (ci + 1 < NCH) {
+              if constexpr (CW == 32) tmem_ld32(t_row + (ci + 1) * CW, acc[(ci + 1) & 1]);
+              else tmem_ld16(t_row + (ci + 1) * CW, acc[(ci + 1) & 1]);
+            }
+            epilogue_store_chunk<BN, OutT, TF32>(p, acc[ci & 1], CW, pix, n, h, w, cout0 + ci * CW,
+                                                 valid && (cout0 + ci * CW < p.Cout));
+          }
         }
       }
       tc_fence_before();
@@ -464,7 +489,7 @@ struct WgCfg {
 };
 
 template <int BN, int NT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
   using Cfg = WgCfg<BN, NT>;
@@ -729,7 +754,7 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mdy, mx, p);
+  kern<<<grid, kWgradThreads, Cfg::kSmemBytes, st>>>(mdy, mx, p);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -9,10 +9,10 @@ $NCU --metrics gpu__time_duration.sum -s 440 -c 3000 --csv --log-file gpurun_out
 timeout 300 python tools/profile_step.py --mode g --warm 1 > gpurun_out/plain_g.log 2>&1 && \
 $NCU --metrics gpu__time_duration.sum -s 440 -c 3000 --csv --log-file gpurun_out/launches_g.csv python tools/profile_step.py --mode g --warm 1 > gpurun_out/ncu_g.log 2>&1
 timeout 300 python tools/profile_step.py --mode d > gpurun_out/plain_d0.log 2>&1 && \
-$NCU --set full --import-source on -k regex:"conv_fwd_kernel<256" -s 7 -c 2 -o gpurun_out/prof_conv_fwd python tools/profile_step.py --mode d > gpurun_out/ncu_full1.log 2>&1
-$NCU --set full --import-source on -k regex:"conv_fwd_kernel<128, 2" -s 0 -c 3 -o gpurun_out/prof_conv_fwd_d python tools/profile_step.py --mode d > gpurun_out/ncu_full1b.log 2>&1
+
+
 $NCU --set full --import-source on -k regex:"gate_fwd_kernel|bn_partial_kernel" -s 12 -c 6 -o gpurun_out/prof_gate_fwd python tools/profile_step.py --mode d > gpurun_out/ncu_full2.log 2>&1
 timeout 300 python tools/profile_step.py --mode g > gpurun_out/plain_g0.log 2>&1 && \
-$NCU --set full --import-source on -k regex:"conv_wgrad_kernel<256" -s 1 -c 2 -o gpurun_out/prof_wgrad python tools/profile_step.py --mode g > gpurun_out/ncu_full3.log 2>&1
+bash tools/ncu_conv.sh
 $NCU --set full --import-source on -k regex:"gate_bwd_reduce_kernel|gate_bwd_apply_kernel" -s 4 -c 4 -o gpurun_out/prof_gate_bwd python tools/profile_step.py --mode g > gpurun_out/ncu_full4.log 2>&1
 ls -la gpurun_out | head -30
