@@ -252,8 +252,8 @@ def run_native(args):
 
         def agg(tag):
             recs = prof.get(tag, [])
-            t = sum(a.elapsed_time(b) for a, b, _ in recs) * 1e-3
-            return len(recs), t, sum(w for _, _, w in recs)
+            t = sum(r[0].elapsed_time(r[1]) for r in recs) * 1e-3
+            return len(recs), t, sum(r[2] for r in recs)
         n, t, fl = agg("conv")
         if n:
             peak = peaks["bf16_tflops_sustained"]

@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcgm.so")
+# MCGM_LIB_PATH: developer override for A/B runs of kernel variants (tools/); the product loads the in-tree build
+LIB_PATH = os.environ.get("MCGM_LIB_PATH") or os.path.join(_HERE, "libmcgm.so")
 
 F32, BF16 = 0, 1
 GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK, GATE_AFFINE = 1, 2, 4, 8, 16

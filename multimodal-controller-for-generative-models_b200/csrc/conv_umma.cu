@@ -148,6 +148,7 @@ static constexpr int kBlockK = 64;                       // bf16 elements = 128 
 static constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
 
 static constexpr int kMaxTaps = 16;
+static constexpr int kMaxBiasBytes = 2048;           // forward: bias of up to 512 (padded) output channels in smem
 
 // Geometry of the generalised forward conv.  M tiles are laid on a TILE GRID (Hg x Wg per image):
 //   plain stride-1 conv   : grid = output = input, taps = R*S with offsets (r-pad, s-pad)
@@ -184,118 +185,129 @@ struct FwdCfg {
   static constexpr int kAccStages = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int kTmemRaw = kAccStages * MT * BN;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // No alignment slack: the dynamic window is declared 1024-byte aligned (the kernel traps if the base it
+  // gets is not).  The total must stay under the 196 KB shared-memory carve-out (200704 B incl. 1 KB the
+  // system reserves): one step more and L1 drops from 60 KB to 28 KB, which costs the epilogue's row-strided
+  // loads and stores 10-40 % (measured on the 1x1 / thin / residual convs).
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kMaxBiasBytes;
+  static_assert(kSmemBytes + 1024 <= 200704, "forward conv must fit the 196 KB carve-out");
 };
 
-template <int BN, typename OutT, bool TF32>
-__device__ __forceinline__ void epilogue_store_chunk(const ConvFwdParams& p, uint32_t (&acc)[32], int ncols,
-                                                     long pix, int n, int h, int w, int col0, bool valid) {
-  // acc: fp32 bit patterns of `ncols` consecutive output channels starting at col0
+// One chunk (CW <= 32 consecutive output channels of one pixel) of the fused epilogue.
+//   acc    fp32 bit patterns from TMEM
+//   sbias  shared-memory bias of these columns (zero-padded; staged once per CTA)
+//   mbits  codebook bits of these columns for the sample of this pixel, fetched one chunk ahead
+//   sd     bf16 pipeline: the residual row of these columns (RES / RES_UP2), else the ReLU-sign row
+//          (POSMASK), fetched one chunk ahead.  With both flags the sign row is read in place; the fp32
+//          parity pipeline (TF32) reads everything in place.
+template <int CW, bool GENERIC_STORE, typename OutT, bool TF32>
+__device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int flags, uint32_t (&acc)[32],
+                                               const long pix, const long rpix, const int col0, const bool valid,
+                                               const float* sbias, const uint32_t mbits, const uint4 (&sd)[4]) {
   if (!valid) return;
   float v[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-  const int flags = p.flags;
+  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(acc[i]);
   if (flags & MCGM_EPI_BIAS) {
-    if ((p.Cout & 3) == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncols && col0 + i < p.Cout) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < ncols && col0 + i < p.Cout) v[i] += __ldg(p.bias + col0 + i);
+    for (int i = 0; i < CW; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);      // warp-uniform address: broadcast
+      v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
     }
   }
-  if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
-    long rpix = pix;
-    if (flags & MCGM_EPI_RES_UP2) rpix = ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1);
+  const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
+  if (res_on) {
     if constexpr (TF32) {                                  // fp32 pipeline: residual is fp32
       const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncols) {
-          Vec<float> r;
-          r.load(rp + i);
+      for (int i = 0; i < CW; i += 4) {
+        Vec<float> r;
+        r.load(rp + i);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[i + j] += r.v[j];
-        }
+        for (int j = 0; j < 4; ++j) v[i + j] += r.v[j];
       }
     } else {
-      const __nv_bfloat16* rp = p.res + rpix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          Vec<__nv_bfloat16> r;
-          r.load(rp + i);
+      for (int i = 0; i < CW; i += 8) {
+        float r[8];
+        unpack16<__nv_bfloat16>(sd[i / 8], r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i + j] += r.v[j];
-        }
+        for (int j = 0; j < 8; ++j) v[i + j] += r[j];
       }
     }
   }
   if (flags & MCGM_EPI_RELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.0f);
   }
   if (flags & MCGM_EPI_MASK) {
-    const uint32_t m = __ldg(p.bits + (size_t)__ldg(p.labels + n) * p.words + (col0 >> 5)) >> (col0 & 31);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = ((m >> i) & 1u) ? v[i] : 0.0f;
+    for (int i = 0; i < CW; ++i) v[i] = ((mbits >> i) & 1u) ? v[i] : 0.0f;
   }
   if (flags & MCGM_EPI_POSMASK) {
     if constexpr (TF32) {
       const float* ap = reinterpret_cast<const float*>(p.aux) + pix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncols) {
-          Vec<float> r;
-          r.load(ap + i);
+      for (int i = 0; i < CW; i += 4) {
+        Vec<float> r;
+        r.load(ap + i);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
-        }
+        for (int j = 0; j < 4; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
       }
-    } else {
+    } else if (res_on) {                                   // rare: both side tensors — sign row read in place
       const __nv_bfloat16* ap = p.aux + pix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncols) {
-          Vec<__nv_bfloat16> r;
-          r.load(ap + i);
+      for (int i = 0; i < CW; i += 8) {
+        Vec<__nv_bfloat16> r;
+        r.load(ap + i);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
-        }
+        for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CW; i += 8) {
+        float r[8];
+        unpack16<__nv_bfloat16>(sd[i / 8], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i + j] = (r[j] > 0.0f) ? v[i + j] : 0.0f;
       }
     }
   }
-  if (flags & MCGM_EPI_TANH) {
+  if constexpr (sizeof(OutT) == 4) {                       // tanh: fp32 outputs only (checked on the host)
+    if (flags & MCGM_EPI_TANH) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+      for (int i = 0; i < CW; ++i) v[i] = tanhf(v[i]);
+    }
   }
   OutT* op = reinterpret_cast<OutT*>(p.out) + pix * p.Cout + col0;
-  if ((p.Cout & 7) == 0) {
+  if constexpr (!GENERIC_STORE) {                          // Cout is a multiple of 32
     constexpr int V = Vec<OutT>::N;
 #pragma unroll
-    for (int i = 0; i < 32; i += V) {
-      if (i < ncols) {
-        Vec<OutT> o;
+    for (int i = 0; i < CW; i += V) {
+      Vec<OutT> o;
 #pragma unroll
-        for (int j = 0; j < V; ++j) o.v[j] = v[i + j];
-        o.store(op + i);
-      }
+      for (int j = 0; j < V; ++j) o.v[j] = v[i + j];
+      o.store(op + i);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < ncols && col0 + i < p.Cout) {
+    for (int i = 0; i < CW; ++i) {
+      if (col0 + i < p.Cout) {
         if constexpr (sizeof(OutT) == 4) op[i] = v[i];
         else op[i] = __float2bfloat16(v[i]);
       }
     }
+  }
+}
+
+// bf16 side row (residual / ReLU-sign source) of one chunk: CW/8 independent 16-byte loads
+template <int CW>
+__device__ __forceinline__ void side_load(const __nv_bfloat16* base, long pix, int Cout, int col0, bool on,
+                                          uint4 (&r)[4]) {
+  if (on) {
+    const uint4* q = reinterpret_cast<const uint4*>(base + pix * Cout + col0);
+#pragma unroll
+    for (int i = 0; i < (CW >= 8 ? CW / 8 : 0); ++i) r[i] = __ldg(q + i);
   }
 }
 
@@ -305,8 +317,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 const ConvFwdParams p) {
   using Cfg = FwdCfg<BN, MT>;
   constexpr int kElems = TF32 ? 32 : 64;                 // operand elements per 128-byte k-block row
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();                       // 128B-swizzled TMA tiles need a 1024-byte aligned base
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr (4 B)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -314,6 +327,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  // bias of all n_tiles * BN (zero-padded) output channels, after the 256 B barrier block
+  float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256);
+  for (int i = threadIdx.x; i < p.n_tiles * BN; i += kConvThreads)
+    sbias[i] = ((p.flags & MCGM_EPI_BIAS) && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -394,48 +411,94 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else {
     // ===== epilogue: 8 warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); the two warps of a
-    // quadrant split the accumulator columns.  The epilogue used to be latency-bound (one warp per SM
-    // sub-partition, TMEM load -> wait -> math -> store serialised): two warps per sub-partition plus
-    // a software pipeline (the TMEM load of chunk c+1 is in flight while chunk c is processed) keep it
-    // shorter than the main loop even for K = 4..18 k-blocks (1x1, phase and 128-wide convs).
+    // quadrant split the accumulator columns.  The epilogue is latency-, not issue-bound (ncu: one or two
+    // warps per scheduler, every global load exposed), so nothing it needs is fetched after the
+    // accumulator is ready: the bias sits in shared memory (staged once per CTA), the labels of the
+    // tile's samples plus the first codebook word and residual / ReLU-sign row are requested BEFORE the
+    // wait on the MMA, and inside the tile the TMEM load, codebook word and side row of chunk q+1 are in
+    // flight while chunk q is processed.  Two chunk bodies (even / odd buffers) in a rolled loop keep the
+    // code inside the instruction cache.
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
     constexpr int CW = BN < 32 ? BN : 32;                    // columns per TMEM load
     constexpr int HALF = (BN / 2 >= CW) ? BN / 2 : BN;       // columns per warp (narrow tiles: warp half 0 only)
     constexpr int NCH = HALF / CW;
+    constexpr int Q = MT * NCH;                              // chunks per CTA tile and warp: 1, 2 or 4
+    static_assert(Q == 1 || Q % 2 == 0, "chunk pipeline handles one chunk or pairs");
     const bool works = half * HALF < BN;
+    const int flags = p.flags;
+    const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
+    const __nv_bfloat16* side = TF32 ? nullptr : (res_on ? p.res : ((flags & MCGM_EPI_POSMASK) ? p.aux : nullptr));
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
       const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
       const int mt0 = ms * MT;
-      const int cout0 = nt * BN + half * HALF;
+      const int cl0 = nt * BN + half * HALF;                 // first output channel of this warp
+      long pix[MT], rpix[MT];
+      bool valid[MT];
+      int lab[MT];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int mt = mt0 + j;
+        const int wg = (mt % p.tiles_w) * p.TW + tw;
+        const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+        const int n = (mt / tiles_per_img_block) * p.TN + tn;
+        valid[j] = works && (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
+        const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
+        pix[j] = ((long)n * p.Ho + h) * p.Wo + w;
+        rpix[j] = (flags & MCGM_EPI_RES_UP2) ? ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1) : pix[j];
+        lab[j] = ((flags & MCGM_EPI_MASK) && valid[j]) ? __ldg(p.labels + n) : 0;
+      }
+      // everything chunk q needs besides the accumulator
+      auto fetch_side = [&](int q, uint4 (&sd)[4], uint32_t& mwd) {
+        const int j = q / NCH, col = cl0 + (q % NCH) * CW;
+        const bool ok = ((MT == 2 && j) ? valid[MT - 1] : valid[0]) && col < p.Cout;
+        if (side != nullptr)
+          side_load<CW>(side, res_on ? ((MT == 2 && j) ? rpix[MT - 1] : rpix[0]) : ((MT == 2 && j) ? pix[MT - 1] : pix[0]),
+                        p.Cout, col, ok, sd);
+        mwd = 0u;
+        if ((flags & MCGM_EPI_MASK) && ok)                   // MASK implies Cout % 32 == 0 (CW == 32)
+          mwd = __ldg(p.bits + (size_t)((MT == 2 && j) ? lab[MT - 1] : lab[0]) * p.words + (col >> 5));
+      };
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + half * HALF;
+      auto fetch_acc = [&](int q, uint32_t (&a)[32]) {
+        const uint32_t ta = t_row + (q / NCH) * BN + (q % NCH) * CW;
+        if constexpr (CW == 32) tmem_ld32(ta, a);
+        else tmem_ld16(ta, a);
+      };
+      auto run = [&](int q, uint32_t (&a)[32], const uint4 (&sd)[4], uint32_t mwd) {
+        const int j = q / NCH, col = cl0 + (q % NCH) * CW;
+        epilogue_chunk<CW, BN == 16, OutT, TF32>(p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0],
+                                                 (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
+                                                 ((MT == 2 && j) ? valid[MT - 1] : valid[0]) && col < p.Cout,
+                                                 sbias + col, mwd, sd);
+      };
+      uint32_t acc[2][32];
+      uint4 sd[2][4];
+      uint32_t mwd[2];
+      fetch_side(0, sd[0], mwd[0]);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (works) {
+        fetch_acc(0, acc[0]);
+        if constexpr (Q == 1) {
+          tmem_ld_wait();
+          run(0, acc[0], sd[0], mwd[0]);
+        } else {
 #pragma unroll 1
-        for (int j = 0; j < MT; ++j) {
-          const int mt = mt0 + j;
-          const int wg = (mt % p.tiles_w) * p.TW + tw;
-          const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
-          const int n = (mt / tiles_per_img_block) * p.TN + tn;
-          const bool valid = (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
-          const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
-          const long pix = ((long)n * p.Ho + h) * p.Wo + w;
-          const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + j * BN + half * HALF;
-          uint32_t acc[2][32];
-          if constexpr (CW == 32) tmem_ld32(t_row, acc[0]);
-          else tmem_ld16(t_row, acc[0]);
-#pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
+          for (int q = 0; q < Q; q += 2) {
             tmem_ld_wait();
-            if (ci + 1 < NCH) {
-              if constexpr (CW == 32) tmem_ld32(t_row + (ci + 1) * CW, acc[(ci + 1) & 1]);
-              else tmem_ld16(t_row + (ci + 1) * CW, acc[(ci + 1) & 1]);
+            fetch_acc(q + 1, acc[1]);
+            fetch_side(q + 1, sd[1], mwd[1]);
+            run(q, acc[0], sd[0], mwd[0]);
+            tmem_ld_wait();
+            if (q + 2 < Q) {
+              fetch_acc(q + 2, acc[0]);
+              fetch_side(q + 2, sd[0], mwd[0]);
             }
-            epilogue_store_chunk<BN, OutT, TF32>(p, acc[ci & 1], CW, pix, n, h, w, cout0 + ci * CW,
-                                                 valid && (cout0 + ci * CW < p.Cout));
+            run(q + 1, acc[1], sd[1], mwd[1]);
           }
         }
       }
@@ -866,6 +929,7 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   if (tf32) MCGM_CHECK_ARG(out_dtype == MCGM_F32, "conv_fwd: fp32 operands need an fp32 output");
   if (Cin % kblk) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cin=%d must be a multiple of %d (use the thin kernels)", Cin, kblk);
   if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "conv_fwd: BIAS flag without bias");
+  if (flags & MCGM_EPI_TANH) MCGM_CHECK_ARG(out_dtype == MCGM_F32, "conv_fwd: TANH needs an fp32 output");
   if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) MCGM_CHECK_ARG(res && (Cout % 8 == 0), "conv_fwd: RES flag needs res and Cout %% 8 == 0");
   if (flags & MCGM_EPI_MASK) MCGM_CHECK_ARG(labels && bits && M > 0 && Cout % 32 == 0, "conv_fwd: MASK needs labels, bits and Cout %% 32 == 0");
   if (flags & MCGM_EPI_POSMASK) MCGM_CHECK_ARG(aux && (Cout % 8 == 0), "conv_fwd: POSMASK needs aux and Cout %% 8 == 0");
@@ -911,6 +975,7 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   // never stored (the epilogue stops at Cout).
   if (p.PH > 1 && Cout % BN && Cout > 16) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: phase conv needs Cout %% %d == 0", BN);
   p.n_tiles = (Cout + BN - 1) / BN;
+  if (p.n_tiles * BN * 4 > kMaxBiasBytes) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: Cout=%d exceeds the %d-channel bias staging buffer", Cout, kMaxBiasBytes / 4);
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_nb;
   p.kpt = Cin / kblk;
   p.num_kb = p.T * p.kpt;

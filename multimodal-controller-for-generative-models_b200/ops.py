@@ -54,12 +54,12 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(ev, tag, work):
+def _prof_end(ev, tag, work, desc=""):
     if ev is None:
         return
     end = torch.cuda.Event(enable_timing=True)
     end.record()
-    PROFILE.setdefault(tag, []).append((ev, end, work))
+    PROFILE.setdefault(tag, []).append((ev, end, work, desc))
 
 
 _workspaces = {}
@@ -132,7 +132,7 @@ def bn_stats(x, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
     _lib.call("mcgm_bn_stats", x.data_ptr(), _dtype_code(x), P, C, mean.data_ptr(), rstd.data_ptr(),
               _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), ws.data_ptr(), _stream())
     _lib.launch_count += 1                       # partial + finalize kernels
-    _prof_end(ev, "gate", x.numel() * x.element_size())
+    _prof_end(ev, "gate", x.numel() * x.element_size(), f"bn_stats P{P} C{C}")
     return mean, rstd
 
 
@@ -146,7 +146,8 @@ def gate_fwd(x, flags, labels=None, packed=None, mean=None, rstd=None, gamma=Non
     _lib.call("mcgm_gate_fwd", x.data_ptr(), y.data_ptr(), _ptr(y_raw), _dtype_code(x), N, H, W, C,
               _ptr(labels), _ptr(packed.bits if packed else None), packed.M if packed else 0,
               _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), flags, _stream())
-    _prof_end(ev, "gate", (x.numel() + y.numel() + (x.numel() if want_raw else 0)) * x.element_size())
+    _prof_end(ev, "gate", (x.numel() + y.numel() + (x.numel() if want_raw else 0)) * x.element_size(),
+              f"gate_fwd {N}x{H}x{W}x{C} f{flags:#x} raw{int(want_raw)}")
     return y, y_raw
 
 
@@ -170,7 +171,7 @@ def gate_bwd(dy, d_raw, x, flags, labels=None, packed=None, mean=None, rstd=None
     passes = 2 if flags & GATE_BN else 1          # BN: reduce pass + apply pass both read dy and x
     nbytes = passes * ((dy.numel() if dy is not None else 0) + x.numel()) + x.numel()
     nbytes += d_raw.numel() if d_raw is not None else 0
-    _prof_end(ev, "gate", nbytes * x.element_size())
+    _prof_end(ev, "gate", nbytes * x.element_size(), f"gate_bwd {N}x{H}x{W}x{C} f{flags:#x} raw{int(d_raw is not None)}")
     return dx, dgamma, dbeta
 
 
@@ -287,7 +288,8 @@ def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None,
               F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, R, S,
               _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
               packed.M if packed else 0, flags, _stream())
-    _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * R * S)
+    _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * R * S,
+              f"conv {N}x{H}x{W} {Cin}->{Cout} k{R} f{flags:#x} {'f32' if out_dtype == torch.float32 else 'bf16'}")
     return out
 
 
@@ -320,7 +322,8 @@ def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=N
               packed.M if packed else 0, flags, _stream())
     # algorithmic flops of the REFERENCE op (3x3 on the upsampled tensor / 4x4 strided), not the executed MACs
     ref_taps = 9 if kind == CONV_PHASE2 else 16
-    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ref_taps)
+    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ref_taps,
+              f"conv_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}")
     return out
 
 
@@ -409,7 +412,8 @@ def conv_wgrad_ex(kind, x, dy, want_bias=True):
     _lib.launch_count += 1
     ref_taps = 9 if kind == CONV_PHASE2 else 16
     _prof_end(ev, "wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * ref_taps
-              if kind == CONV_PHASE2 else 2.0 * N * (H // 2) * (W // 2) * Cout * Cin * 16)
+              if kind == CONV_PHASE2 else 2.0 * N * (H // 2) * (W // 2) * Cout * Cin * 16,
+              f"wgrad_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout}")
     return dw, db
 
 
@@ -428,7 +432,7 @@ def conv_wgrad(x, dy, R, S, want_bias=True):
     _lib.call("mcgm_conv_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, R, S,
               ws.data_ptr(), _stream())
     _lib.launch_count += 1                       # wgrad + split-K / bias reduce
-    _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S)
+    _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S, f"wgrad {N}x{H}x{W} {Cin}->{Cout} k{R}")
     return dw, db
 
 

@@ -46,6 +46,24 @@ if "conv" in which:
         t = timeit(lambda: ops.conv_fwd(x, w, torch.bfloat16 if Cout != 32 else torch.float32))
         fl = 2.0 * N * H * H * Cin * Cout * R * R
         print(f"conv_fwd N{N} {H}x{H} {Cin}->{Cout} k{R}: {t * 1e6:8.1f} us  {fl / t / 1e12:7.1f} TFLOP/s", flush=True)
+if "epi" in which:
+    from mcgm_b200._lib import EPI_BIAS, EPI_MASK, EPI_POSMASK, EPI_RELU, EPI_RES, EPI_RES_UP2
+    M = 10
+    labels = torch.randint(0, M, (N,), device=dev).to(torch.int32)
+    for (H, Cin, Cout, R, fl) in [(32, 128, 128, 3, 0x3), (32, 128, 128, 3, 0x40), (32, 64, 128, 1, 0x19), (32, 64, 128, 1, 0x1),
+                                  (16, 128, 128, 3, 0x3), (16, 128, 128, 3, 0x19), (8, 128, 128, 3, 0x3), (32, 256, 256, 3, 0x5),
+                                  (16, 128, 128, 1, 0x1), (16, 256, 256, 1, 0x1)]:
+        x = torch.randn(N, H, H, Cin, device=dev).to(torch.bfloat16)
+        w = torch.randn(Cout, R, R, Cin, device=dev).to(torch.bfloat16)
+        bias = torch.randn(Cout, device=dev) if fl & EPI_BIAS else None
+        res = torch.randn(N, H // 2 if fl & EPI_RES_UP2 else H, H // 2 if fl & EPI_RES_UP2 else H, Cout, device=dev).to(torch.bfloat16) \
+            if fl & (EPI_RES | EPI_RES_UP2) else None
+        aux = torch.randn(N, H, H, Cout, device=dev).to(torch.bfloat16) if fl & EPI_POSMASK else None
+        packed = ops.PackedCodebook((torch.rand(M, Cout) > 0.5).float().to(dev)) if fl & EPI_MASK else None
+        t = timeit(lambda: ops.conv_fwd(x, w, torch.bfloat16, bias, res, aux, labels if packed else None, packed, fl))
+        fl_ = 2.0 * N * H * H * Cin * Cout * R * R
+        by = (x.numel() + N * H * H * Cout + (res.numel() if res is not None else 0) + (aux.numel() if aux is not None else 0)) * 2
+        print(f"conv_epi N{N} {H}x{H} {Cin}->{Cout} k{R} f{fl:#x}: {t * 1e6:8.1f} us  {fl_ / t / 1e12:7.1f} TFLOP/s  {by / t / 1e9:7.0f} GB/s", flush=True)
 if "wgrad" in which:
     for (H, Cin, Cout, R) in [(32, 256, 256, 3), (16, 256, 256, 3), (8, 256, 256, 3), (32, 128, 128, 3), (16, 128, 128, 3),
                               (8, 128, 128, 3), (16, 256, 256, 1), (32, 64, 128, 1), (32, 256, 64, 1)]:
