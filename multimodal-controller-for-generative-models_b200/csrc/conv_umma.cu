@@ -20,6 +20,7 @@
 // over tiles, smem ring of kStages, double-buffered TMEM accumulator so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -172,6 +173,7 @@ struct ConvFwdParams {
   const uint32_t* bits;
   int words;
   int flags;
+  int quad;                                  // 4 consecutive tile pixels never straddle a tile row (TW % 4 == 0)
   void* out;
 };
 
@@ -193,18 +195,47 @@ struct FwdCfg {
   static_assert(kSmemBytes + 1024 <= 200704, "forward conv must fit the 196 KB carve-out");
 };
 
-// One chunk (CW <= 32 consecutive output channels of one pixel) of the fused epilogue.
+// 4x4 transpose of 16-byte units across the 4 lanes of a quad.  Before: lane l holds units 0..3 (64
+// contiguous bytes) of ITS row.  After: lane l holds unit (l & 3) of the rows of lanes (l & ~3) + 0..3, so
+// one 16-byte access per lane moves 64 contiguous bytes per row and a warp instruction touches 8 rows
+// instead of 32.  The thread-per-row layout TMEM hands out would otherwise make every STG / LDG a 32-line
+// scatter of half sectors, which is what bounded the epilogue (removing the stores alone sped the 256-wide
+// 3x3 conv up 14 % and the 1x1 / thin convs 1.5-1.9x).  The transpose is its own inverse.
+__device__ __forceinline__ void quad_transpose(uint4 (&u)[4], const int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+  for (int s = 0; s < 4; s += 2) {                         // unit pairs (0,1), (2,3) with lane ^ 1
+    const uint4 send = b0 ? u[s] : u[s + 1];
+    uint4 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+    if (b0) u[s] = recv; else u[s + 1] = recv;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {                            // unit pairs (0,2), (1,3) with lane ^ 2
+    const uint4 send = b1 ? u[s] : u[s + 2];
+    uint4 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 2); recv.y = __shfl_xor_sync(0xffffffffu, send.y, 2);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 2); recv.w = __shfl_xor_sync(0xffffffffu, send.w, 2);
+    if (b1) u[s] = recv; else u[s + 2] = recv;
+  }
+}
+
+// One chunk (CW <= 32 consecutive output channels of one pixel) of the fused epilogue.  Executed by ALL
+// lanes of the warp (quad shuffles inside); `row_ok` only predicates the global accesses of this row.
 //   acc    fp32 bit patterns from TMEM
 //   sbias  shared-memory bias of these columns (zero-padded; staged once per CTA)
 //   mbits  codebook bits of these columns for the sample of this pixel, fetched one chunk ahead
 //   sd     bf16 pipeline: the residual row of these columns (RES / RES_UP2), else the ReLU-sign row
-//          (POSMASK), fetched one chunk ahead.  With both flags the sign row is read in place; the fp32
-//          parity pipeline (TF32) reads everything in place.
-template <int CW, bool GENERIC_STORE, typename OutT, bool TF32>
+//          (POSMASK), fetched one chunk ahead — quad-transposed when QUAD.  With both flags the sign row is
+//          read in place; the fp32 parity pipeline (TF32) reads everything in place.
+//   QUAD   bf16 rows move as quad-transposed 64-byte runs (needs CW == 32 and quads that do not straddle a
+//          tile row: p.quad)
+template <int CW, bool GENERIC_STORE, bool QUAD, typename OutT, bool TF32>
 __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int flags, uint32_t (&acc)[32],
-                                               const long pix, const long rpix, const int col0, const bool valid,
-                                               const float* sbias, const uint32_t mbits, const uint4 (&sd)[4]) {
-  if (!valid) return;
+                                               const int pix, const int rpix, const int col0, const bool row_ok,
+                                               const float* sbias, const uint32_t mbits, uint4 (&sd)[4],
+                                               const int lane) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(acc[i]);
@@ -216,15 +247,20 @@ __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int
     }
   }
   const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
+  if constexpr (QUAD) {
+    if (res_on || (flags & MCGM_EPI_POSMASK)) quad_transpose(sd, lane);   // back to one row per lane
+  }
   if (res_on) {
     if constexpr (TF32) {                                  // fp32 pipeline: residual is fp32
-      const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.Cout + col0;
+      if (row_ok) {
+        const float* rp = reinterpret_cast<const float*>(p.res) + (long)rpix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < CW; i += 4) {
-        Vec<float> r;
-        r.load(rp + i);
+        for (int i = 0; i < CW; i += 4) {
+          Vec<float> r;
+          r.load(rp + i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[i + j] += r.v[j];
+          for (int j = 0; j < 4; ++j) v[i + j] += r.v[j];
+        }
       }
     } else {
 #pragma unroll
@@ -246,22 +282,26 @@ __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int
   }
   if (flags & MCGM_EPI_POSMASK) {
     if constexpr (TF32) {
-      const float* ap = reinterpret_cast<const float*>(p.aux) + pix * p.Cout + col0;
+      if (row_ok) {
+        const float* ap = reinterpret_cast<const float*>(p.aux) + (long)pix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < CW; i += 4) {
-        Vec<float> r;
-        r.load(ap + i);
+        for (int i = 0; i < CW; i += 4) {
+          Vec<float> r;
+          r.load(ap + i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+          for (int j = 0; j < 4; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+        }
       }
     } else if (res_on) {                                   // rare: both side tensors — sign row read in place
-      const __nv_bfloat16* ap = p.aux + pix * p.Cout + col0;
+      if (row_ok) {
+        const __nv_bfloat16* ap = p.aux + (long)pix * p.Cout + col0;
 #pragma unroll
-      for (int i = 0; i < CW; i += 8) {
-        Vec<__nv_bfloat16> r;
-        r.load(ap + i);
+        for (int i = 0; i < CW; i += 8) {
+          Vec<__nv_bfloat16> r;
+          r.load(ap + i);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+          for (int j = 0; j < 8; ++j) v[i + j] = (r.v[j] > 0.0f) ? v[i + j] : 0.0f;
+        }
       }
     } else {
 #pragma unroll
@@ -279,35 +319,74 @@ __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int
       for (int i = 0; i < CW; ++i) v[i] = tanhf(v[i]);
     }
   }
-  OutT* op = reinterpret_cast<OutT*>(p.out) + pix * p.Cout + col0;
-  if constexpr (!GENERIC_STORE) {                          // Cout is a multiple of 32
-    constexpr int V = Vec<OutT>::N;
+  if constexpr (QUAD && sizeof(OutT) == 2) {               // bf16 rows as quad-transposed 64-byte runs
+    uint4 o[4];
 #pragma unroll
-    for (int i = 0; i < CW; i += V) {
-      Vec<OutT> o;
+    for (int i = 0; i < 4; ++i) {
+      uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < V; ++j) o.v[j] = v[i + j];
-      o.store(op + i);
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      o[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    quad_transpose(o, lane);
+    const uint32_t okb = __ballot_sync(0xffffffffu, row_ok);
+    const int base = lane & ~3;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + col0 + (lane & 3) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pk = __shfl_sync(0xffffffffu, pix, base + k);
+      if ((okb >> (base + k)) & 1u) *reinterpret_cast<uint4*>(op + (long)pk * p.Cout) = o[k];
+    }
+  } else if constexpr (!GENERIC_STORE) {                   // Cout is a multiple of 32
+    if (row_ok) {
+      OutT* op = reinterpret_cast<OutT*>(p.out) + (long)pix * p.Cout + col0;
+      constexpr int V = Vec<OutT>::N;
+#pragma unroll
+      for (int i = 0; i < CW; i += V) {
+        Vec<OutT> o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = v[i + j];
+        o.store(op + i);
+      }
     }
   } else {
+    if (row_ok) {
+      OutT* op = reinterpret_cast<OutT*>(p.out) + (long)pix * p.Cout + col0;
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      if (col0 + i < p.Cout) {
-        if constexpr (sizeof(OutT) == 4) op[i] = v[i];
-        else op[i] = __float2bfloat16(v[i]);
+      for (int i = 0; i < CW; ++i) {
+        if (col0 + i < p.Cout) {
+          if constexpr (sizeof(OutT) == 4) op[i] = v[i];
+          else op[i] = __float2bfloat16(v[i]);
+        }
       }
     }
   }
 }
 
-// bf16 side row (residual / ReLU-sign source) of one chunk: CW/8 independent 16-byte loads
-template <int CW>
-__device__ __forceinline__ void side_load(const __nv_bfloat16* base, long pix, int Cout, int col0, bool on,
-                                          uint4 (&r)[4]) {
-  if (on) {
-    const uint4* q = reinterpret_cast<const uint4*>(base + pix * Cout + col0);
+// bf16 side row (residual / ReLU-sign source) of one chunk: CW/8 independent 16-byte loads.  QUAD: lane l
+// reads unit (l & 3) of the rows of its quad (64 contiguous bytes per row and instruction); the consumer
+// transposes back.  All lanes of the warp take part.
+template <int CW, bool QUAD>
+__device__ __forceinline__ void side_load(const __nv_bfloat16* base, const int pix, const int Cout, const int col0,
+                                          const bool on, uint4 (&r)[4], const int lane) {
+  if constexpr (QUAD) {
+    const uint32_t okb = __ballot_sync(0xffffffffu, on);
+    const int b = lane & ~3;
+    const __nv_bfloat16* q = base + col0 + (lane & 3) * 8;
 #pragma unroll
-    for (int i = 0; i < (CW >= 8 ? CW / 8 : 0); ++i) r[i] = __ldg(q + i);
+    for (int k = 0; k < 4; ++k) {
+      const int pk = __shfl_sync(0xffffffffu, pix, b + k);
+      if ((okb >> (b + k)) & 1u) r[k] = __ldg(reinterpret_cast<const uint4*>(q + (long)pk * Cout));
+    }
+  } else {
+    if (on) {
+      const uint4* q = reinterpret_cast<const uint4*>(base + (long)pix * Cout + col0);
+#pragma unroll
+      for (int i = 0; i < (CW >= 8 ? CW / 8 : 0); ++i) r[i] = __ldg(q + i);
+    }
   }
 }
 
@@ -417,7 +496,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // tile's samples plus the first codebook word and residual / ReLU-sign row are requested BEFORE the
     // wait on the MMA, and inside the tile the TMEM load, codebook word and side row of chunk q+1 are in
     // flight while chunk q is processed.  Two chunk bodies (even / odd buffers) in a rolled loop keep the
-    // code inside the instruction cache.
+    // code inside the instruction cache.  bf16 rows travel quad-transposed (see quad_transpose).
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
@@ -426,84 +505,94 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     constexpr int NCH = HALF / CW;
     constexpr int Q = MT * NCH;                              // chunks per CTA tile and warp: 1, 2 or 4
     static_assert(Q == 1 || Q % 2 == 0, "chunk pipeline handles one chunk or pairs");
+    constexpr bool kQuadOk = CW == 32 && !TF32;
     const bool works = half * HALF < BN;
     const int flags = p.flags;
     const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
     const __nv_bfloat16* side = TF32 ? nullptr : (res_on ? p.res : ((flags & MCGM_EPI_POSMASK) ? p.aux : nullptr));
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
-      const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
-      const int mt0 = ms * MT;
-      const int cl0 = nt * BN + half * HALF;                 // first output channel of this warp
-      long pix[MT], rpix[MT];
-      bool valid[MT];
-      int lab[MT];
+    auto tile_loop = [&](auto quad_tag) {
+      constexpr bool QUAD = decltype(quad_tag)::value;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
+        const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
+        const int mt0 = ms * MT;
+        const int cl0 = nt * BN + half * HALF;                 // first output channel of this warp
+        int pix[MT], rpix[MT], lab[MT];                        // pixel indices fit 31 bits (checked on the host)
+        bool valid[MT];
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const int mt = mt0 + j;
-        const int wg = (mt % p.tiles_w) * p.TW + tw;
-        const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
-        const int n = (mt / tiles_per_img_block) * p.TN + tn;
-        valid[j] = works && (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
-        const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
-        pix[j] = ((long)n * p.Ho + h) * p.Wo + w;
-        rpix[j] = (flags & MCGM_EPI_RES_UP2) ? ((long)n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1) : pix[j];
-        lab[j] = ((flags & MCGM_EPI_MASK) && valid[j]) ? __ldg(p.labels + n) : 0;
-      }
-      // everything chunk q needs besides the accumulator
-      auto fetch_side = [&](int q, uint4 (&sd)[4], uint32_t& mwd) {
-        const int j = q / NCH, col = cl0 + (q % NCH) * CW;
-        const bool ok = ((MT == 2 && j) ? valid[MT - 1] : valid[0]) && col < p.Cout;
-        if (side != nullptr)
-          side_load<CW>(side, res_on ? ((MT == 2 && j) ? rpix[MT - 1] : rpix[0]) : ((MT == 2 && j) ? pix[MT - 1] : pix[0]),
-                        p.Cout, col, ok, sd);
-        mwd = 0u;
-        if ((flags & MCGM_EPI_MASK) && ok)                   // MASK implies Cout % 32 == 0 (CW == 32)
-          mwd = __ldg(p.bits + (size_t)((MT == 2 && j) ? lab[MT - 1] : lab[0]) * p.words + (col >> 5));
-      };
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + half * HALF;
-      auto fetch_acc = [&](int q, uint32_t (&a)[32]) {
-        const uint32_t ta = t_row + (q / NCH) * BN + (q % NCH) * CW;
-        if constexpr (CW == 32) tmem_ld32(ta, a);
-        else tmem_ld16(ta, a);
-      };
-      auto run = [&](int q, uint32_t (&a)[32], const uint4 (&sd)[4], uint32_t mwd) {
-        const int j = q / NCH, col = cl0 + (q % NCH) * CW;
-        epilogue_chunk<CW, BN == 16, OutT, TF32>(p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0],
-                                                 (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
-                                                 ((MT == 2 && j) ? valid[MT - 1] : valid[0]) && col < p.Cout,
-                                                 sbias + col, mwd, sd);
-      };
-      uint32_t acc[2][32];
-      uint4 sd[2][4];
-      uint32_t mwd[2];
-      fetch_side(0, sd[0], mwd[0]);
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      if (works) {
-        fetch_acc(0, acc[0]);
-        if constexpr (Q == 1) {
-          tmem_ld_wait();
-          run(0, acc[0], sd[0], mwd[0]);
-        } else {
+        for (int j = 0; j < MT; ++j) {
+          const int mt = mt0 + j;
+          const int wg = (mt % p.tiles_w) * p.TW + tw;
+          const int hg = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+          const int n = (mt / tiles_per_img_block) * p.TN + tn;
+          valid[j] = works && (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
+          const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);     // output pixel (phase = (ph_h, ph_w))
+          pix[j] = (n * p.Ho + h) * p.Wo + w;
+          rpix[j] = (flags & MCGM_EPI_RES_UP2) ? (n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1) : pix[j];
+          lab[j] = ((flags & MCGM_EPI_MASK) && valid[j]) ? __ldg(p.labels + n) : 0;
+        }
+        // everything chunk q needs besides the accumulator
+        auto fetch_side = [&](int q, uint4 (&sd)[4], uint32_t& mwd) {
+          const int j = q / NCH, col = cl0 + (q % NCH) * CW;
+          const bool ok = ((MT == 2 && j) ? valid[MT - 1] : valid[0]) && col < p.Cout;
+          if (side != nullptr)
+            side_load<CW, QUAD>(side, res_on ? ((MT == 2 && j) ? rpix[MT - 1] : rpix[0]) : ((MT == 2 && j) ? pix[MT - 1] : pix[0]),
+                                p.Cout, col, ok, sd, lane);
+          mwd = 0u;
+          if ((flags & MCGM_EPI_MASK) && ok)                   // MASK implies Cout % 32 == 0 (CW == 32)
+            mwd = __ldg(p.bits + (size_t)((MT == 2 && j) ? lab[MT - 1] : lab[0]) * p.words + (col >> 5));
+        };
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN) + half * HALF;
+        auto fetch_acc = [&](int q, uint32_t (&a)[32]) {
+          const uint32_t ta = t_row + (q / NCH) * BN + (q % NCH) * CW;
+          if constexpr (CW == 32) tmem_ld32(ta, a);
+          else tmem_ld16(ta, a);
+        };
+        auto run = [&](int q, uint32_t (&a)[32], uint4 (&sd)[4], uint32_t mwd) {
+          const int j = q / NCH, col = cl0 + (q % NCH) * CW;
+          if (col < p.Cout)                                    // warp-uniform
+            epilogue_chunk<CW, BN == 16, QUAD, OutT, TF32>(p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0],
+                                                           (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
+                                                           (MT == 2 && j) ? valid[MT - 1] : valid[0],
+                                                           sbias + col, mwd, sd, lane);
+        };
+        uint32_t acc[2][32];
+        uint4 sd[2][4];
+        uint32_t mwd[2];
+        if (works) fetch_side(0, sd[0], mwd[0]);
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        if (works) {
+          fetch_acc(0, acc[0]);
+          if constexpr (Q == 1) {
+            tmem_ld_wait();
+            run(0, acc[0], sd[0], mwd[0]);
+          } else {
 #pragma unroll 1
-          for (int q = 0; q < Q; q += 2) {
-            tmem_ld_wait();
-            fetch_acc(q + 1, acc[1]);
-            fetch_side(q + 1, sd[1], mwd[1]);
-            run(q, acc[0], sd[0], mwd[0]);
-            tmem_ld_wait();
-            if (q + 2 < Q) {
-              fetch_acc(q + 2, acc[0]);
-              fetch_side(q + 2, sd[0], mwd[0]);
+            for (int q = 0; q < Q; q += 2) {
+              tmem_ld_wait();
+              fetch_acc(q + 1, acc[1]);
+              fetch_side(q + 1, sd[1], mwd[1]);
+              run(q, acc[0], sd[0], mwd[0]);
+              tmem_ld_wait();
+              if (q + 2 < Q) {
+                fetch_acc(q + 2, acc[0]);
+                fetch_side(q + 2, sd[0], mwd[0]);
+              }
+              run(q + 1, acc[1], sd[1], mwd[1]);
             }
-            run(q + 1, acc[1], sd[1], mwd[1]);
           }
         }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+    };
+    if constexpr (kQuadOk) {
+      if (p.quad) tile_loop(std::true_type{});
+      else tile_loop(std::false_type{});
+    } else {
+      tile_loop(std::false_type{});
     }
   }
 
@@ -962,6 +1051,8 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   if (p.TW * p.IS > 256 || p.TH * p.IS > 256) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: TMA box too large for stride %d", p.IS);
   p.tiles_w = p.Wg / p.TW;
   p.tiles_h = p.Hg / p.TH;
+  p.quad = (p.TW % 4 == 0);
+  if ((long)N * p.Ho * p.Wo >= (1l << 31)) return fail(MCGM_E_UNSUPPORTED, "conv_fwd: more than 2^31 output pixels");
   const int tiles_nb = (N + p.TN - 1) / p.TN;
   int BN;
   if (Cout % 256 == 0) BN = 256;
