@@ -218,6 +218,20 @@ int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, i
 int mcgm_split_tf32(const float* x, float* big, float* small, long n, void* stream);
 int mcgm_split_bf16x3(const float* x, void* p1, void* p2, void* p3, long n, void* stream);
 
+/* ---- optimiser step on flat fp32 buffers (optim.Adam src/train_gan.py:223-236, eps 1e-8, no amsgrad;
+ * clip_grad_norm_ + Adam src/train_vae.py:110-111, src/train_glow.py:120-121).  n must be a multiple of 4,
+ * buffers 16-byte aligned.  `step` is a DEVICE int32 (number of updates applied so far; advanced by the
+ * call), so the update is CUDA-graph capturable.  The gradient is read as
+ * grad_scale * (grad_scale_dev ? grad_scale_dev[0] : 1) * grad — the data-parallel 1/world factor and the
+ * clip coefficient cost no pass of their own.
+ * mcgm_grad_clip_coef: coef_out[0] = min(1, max_norm / (||grad||_2 + 1e-6)), coef_out[1] = ||grad||_2
+ * (deterministic two-level reduction; no host synchronisation). */
+size_t mcgm_grad_clip_workspace_bytes(void);
+int mcgm_grad_clip_coef(const float* grad, long n, float max_norm, float* coef_out, void* workspace, void* stream);
+int mcgm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   const float* grad_scale_dev, void* stream);
+
 /* ---- pooling / resampling helpers on bf16 NHWC (AvgPool2d(2) mcgan.py:81,88;
  * Upsample backward = 2x2 sum).  avgpool2: y[n,h,w,c] = scale * sum_{2x2} x;
  * upsample2_add: y[n,h,w,c] = a[n,h,w,c] + b[n,h/2,w/2,c] (b may be NULL → copy-upsample of a at half res is not needed). */

@@ -60,6 +60,10 @@ SIGNATURES = {
                                  c_void_p]),
     "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mcgm_unpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mcgm_grad_clip_workspace_bytes": (c_size_t, []),
+    "mcgm_grad_clip_coef": (c_int, [c_void_p, c_long, c_float, c_void_p, c_void_p, c_void_p]),
+    "mcgm_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,
+                               c_float, c_float, c_float, c_void_p, c_void_p]),
     "mcgm_debug_set": (c_int, [c_int, c_uint64]),
 }
 

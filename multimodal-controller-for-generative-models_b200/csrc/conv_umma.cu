@@ -805,14 +805,33 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   if (dbias && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
       float a = 0.0f;
-      for (int s = 0; s < bias_rows; ++s) a += bias_partial[(size_t)s * Cout + c];
+      int s = 0;
+      for (; s + 8 <= bias_rows; s += 8) {
+        float b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b[u] = bias_partial[(size_t)(s + u) * Cout + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += b[u];
+      }
+      for (; s < bias_rows; ++s) a += bias_partial[(size_t)s * Cout + c];
       dbias[c] = a;
     }
   }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 a = reinterpret_cast<const float4*>(partial)[i];
-    for (int s = 1; s < splits; ++s) {
-      float4 b = reinterpret_cast<const float4*>(partial)[(size_t)s * n4 + i];
+    // fixed summation order (deterministic); the loads of 8 splits are in flight together — one load per
+    // add serialised ~30 L2 round trips and made this kernel 13 us per call
+    const float4* pp = reinterpret_cast<const float4*>(partial) + i;
+    float4 a = pp[0];
+    int s = 1;
+    for (; s + 8 <= splits; s += 8) {
+      float4 b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) b[u] = pp[(size_t)(s + u) * n4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a.x += b[u].x; a.y += b[u].y; a.z += b[u].z; a.w += b[u].w; }
+    }
+    for (; s < splits; ++s) {
+      const float4 b = pp[(size_t)s * n4];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     reinterpret_cast<float4*>(dw)[i] = a;
@@ -950,7 +969,9 @@ static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout
   int splits = sms / tiles;                        // at most one wave of CTAs
   if (g_knobs.wg_splits) splits = (int)g_knobs.wg_splits;
   if (splits > pl->total_kb) splits = pl->total_kb;
-  if (splits > 64) splits = 64;
+  // one wave of CTAs; the cap only binds for single-tile problems (thin / 1x1 weight gradients), whose
+  // partials are small — capping at 64 left 84 SMs idle on an HBM-bound reduction
+  if (splits > sms) splits = sms;
   if (splits < 1) splits = 1;
   pl->kb_per_split = (pl->total_kb + splits - 1) / splits;
   pl->splits = (pl->total_kb + pl->kb_per_split - 1) / pl->kb_per_split;

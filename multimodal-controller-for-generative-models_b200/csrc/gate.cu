@@ -129,24 +129,51 @@ bn_partial_kernel(const T* __restrict__ x, long P, int C, float* __restrict__ pa
   }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
-                                   float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float momentum, float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= C) return;
-  const int c = warp;
-  double S = 0.0, Q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    S += (double)partial[((size_t)b * 2 + 0) * C + c];
-    Q += (double)partial[((size_t)b * 2 + 1) * C + c];
-  }
+// Per-channel sums of the [nblocks][2][C] block partials, in fp64 and in a fixed order (deterministic).
+// Block = 32 channels x 32 partial lanes: every warp reads 128 contiguous bytes, four independent loads per
+// lane are in flight, and the 32 lane sums of a channel are combined through shared memory in lane order.
+// (One warp per channel with lane-strided rows was a chain of ~20 dependent L2 round trips: 10 us.)
+__device__ __forceinline__ void channel_partial_sums(const float* __restrict__ partial, int nblocks, int C,
+                                                     double& S, double& Q) {
+  __shared__ double sS[32][33], sQ[32][33];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  S = 0.0; Q = 0.0;
+  if (c < C) {
+    int b = bl;
+    for (; b + 96 < nblocks; b += 128) {
+      float s[4], q[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    S += __shfl_xor_sync(0xffffffffu, S, o);
-    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+      for (int u = 0; u < 4; ++u) {
+        s[u] = partial[((size_t)(b + 32 * u) * 2 + 0) * C + c];
+        q[u] = partial[((size_t)(b + 32 * u) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { S += (double)s[u]; Q += (double)q[u]; }
+    }
+    for (; b < nblocks; b += 32) {
+      S += (double)partial[((size_t)b * 2 + 0) * C + c];
+      Q += (double)partial[((size_t)b * 2 + 1) * C + c];
+    }
   }
-  if (lane == 0) {
+  sS[bl][cl] = S; sQ[bl][cl] = Q;
+  __syncthreads();
+  if (bl == 0) {
+    S = 0.0; Q = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) { S += sS[k][cl]; Q += sQ[k][cl]; }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
+                   float* __restrict__ mean, float* __restrict__ rstd,
+                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float momentum, float eps) {
+  double S, Q;
+  channel_partial_sums(partial, nblocks, C, S, Q);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if ((threadIdx.x >> 5) == 0 && c < C) {
     double m = S / count;
     double var = Q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -358,21 +385,13 @@ gate_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const 
   }
 }
 
-__global__ void gate_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
-                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= C) return;
-  double S = 0.0, Q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    S += (double)partial[((size_t)b * 2 + 0) * C + warp];
-    Q += (double)partial[((size_t)b * 2 + 1) * C + warp];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    S += __shfl_xor_sync(0xffffffffu, S, o);
-    Q += __shfl_xor_sync(0xffffffffu, Q, o);
-  }
-  if (lane == 0) { dbeta[warp] = (float)S; dgamma[warp] = (float)Q; }
+__global__ void __launch_bounds__(1024)
+gate_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  double S, Q;
+  channel_partial_sums(partial, nblocks, C, S, Q);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if ((threadIdx.x >> 5) == 0 && c < C) { dbeta[c] = (float)S; dgamma[c] = (float)Q; }
 }
 
 template <typename T, bool UP2>
@@ -589,7 +608,7 @@ extern "C" int mcgm_bn_stats(const void* x, int dtype, long P_total, int C, floa
   else
     bn_partial_kernel<__nv_bfloat16><<<grid, kGateThreads, smem, st>>>((const __nv_bfloat16*)x, P_total, C, partial);
   MCGM_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(partial, grid, C, (double)P_total, mean, rstd,
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, grid, C, (double)P_total, mean, rstd,
                                                            running_mean, running_var, momentum, eps);
   MCGM_LAUNCH_CHECK();
   return 0;
@@ -661,7 +680,7 @@ static int gate_bwd_t(const void* dy, const void* d_raw, const void* x, void* dx
     else
       gate_bwd_reduce_kernel<T, false><<<grid, kGateThreads, smem, st>>>((const T*)dy, (const T*)x, g, labels, bits, words, mean, rstd, gamma, beta, flags, partial);
     MCGM_LAUNCH_CHECK();
-    gate_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(partial, grid, C, dgamma, dbeta);
+    gate_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, grid, C, dgamma, dbeta);
     MCGM_LAUNCH_CHECK();
   }
   const int grid = gate_grid(g.P, TP, 148 * 8);

@@ -1,0 +1,131 @@
+"""Optimiser side of the training steps on the B200 kernels.
+
+``FusedAdam`` is ``torch.optim.Adam`` (src/train_gan.py:223-236: eps 1e-8, no amsgrad) and, with
+``clip_norm``, ``clip_grad_norm_`` + Adam (src/train_vae.py:110-111, src/train_glow.py:120-121) as ONE
+pass of ``mcgm_adam_step`` over a flat fp32 buffer per network: parameters, gradients and both moments
+are views of four flat buffers, the step counter and the clip coefficient live on the device, so a
+step is two or four kernel launches, never synchronises with the host and can be captured in a CUDA
+graph.  torch's multi-tensor path needs ~10 launches per step (plus a host round trip for the clip).
+
+The parameters stay the reference's ``nn.Parameter`` objects with the reference's names and shapes
+(``state_dict`` is unchanged); only their storage moves into the flat buffer.
+"""
+import torch
+
+from . import _lib
+
+_ALIGN = 64                      # floats: every parameter segment starts on a 256-byte boundary
+_FLAT_OF = {}                    # id(param) -> FlatBuffers
+
+
+class FlatBuffers:
+    """Parameters and gradients of one network as views of two flat fp32 buffers."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('Not valid parameters: nothing to optimise')
+        dev = self.params[0].device
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError('Not valid parameters: flat buffers need fp32 parameters on one device')
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                v = self.param[o:o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+                g = self.grad[o:o + p.numel()].view_as(p)
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                p.grad = g
+                self.grad_views.append(g)
+        for p in self.params:
+            _FLAT_OF[id(p)] = self
+
+    def zero_grad(self):
+        """One memset; ``p.grad`` stay views of the flat buffer (autograd accumulates in place)."""
+        self.grad.zero_()
+        for p, g in zip(self.params, self.grad_views):
+            if p.grad is not g:
+                p.grad = g
+
+
+def flat_buffers(params):
+    """The FlatBuffers that already holds exactly these parameters, else a new one."""
+    params = [p for p in params if p.requires_grad]
+    fb = _FLAT_OF.get(id(params[0])) if params else None
+    if fb is not None and len(fb.params) == len(params) and all(a is b for a, b in zip(fb.params, params)) \
+            and all(p.data.data_ptr() == fb.param.data_ptr() + 4 * o for p, o in zip(fb.params, fb.offsets)):
+        return fb
+    return FlatBuffers(params)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam on a flat buffer through ``mcgm_adam_step`` (CUDA only; there is no CPU path).
+
+    clip_norm: fold ``clip_grad_norm_(params, clip_norm)`` into the step (device-side coefficient).
+    grad_scale: constant factor on the gradient (e.g. 1/world_size for summed data-parallel gradients).
+    Parameters that never receive a gradient see g = 0, which leaves them (and their zero moments)
+    unchanged — the same outcome as torch skipping ``grad is None`` parameters.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clip_norm=None,
+                 grad_scale=1.0):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise ValueError('Not valid param groups: FusedAdam takes one group')
+        ps = self.param_groups[0]['params']
+        if not ps or not ps[0].is_cuda:
+            raise ValueError('Not valid device: FusedAdam needs CUDA parameters (no CPU fallback)')
+        self.flat = flat_buffers(ps)
+        dev = self.flat.param.device
+        self.exp_avg = torch.zeros_like(self.flat.param)
+        self.exp_avg_sq = torch.zeros_like(self.flat.param)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.clip_norm, self.grad_scale = clip_norm, float(grad_scale)
+        self.clip_out = torch.zeros(2, dtype=torch.float32, device=dev)       # [coef, total_norm]
+        self.clip_ws = torch.zeros(_lib.query("mcgm_grad_clip_workspace_bytes") // 4, dtype=torch.float32, device=dev)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    def reset_state(self):
+        """Back to step 0 with zero moments (what a freshly built optimiser holds)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_dev.zero_()
+
+    @property
+    def total_norm(self):
+        """Gradient norm seen by the last clipped step (device tensor)."""
+        return self.clip_out[1]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        st = torch.cuda.current_stream().cuda_stream
+        f = self.flat
+        coef = None
+        if self.clip_norm is not None:
+            _lib.call("mcgm_grad_clip_coef", f.grad.data_ptr(), f.numel, float(self.clip_norm),
+                      self.clip_out.data_ptr(), self.clip_ws.data_ptr(), st)
+            _lib.launch_count += 1
+            coef = self.clip_out.data_ptr()
+        _lib.call("mcgm_adam_step", f.param.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), f.numel, self.step_dev.data_ptr(), float(g['lr']),
+                  float(g['betas'][0]), float(g['betas'][1]), float(g['eps']), float(g['weight_decay']),
+                  self.grad_scale, coef, st)
+        _lib.launch_count += 1
+        # the update wrote through raw pointers: tell autograd (and the packed-weight caches keyed on
+        # ``Parameter._version``) that the parameters changed
+        torch.autograd.graph.increment_version(f.params)
+        return None

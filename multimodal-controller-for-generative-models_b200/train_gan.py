@@ -14,19 +14,27 @@ import torch.nn.functional as F
 from .config import GAN_HYPER, cfg
 
 
-def make_optimizer(model, lr, betas, capturable=False):
+def make_optimizer(model, lr, betas, capturable=False, fused=None):
     """Adam with torch defaults eps=1e-8, no amsgrad (src/train_gan.py:223-236).
-    ``capturable`` keeps the step counter on the device so the update can live in a CUDA graph."""
-    return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas,
+    On CUDA this is ``optim.FusedAdam`` (one native pass over a flat buffer, device-side step counter:
+    always graph-capturable); ``fused=False`` or CPU parameters give ``torch.optim.Adam``, where
+    ``capturable`` keeps the step counter on the device."""
+    params = list(model.parameters())
+    if fused is None:
+        fused = bool(params) and params[0].is_cuda
+    if fused:
+        from .optim import FusedAdam
+        return FusedAdam(params, lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas)
+    return torch.optim.Adam(params, lr=lr, weight_decay=GAN_HYPER['weight_decay'], betas=betas,
                             capturable=capturable)
 
 
-def make_optimizers(model, capturable=False):
+def make_optimizers(model, capturable=False, fused=None):
     return {
         'generator': make_optimizer(model.generator, GAN_HYPER['lr']['generator'], GAN_HYPER['betas']['generator'],
-                                    capturable),
+                                    capturable, fused),
         'discriminator': make_optimizer(model.discriminator, GAN_HYPER['lr']['discriminator'],
-                                        GAN_HYPER['betas']['discriminator'], capturable),
+                                        GAN_HYPER['betas']['discriminator'], capturable, fused),
     }
 
 
@@ -48,31 +56,24 @@ class GradAllReduce:
         self.group = group
         self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        from .optim import flat_buffers
         self.params = [p for p in module.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        self.views = []
-        for p in self.params:
-            g = self.flat[off:off + p.numel()].view_as(p)
-            p.grad = g
-            self.views.append(g)
-            off += p.numel()
+        fb = flat_buffers(self.params)          # shared with FusedAdam when the optimiser was built first
+        self.flat, self.views = fb.grad, fb.grad_views
+        total = fb.numel
         # buckets over the flat buffer, filled from the END (backward reaches late layers first)
         self.buckets = []           # (start, stop, n_params)
         self.bucket_of = {}
-        start = stop = total
+        stop = total
         count = 0
-        for p in reversed(self.params):
-            start -= p.numel()
+        for p, start in zip(reversed(self.params), reversed(fb.offsets)):
             count += 1
             self.bucket_of[id(p)] = len(self.buckets)
             if (stop - start) * 4 >= bucket_bytes:
                 self.buckets.append([start, stop, count])
                 stop, count = start, 0
         if count:
-            self.buckets.append([start, stop, count])
+            self.buckets.append([0, stop, count])
         self.pending = [0] * len(self.buckets)
         self.handles = []
         self.enabled = True
@@ -120,20 +121,35 @@ def hinge_d(d_real, d_fake):
 
 
 def d_forward_backward(model, img, label, z):
-    """Forward + backward of one D update (src/train_gan.py:143-157); returns the hinge loss."""
+    """Forward + backward of one D update (src/train_gan.py:143-157); returns the hinge loss.
+    G(z) is detached by the reference (:148), so the generator runs without an autograd tape."""
     d_x = model.discriminate(img, label)
-    generated = model.generate(label, z)
-    d_g = model.discriminate(generated.detach(), label)
+    with torch.no_grad():
+        generated = model.generate(label, z)
+    d_g = model.discriminate(generated, label)
     d_loss = hinge_d(d_x, d_g)
     d_loss.backward()
     return d_loss
 
 
 def g_forward_backward(model, label, z):
-    """Forward + backward of one G update (src/train_gan.py:165-175); returns -D(G(z)).mean()."""
-    generated = model.generate(label, z)
-    g_loss = -model.discriminate(generated, label).mean()
-    g_loss.backward()
+    """Forward + backward of one G update (src/train_gan.py:165-175); returns -D(G(z)).mean().
+
+    The reference lets autograd fill D's parameter gradients here and throws them away at the next
+    ``zero_grad`` (:141 / :163) before anyone reads them.  D's parameters are therefore frozen for this
+    backward: the discriminator only propagates the gradient to its input (dgrad), its eleven weight
+    gradients and spectral-norm backward passes are not computed.  Every value the reference ever uses
+    is unchanged."""
+    d_params = [p for p in model.discriminator.parameters() if p.requires_grad]
+    for p in d_params:
+        p.requires_grad_(False)
+    try:
+        generated = model.generate(label, z)
+        g_loss = -model.discriminate(generated, label).mean()
+        g_loss.backward()
+    finally:
+        for p in d_params:
+            p.requires_grad_(True)
     return g_loss
 
 

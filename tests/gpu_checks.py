@@ -461,3 +461,38 @@ def check_conv_variants():
 
 ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
                      check_conv_wgrad, check_thin, check_conv_variants, check_sn, check_conv_ex, check_conv_tf32]
+
+
+# ----------------------------------------------------------------------------- optimiser
+def check_optim():
+    """optim.FusedAdam (mcgm_adam_step / mcgm_grad_clip_coef) against torch.optim.Adam
+    (+ clip_grad_norm_) on identical parameters and gradients, several steps.  fp32 elementwise
+    arithmetic in a different association order: agreement to a few ulp of the update."""
+    from mcgm_b200.optim import FusedAdam
+    rows = []
+    for (clip, wd, betas) in [(None, 0.0, (0.0, 0.9)), (1.0, 0.0, (0.9, 0.999)), (0.05, 1e-2, (0.5, 0.99))]:
+        g = torch.Generator().manual_seed(7)
+        shapes = [(64, 32, 3, 3), (64,), (130, 7), (5,), (256, 128, 1, 1)]
+        ref = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+        got = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+        o_ref = torch.optim.Adam(ref, lr=2e-3, betas=betas, weight_decay=wd)
+        o_got = FusedAdam(got, lr=2e-3, betas=betas, weight_decay=wd, clip_norm=clip)
+        for it in range(5):
+            grads = [torch.randn(*s, generator=g).to(DEV) * (10.0 if it == 2 else 0.3) for s in shapes]
+            o_ref.zero_grad()
+            o_got.zero_grad()
+            for p, q, gr in zip(ref, got, grads):
+                p.grad = gr.clone()
+                q.grad.add_(gr)                       # accumulates into the flat-buffer view, like autograd
+            if clip is not None:
+                tn = torch.nn.utils.clip_grad_norm_(ref, clip)
+            o_ref.step()
+            o_got.step()
+            if clip is not None:
+                rows.append((f"adam clip={clip} step {it}: total_norm", rel(o_got.total_norm, tn), F32_TOL))
+        for i, (p, q) in enumerate(zip(ref, got)):
+            rows.append((f"adam clip={clip} wd={wd} betas={betas}: param {i} after 5 steps", rel(q, p), F32_TOL))
+        rows.append((f"adam clip={clip}: device step counter", float(abs(int(o_got.step_dev.item()) - 5)), EXACT))
+        rows.append((f"adam clip={clip}: params are views of the flat buffer",
+                     float(got[0].data_ptr() != o_got.flat.param.data_ptr()), EXACT))
+    return rows

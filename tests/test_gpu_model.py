@@ -190,8 +190,7 @@ def test_graph_replay_equals_eager(golden):
     m_graph.load_state_dict(m_eager.state_dict())
     opt_e = train_gan.make_optimizers(m_eager, capturable=True)
     for o in opt_g.values():
-        for st in o.state.values():
-            st["step"].zero_(); st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        o.reset_state()
     for _ in range(2):
         out_e = train_gan.train_step(m_eager, opt_e, batch, z=batch["z"])
         out_g = graphed(batch)
