@@ -218,6 +218,32 @@ int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, i
 int mcgm_split_tf32(const float* x, float* big, float* small, long n, void* stream);
 int mcgm_split_bf16x3(const float* x, void* p1, void* p2, void* p3, long n, void* stream);
 
+/* ---- Glow flow step, few-channel part (fp32 NHWC [P = N*H*W, C], C a multiple of 4, C <= 64)
+ * front = ActNorm(C) -> InvConv2dLU (src/models/mcglow.py:24-55, 76-116):
+ *     y = W (scale * (x + loc)),  W = [C_out][C_in] row-major (calc_weight(), mcglow.py:104-110);
+ *     xa (optional) = bf16 y[:, :C/2] zero-padded to xa_ch channels — the coupling network's input in the
+ *     operand layout of mcgm_conv_fwd.
+ *   mcgm_flow_front_bwd: dx = scale * W^T g with g = dy + [dxa, 0]; G_out [C][C+1]:
+ *     G[o][i] = sum_p g[p,o] (x[p,i] + loc[i]) (i < C), G[o][C] = sum_p g[p,o]; the caller forms
+ *     dW = G[:, :C] * scale, dscale = sum_o W * G[:, :C], dloc = scale * (W^T G[:, C]).
+ * tail = AffineCoupling around its network (mcglow.py:153-164) with ZeroConv2d's scale (mcglow.py:119-130):
+ *     h = net * exp(3 zscale); affine: s = sigmoid(h[:C/2] + 2), out = [y[:C/2], (y[C/2:] + h[C/2:]) s],
+ *     logdet[n] = sum log s; additive (affine = 0): out = [y[:C/2], y[C/2:] + h[:C/2]].
+ *     net is fp32 NHWC with net_ch >= C (affine) / C/2 channels per pixel.
+ *   mcgm_flow_tail_bwd: dy, dnet (all net_ch channels written) and dz_partial [N][C or C/2] whose sum over
+ *     n is dzscale. */
+int mcgm_flow_front_fwd(const float* x, const float* loc, const float* scale, const float* W, float* y,
+                        void* xa_bf16, long P, int C, int xa_ch, void* stream);
+size_t mcgm_flow_front_bwd_workspace_bytes(int C);
+int mcgm_flow_front_bwd(const float* dy, const void* dxa_bf16, const float* x, const float* loc, const float* scale,
+                        const float* W, float* dx, float* G_out, long P, int C, int xa_ch, void* workspace,
+                        void* stream);
+int mcgm_flow_tail_fwd(const float* y, const float* net, const float* zscale, float* out, float* logdet, int N,
+                       int HW, int C, int net_ch, int affine, void* stream);
+int mcgm_flow_tail_bwd(const float* dout, const float* dlogdet, const float* y, const float* net,
+                       const float* zscale, float* dy, float* dnet, float* dz_partial, int N, int HW, int C,
+                       int net_ch, int affine, void* stream);
+
 /* ---- optimiser step on flat fp32 buffers (optim.Adam src/train_gan.py:223-236, eps 1e-8, no amsgrad;
  * clip_grad_norm_ + Adam src/train_vae.py:110-111, src/train_glow.py:120-121).  n must be a multiple of 4,
  * buffers 16-byte aligned.  `step` is a DEVICE int32 (number of updates applied so far; advanced by the

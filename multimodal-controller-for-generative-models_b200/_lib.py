@@ -60,6 +60,15 @@ SIGNATURES = {
                                  c_void_p]),
     "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mcgm_unpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mcgm_flow_front_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int,
+                                    c_void_p]),
+    "mcgm_flow_front_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "mcgm_flow_front_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_long, c_int, c_int, c_void_p, c_void_p]),
+    "mcgm_flow_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
+    "mcgm_flow_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mcgm_grad_clip_workspace_bytes": (c_size_t, []),
     "mcgm_grad_clip_coef": (c_int, [c_void_p, c_long, c_float, c_void_p, c_void_p, c_void_p]),
     "mcgm_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,

@@ -5,9 +5,12 @@ Where the work is.  Per flow step the coupling network
     Conv3x3(C/2→512) → ActNorm → ReLU → MC → Conv1x1(512→512) → ActNorm → ReLU → MC → ZeroConv3x3(512→C)
 carries > 99.9 % of the flops and bytes; it runs on the tcgen05 conv kernels with
 ActNorm → ReLU → MC fused into ONE gate kernel pair (``ops.ActNormGateFn``).  The few-channel
-(C ≤ 48) flow arithmetic around it — ActNorm(C), the LU-parameterised invertible 1x1 conv, the affine
-coupling, squeeze / split / Gaussian prior — stays in torch on fp32 NCHW tensors that are 10–40x
-smaller than the 512-channel activations.
+(C ≤ 48) arithmetic around it runs on fp32 NHWC tensors through two native kernel pairs (csrc/flow.cu):
+``ops.FlowFrontFn`` = ActNorm(C) → invertible 1x1 conv, which also emits the coupling network's bf16
+input, and ``ops.FlowTailFn`` = ZeroConv2d's exp(3·scale) → sigmoid → affine coupling → per-sample
+logdet.  Only parameter-sized work (the C×C LU product, Σ log|scale|), the squeeze / split reshapes
+and the three Gaussian priors per forward stay in torch.  The sampling path (``reverse``) is the
+reference's NCHW formulation on the same coupling-network kernels.
 
 Channel padding: the tensor-core kernels take input channels in multiples of 64 and output channels
 in {<=16, 32, 64k}; C/2 ∈ {6, 12, 24} inputs are zero-padded to 64 channels and C ∈ {12, 24, 48}
@@ -175,31 +178,29 @@ class AffineCoupling(nn.Module):
             actnorm.initialize_from(hf.mean(dim=(0, 1, 2)), hf.std(dim=(0, 1, 2)))
         return ops.ActNormGateFn.apply(h, actnorm.scale, actnorm.loc, ctx.labels, mc.packed())
 
-    def run_net(self, in_a, ctx):
-        """in_a: NCHW fp32 [N, C/2, H, W] -> net output NCHW fp32 [N, C_out, H, W]."""
-        c_in = in_a.size(1)
+    def net_nhwc(self, xa, ctx):
+        """xa: bf16 NHWC [N,H,W,64] (C/2 live channels) -> RAW zero-conv output fp32 NHWC [N,H,W,64]
+        (C or C/2 live channels; ZeroConv2d's exp(3*scale) is applied by the consumer)."""
         conv1, conv2, zero = self.net[0].module, self.net[4].module, self.net[8].module
-        c_out = zero.conv.out_channels
-        x = _pad_to(in_a.permute(0, 2, 3, 1), 3, 64).to(torch.bfloat16).contiguous()      # NHWC, Cin -> 64
-        h = _conv(x, _pad_to(conv1.weight, 1, 64), conv1.bias)
+        h = _conv(xa, _pad_to(conv1.weight, 1, 64), conv1.bias)
         h = self._gate(h, self.net[1].module, self.net[3], ctx)
         h = _conv(h, conv2.weight, conv2.bias)
         h = self._gate(h, self.net[5].module, self.net[7], ctx)
-        out = _conv(h, _pad_to(zero.conv.weight, 0, 64), _pad_to(zero.conv.bias, 0, 64), True)  # fp32 [N,H,W,64]
-        out = out[..., :c_out].permute(0, 3, 1, 2)
+        return _conv(h, _pad_to(zero.conv.weight, 0, 64), _pad_to(zero.conv.bias, 0, 64), True)
+
+    def run_net(self, in_a, ctx):
+        """in_a: NCHW fp32 [N, C/2, H, W] -> net output NCHW fp32 [N, C_out, H, W] (sampling path)."""
+        zero = self.net[8].module
+        c_out = zero.conv.out_channels
+        x = _pad_to(in_a.permute(0, 2, 3, 1), 3, 64).to(torch.bfloat16).contiguous()      # NHWC, Cin -> 64
+        out = self.net_nhwc(x, ctx)[..., :c_out].permute(0, 3, 1, 2)
         return out * torch.exp(zero.scale * 3)
 
-    def forward(self, input, ctx):
-        in_a, in_b = input.chunk(2, 1)
-        if self.affine:
-            log_s, t = self.run_net(in_a, ctx).chunk(2, 1)
-            s = torch.sigmoid(log_s + 2)
-            out_b = (in_b + t) * s
-            logdet = torch.sum(torch.log(s).reshape(input.size(0), -1), 1)
-        else:
-            out_b = in_b + self.run_net(in_a, ctx)
-            logdet = None
-        return torch.cat([in_a, out_b], 1), logdet
+    def forward(self, y, xa, ctx):
+        """y: fp32 NHWC [N,H,W,C] (the flow variable after the invertible conv), xa: its first half as the
+        network's bf16 input (both from ``ops.FlowFrontFn``) -> (out NHWC, logdet [N] or None)."""
+        out, logdet = ops.FlowTailFn.apply(y, self.net_nhwc(xa, ctx), self.net[8].module.scale, self.affine)
+        return out, (logdet if self.affine else None)
 
     def reverse(self, output, ctx):
         out_a, out_b = output.chunk(2, 1)
@@ -221,10 +222,14 @@ class Flow(nn.Module):
         self.coupling = AffineCoupling(input_size, hidden_size, affine, num_mode, controller_rate)
 
     def forward(self, input, ctx):
-        out, logdet = self.actnorm(input)
-        out, det1 = self.invconv(out)
-        out, det2 = self.coupling(out, ctx)
-        logdet = logdet + det1
+        """input: fp32 NHWC [N,H,W,C] -> (out NHWC, logdet [N])   (src/models/mcglow.py:186-193)."""
+        an, hw = self.actnorm, input.size(1) * input.size(2)
+        if an.needs_init():
+            xf = input.detach()
+            an.initialize_from(xf.mean(dim=(0, 1, 2)), xf.std(dim=(0, 1, 2)))
+        y, xa = ops.FlowFrontFn.apply(input, an.loc, an.scale, self.invconv.calc_weight()[:, :, 0, 0])
+        out, det2 = self.coupling(y, xa, ctx)
+        logdet = hw * (torch.sum(logabs(an.scale)) + torch.sum(self.invconv.w_s))
         if det2 is not None:
             logdet = logdet + det2
         return out, logdet
@@ -244,20 +249,23 @@ class Block(nn.Module):
         self.prior = ZeroConv2d(input_size * 2, input_size * 4) if split else ZeroConv2d(input_size * 4, input_size * 8)
 
     def forward(self, input, ctx):
-        b, c, h, w = input.shape
-        out = input.reshape(b, c, h // 2, 2, w // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(b, c * 4, h // 2, w // 2)
+        """input: fp32 NHWC [N,H,W,c] -> (out NHWC, logdet, log_p, z_new NCHW)   (mcglow.py:213-239).
+        Squeeze keeps the reference's channel order c*4 + i*2 + j."""
+        b, h, w, c = input.shape
+        out = input.reshape(b, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 5, 2, 4).reshape(b, h // 2, w // 2, c * 4)
         logdet = 0
         for flow in self.flows:
             out, det = flow(out, ctx)
             logdet = logdet + det
         if self.split:
-            out, z_new = out.chunk(2, 1)
-            mean, log_sd = self.prior(out).chunk(2, 1)
+            out, z_new = out.chunk(2, 3)
+            z_new = z_new.permute(0, 3, 1, 2)                       # NCHW views of the (small) NHWC halves
+            mean, log_sd = self.prior(out.permute(0, 3, 1, 2)).chunk(2, 1)
             log_p = gaussian_log_p(z_new, mean, log_sd).reshape(b, -1).sum(1)
         else:
-            mean, log_sd = self.prior(torch.zeros_like(out)).chunk(2, 1)
-            log_p = gaussian_log_p(out, mean, log_sd).reshape(b, -1).sum(1)
-            z_new = out
+            z_new = out.permute(0, 3, 1, 2)
+            mean, log_sd = self.prior(torch.zeros_like(z_new)).chunk(2, 1)
+            log_p = gaussian_log_p(z_new, mean, log_sd).reshape(b, -1).sum(1)
         return out, logdet, log_p, z_new
 
     def reverse(self, output, ctx, eps=None, reconstruct=False):
@@ -308,6 +316,7 @@ class MCGlow(nn.Module):
         ctx = _Ctx(_labels_from_indicator(input['label']))
         x = input['img'] * 0.5
         x = x + (torch.rand_like(x) if noise is None else noise) / 256
+        x = x.permute(0, 2, 3, 1).contiguous()                     # the flow variables travel as fp32 NHWC
         z, log_p_sum, logdet = [], 0, 0
         for block in self.blocks:
             x, det, log_p, z_new = block(x, ctx)

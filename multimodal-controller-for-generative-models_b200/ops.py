@@ -898,3 +898,84 @@ class Pool2Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         return unpool2(dy.contiguous(), 0.25)
+
+
+# ----------------------------------------------------------------------------- Glow flow step (few-channel part)
+FLOW_XA_CH = 64          # channels of the coupling network's bf16 input (tcgen05 conv operand granularity)
+
+
+class FlowFrontFn(torch.autograd.Function):
+    """ActNorm(C) -> InvConv2dLU of one flow step (src/models/mcglow.py:24-55, 76-116) on fp32 NHWC:
+    y = W (scale*(x+loc)); second output xa = bf16 y[..., :C/2] zero-padded to 64 channels, the coupling
+    network's input.  W is the CxC matrix from ``InvConv2dLU.calc_weight()`` (autograd carries the
+    gradient on through the LU parameters)."""
+
+    @staticmethod
+    def forward(ctx, x, loc, scale, W):
+        _check_cuda(x, loc, scale, W)
+        N, H, Wd, C = x.shape
+        lc, sc, Wc = loc.detach().reshape(C).contiguous(), scale.detach().reshape(C).contiguous(), W.detach().contiguous()
+        y = torch.empty_like(x)
+        xa = torch.empty(N, H, Wd, FLOW_XA_CH, dtype=torch.bfloat16, device=x.device)
+        _lib.call("mcgm_flow_front_fwd", x.data_ptr(), lc.data_ptr(), sc.data_ptr(), Wc.data_ptr(), y.data_ptr(),
+                  xa.data_ptr(), N * H * Wd, C, FLOW_XA_CH, _stream())
+        ctx.save_for_backward(x, lc, sc, Wc)
+        ctx.pshape = loc.shape
+        return y, xa
+
+    @staticmethod
+    def backward(ctx, dy, dxa):
+        x, lc, sc, Wc = ctx.saved_tensors
+        N, H, Wd, C = x.shape
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dy = dy.contiguous()
+        dxa = dxa.contiguous() if dxa is not None else None
+        dx = torch.empty_like(x)
+        G = torch.empty(C, C + 1, dtype=torch.float32, device=x.device)
+        ws = _workspace("flow_front", _lib.query("mcgm_flow_front_bwd_workspace_bytes", C), x.device)
+        _lib.call("mcgm_flow_front_bwd", dy.data_ptr(), _ptr(dxa), x.data_ptr(), lc.data_ptr(), sc.data_ptr(),
+                  Wc.data_ptr(), dx.data_ptr(), G.data_ptr(), N * H * Wd, C, FLOW_XA_CH, ws.data_ptr(), _stream())
+        _lib.launch_count += 2
+        Gm, S = G[:, :C], G[:, C]
+        dW = Gm * sc[None, :]
+        dscale = (Wc * Gm).sum(0)
+        dloc = sc * (Wc.t() @ S)
+        return dx, dloc.reshape(ctx.pshape), dscale.reshape(ctx.pshape), dW
+
+
+class FlowTailFn(torch.autograd.Function):
+    """The affine (or additive) coupling around its network plus ZeroConv2d's exp(3*scale)
+    (src/models/mcglow.py:119-130, 153-164): y fp32 NHWC [N,H,W,C], net fp32 NHWC [N,H,W,>=C] (the raw
+    zero-conv output) -> out [N,H,W,C], logdet [N]."""
+
+    @staticmethod
+    def forward(ctx, y, net, zscale, affine):
+        _check_cuda(y, net, zscale)
+        N, H, Wd, C = y.shape
+        y, net = y.contiguous(), net.contiguous()
+        zs = zscale.detach().reshape(-1).contiguous()
+        out = torch.empty_like(y)
+        logdet = torch.zeros(N, dtype=torch.float32, device=y.device)
+        _lib.call("mcgm_flow_tail_fwd", y.data_ptr(), net.data_ptr(), zs.data_ptr(), out.data_ptr(), logdet.data_ptr(),
+                  N, H * Wd, C, net.shape[-1], 1 if affine else 0, _stream())
+        ctx.save_for_backward(y, net, zs)
+        ctx.affine, ctx.zshape = affine, zscale.shape
+        return out, logdet
+
+    @staticmethod
+    def backward(ctx, dout, dlogdet):
+        y, net, zs = ctx.saved_tensors
+        N, H, Wd, C = y.shape
+        if dout is None:
+            dout = torch.zeros_like(y)
+        dout = dout.contiguous()
+        dlogdet = dlogdet.contiguous() if dlogdet is not None else None
+        dy = torch.empty_like(y)
+        dnet = torch.empty_like(net)
+        nz = C if ctx.affine else C // 2
+        dzp = torch.empty(N, nz, dtype=torch.float32, device=y.device)
+        _lib.call("mcgm_flow_tail_bwd", dout.data_ptr(), _ptr(dlogdet), y.data_ptr(), net.data_ptr(), zs.data_ptr(),
+                  dy.data_ptr(), dnet.data_ptr(), dzp.data_ptr(), N, H * Wd, C, net.shape[-1],
+                  1 if ctx.affine else 0, _stream())
+        return dy, dnet, dzp.sum(0).reshape(ctx.zshape), None

@@ -496,3 +496,67 @@ def check_optim():
         rows.append((f"adam clip={clip}: params are views of the flat buffer",
                      float(got[0].data_ptr() != o_got.flat.param.data_ptr()), EXACT))
     return rows
+
+
+# ----------------------------------------------------------------------------- Glow flow kernels
+def check_flow():
+    """csrc/flow.cu through ops.FlowFrontFn / ops.FlowTailFn against the reference formulation
+    (ActNorm -> 1x1 conv; ZeroConv scale -> sigmoid -> affine coupling -> logdet) in torch fp32 on the
+    CPU, values and every gradient.  fp32 arithmetic, different summation order: F32 tolerance; the bf16
+    network input is compared after the same rounding."""
+    rows = []
+    for (N, H, C, affine) in [(5, 16, 12, True), (3, 8, 24, True), (4, 4, 48, True), (2, 8, 4, True), (3, 4, 24, False)]:
+        g = torch.Generator().manual_seed(100 + C + H)
+        x = torch.randn(N, H, H, C, generator=g)
+        loc, scale = torch.randn(1, C, 1, 1, generator=g) * 0.3, torch.rand(1, C, 1, 1, generator=g) + 0.5
+        Wm = torch.randn(C, C, generator=g) / C ** 0.5 + torch.eye(C)
+        dy, dxa = torch.randn(N, H, H, C, generator=g), torch.randn(N, H, H, 64, generator=g).to(torch.bfloat16)
+        # reference (NCHW, as the modules compute it)
+        xr, lr_, sr, Wr = [t.clone().requires_grad_(True) for t in (x, loc, scale, Wm)]
+        a = sr * (xr.permute(0, 3, 1, 2) + lr_)
+        yr = F.conv2d(a, Wr[:, :, None, None]).permute(0, 2, 3, 1)
+        (yr * dy).sum().backward(retain_graph=True)
+        (yr[..., :C // 2] * dxa[..., :C // 2].float()).sum().backward()
+        xd, ld, sd_, Wd = [t.to(DEV).requires_grad_(True) for t in (x, loc, scale, Wm)]
+        y, xa = ops.FlowFrontFn.apply(xd, ld, sd_, Wd)
+        torch.autograd.backward([y, xa], [dy.to(DEV), dxa.to(DEV)])
+        tag = f"flow front N={N} H={H} C={C}"
+        rows.append((tag + " y", rel(y, yr), F32_TOL))
+        want_xa = torch.zeros(N, H, H, 64)
+        want_xa[..., :C // 2] = yr[..., :C // 2].detach()
+        rows.append((tag + " xa (bf16, zero padded)", rel(xa.float(), want_xa.to(torch.bfloat16).float()), BF16_OUT))
+        rows.append((tag + " xa padding is zero", float(xa[..., C // 2:].float().abs().max()), EXACT))
+        for nm, got, ref in (("dx", xd.grad, xr.grad), ("dloc", ld.grad, lr_.grad), ("dscale", sd_.grad, sr.grad),
+                             ("dW", Wd.grad, Wr.grad)):
+            rows.append((f"{tag} {nm}", rel(got, ref), F32_TOL))
+        # tail
+        yv = torch.randn(N, H, H, C, generator=g)
+        nout = C if affine else C // 2
+        net = torch.zeros(N, H, H, 64)
+        net[..., :nout] = torch.randn(N, H, H, nout, generator=g)
+        zs = torch.randn(1, nout, 1, 1, generator=g) * 0.2
+        dout, dld = torch.randn(N, H, H, C, generator=g), torch.randn(N, generator=g)
+        yr2, nr, zr = [t.clone().requires_grad_(True) for t in (yv, net, zs)]
+        hcl = nr[..., :nout] * torch.exp(zr.reshape(nout) * 3)
+        in_a, in_b = yr2[..., :C // 2], yr2[..., C // 2:]
+        if affine:
+            s = torch.sigmoid(hcl[..., :C // 2] + 2)
+            outr = torch.cat([in_a, (in_b + hcl[..., C // 2:]) * s], -1)
+            ldr = torch.log(s).reshape(N, -1).sum(1)
+            ((outr * dout).sum() + (ldr * dld).sum()).backward()
+        else:
+            outr = torch.cat([in_a, in_b + hcl], -1)
+            (outr * dout).sum().backward()
+        yd2, nd, zd = [t.to(DEV).requires_grad_(True) for t in (yv, net, zs)]
+        out, ldg = ops.FlowTailFn.apply(yd2, nd, zd, affine)
+        if affine:
+            torch.autograd.backward([out, ldg], [dout.to(DEV), dld.to(DEV)])
+            rows.append((f"flow tail C={C} logdet", rel(ldg, ldr), F32_TOL))
+        else:
+            out.backward(dout.to(DEV))
+        tag = f"flow tail N={N} H={H} C={C} affine={affine}"
+        rows.append((tag + " out", rel(out, outr), F32_TOL))
+        rows.append((tag + " dy", rel(yd2.grad, yr2.grad), F32_TOL))
+        rows.append((tag + " dnet", rel(nd.grad, nr.grad), F32_TOL))
+        rows.append((tag + " dzscale", rel(zd.grad, zr.grad), F32_TOL))
+    return rows

@@ -83,11 +83,10 @@ def test_glow_forward_gradients_and_step_vs_reference(golden):
     assert errs[0][0] < 1.2e-1, errs[:4]
     assert errs[len(errs) // 2][0] < 3e-2
     # one optimiser step (clip + Adam 3e-4), then the next loss
-    opt = train_vae.make_optimizer(model)
+    opt = train_vae.make_optimizer(model)            # FusedAdam: clip_grad_norm_(1) folded into the step
     opt.zero_grad()
     out = model(inp, noise)
     out["loss"].backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
     opt.step()
     out2 = model(inp, noise)
     print("glow step loss", float(out2["loss"].detach()), case["loss_step2"])
