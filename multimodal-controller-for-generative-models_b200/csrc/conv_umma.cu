@@ -799,42 +799,59 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/,
-                                    float* __restrict__ dw, const float* __restrict__ bias_partial, int bias_rows,
-                                    int Cout, float* __restrict__ dbias) {
-  if (dbias && blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
-      float a = 0.0f;
-      int s = 0;
-      for (; s + 8 <= bias_rows; s += 8) {
-        float b[8];
+// Split-K reduction: dw[i] = sum_s partial[s][i], dbias[c] = sum_r bias_partial[r][c].
+// Block = 32 consecutive outputs x 8 split lanes (one warp each): a warp reads 512 contiguous bytes of one
+// split, lane w of a column sums splits w, w+8, ... with four loads in flight, and the eight lane sums are
+// combined through shared memory in lane order — a fixed order, hence deterministic.  (One thread per output
+// walking all splits was a chain of up to 148 dependent L2 round trips on 8..144 blocks: 13-16 us a call.)
+static constexpr int kRedLanes = 8;
+
+template <typename V>
+__device__ __forceinline__ V red_zero();
+template <> __device__ __forceinline__ float4 red_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float red_zero<float>() { return 0.f; }
+__device__ __forceinline__ void red_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void red_add(float& a, const float& b) { a += b; }
+
+template <typename V>
+__device__ __forceinline__ void reduce_columns(const V* __restrict__ src, int rows, size_t row_stride, size_t n,
+                                               size_t i0, V* __restrict__ dst, V (*sm)[32]) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t i = i0 + lane;
+  V a = red_zero<V>();
+  if (i < n) {
+    int s = w;
+    for (; s + 3 * kRedLanes < rows; s += 4 * kRedLanes) {
+      V b[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) b[u] = bias_partial[(size_t)(s + u) * Cout + c];
+      for (int u = 0; u < 4; ++u) b[u] = src[(size_t)(s + u * kRedLanes) * row_stride + i];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a += b[u];
-      }
-      for (; s < bias_rows; ++s) a += bias_partial[(size_t)s * Cout + c];
-      dbias[c] = a;
+      for (int u = 0; u < 4; ++u) red_add(a, b[u]);
     }
+    for (; s < rows; s += kRedLanes) red_add(a, src[(size_t)s * row_stride + i]);
   }
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    // fixed summation order (deterministic); the loads of 8 splits are in flight together — one load per
-    // add serialised ~30 L2 round trips and made this kernel 13 us per call
-    const float4* pp = reinterpret_cast<const float4*>(partial) + i;
-    float4 a = pp[0];
-    int s = 1;
-    for (; s + 8 <= splits; s += 8) {
-      float4 b[8];
+  sm[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && i < n) {
+    V t = sm[0][lane];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) b[u] = pp[(size_t)(s + u) * n4];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { a.x += b[u].x; a.y += b[u].y; a.z += b[u].z; a.w += b[u].w; }
-    }
-    for (; s < splits; ++s) {
-      const float4 b = pp[(size_t)s * n4];
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    reinterpret_cast<float4*>(dw)[i] = a;
+    for (int k = 1; k < kRedLanes; ++k) red_add(t, sm[k][lane]);
+    dst[i] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(32 * kRedLanes)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/, float* __restrict__ dw,
+                    const float* __restrict__ bias_partial, int bias_rows, int Cout, float* __restrict__ dbias,
+                    int wblocks) {
+  __shared__ float4 sm4[kRedLanes][32];
+  if ((int)blockIdx.x < wblocks) {
+    for (size_t i0 = (size_t)blockIdx.x * 32; i0 < n4; i0 += (size_t)wblocks * 32)
+      reduce_columns<float4>(reinterpret_cast<const float4*>(partial), splits, n4, n4, i0, reinterpret_cast<float4*>(dw), sm4);
+  } else {
+    float (*sm1)[32] = reinterpret_cast<float (*)[32]>(&sm4[0][0]);
+    reduce_columns<float>(bias_partial, bias_rows, (size_t)Cout, (size_t)Cout, (size_t)(blockIdx.x - wblocks) * 32, dbias, sm1);
   }
 }
 
@@ -1197,9 +1214,11 @@ static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy
   }
   if (e) return e;
   const size_t n4 = pl.per_split / 4;
-  long blocks = (long)((n4 + 255) / 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial, pl.splits * p.bias_slots, Cout, dbias);
+  long wblocks = (long)((n4 + 31) / 32);
+  if (wblocks > 148 * 16) wblocks = 148 * 16;
+  const int bblocks = (dbias && p.bias_partial) ? (Cout + 31) / 32 : 0;
+  wgrad_reduce_kernel<<<(int)wblocks + bblocks, 32 * kRedLanes, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial,
+                                                                        pl.splits * p.bias_slots, Cout, dbias, (int)wblocks);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -22,8 +22,11 @@ template <typename OT>
 __global__ void __launch_bounds__(256)
 thin_im2col_kernel(const float* __restrict__ thin, OT* __restrict__ U, int N, int H, int W, int Ho, int Wo,
                    int Ct, int R, int S, int stride, int pad, int sgn, int KU, PixDiv dw, PixDiv dhw) {
-  // column -> (row offset, column offset, channel) tables: no division in the hot loop
+  // column -> (row offset, column offset, channel) tables: no division in the hot loop.  toff is the
+  // element offset of a column's source relative to the centre pixel: for interior pixels (every tap in
+  // bounds — 88 % of a 32x32 image) a value is one table read and one load, no bounds arithmetic.
   __shared__ signed char tdr[128], tds[128], tj[128];
+  __shared__ int toff[128];
   const int T = R * S;
   for (int col = threadIdx.x; col < KU; col += blockDim.x) {
     if (col < T * Ct) {
@@ -31,11 +34,16 @@ thin_im2col_kernel(const float* __restrict__ thin, OT* __restrict__ U, int N, in
       tdr[col] = (signed char)(sgn * (r - pad));
       tds[col] = (signed char)(sgn * (t - r * S - pad));
       tj[col] = (signed char)(col - t * Ct);
+      toff[col] = (sgn * (r - pad) * W + sgn * (t - r * S - pad)) * Ct + (col - t * Ct);
     } else {
       tj[col] = -1;
+      toff[col] = 0;
     }
   }
   __syncthreads();
+  const int dr_a = sgn * (0 - pad), dr_b = sgn * (R - 1 - pad), ds_a = sgn * (0 - pad), ds_b = sgn * (S - 1 - pad);
+  const int dr_lo = dr_a < dr_b ? dr_a : dr_b, dr_hi = dr_a < dr_b ? dr_b : dr_a;
+  const int ds_lo = ds_a < ds_b ? ds_a : ds_b, ds_hi = ds_a < ds_b ? ds_b : ds_a;
   constexpr int V = Vec<OT>::N;
   const uint32_t groups = KU / V, used = (T * Ct + V - 1) / V;
   const uint32_t HWo = (uint32_t)Ho * Wo;
@@ -47,12 +55,21 @@ thin_im2col_kernel(const float* __restrict__ thin, OT* __restrict__ U, int N, in
     for (int i = 0; i < V; ++i) o.v[i] = 0.0f;
     if (gidx < used) {
       const uint32_t n = dhw.div(p), hw = p - n * HWo, h = dw.div(hw), w = hw - h * Wo;
+      const int h0 = (int)h * stride, w0 = (int)w * stride;
+      if (h0 + dr_lo >= 0 && h0 + dr_hi < H && w0 + ds_lo >= 0 && w0 + ds_hi < W) {
+        const float* base = thin + ((size_t)(n * H + h0) * W + w0) * Ct;
+        const int nv = T * Ct - (int)gidx * V;               // live columns of this group
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int col = gidx * V + i, j = tj[col];
-        const int hh = (int)h * stride + tdr[col], ww = (int)w * stride + tds[col];
-        if (j >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W)
-          o.v[i] = __ldg(thin + ((size_t)(n * H + hh) * W + ww) * Ct + j);
+        for (int i = 0; i < V; ++i)
+          if (i < nv) o.v[i] = __ldg(base + toff[gidx * V + i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const int col = gidx * V + i, j = tj[col];
+          const int hh = h0 + tdr[col], ww = w0 + tds[col];
+          if (j >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W)
+            o.v[i] = __ldg(thin + ((size_t)(n * H + hh) * W + ww) * Ct + j);
+        }
       }
     }
     o.store(U + (size_t)p * KU + gidx * V);

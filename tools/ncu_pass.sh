@@ -5,9 +5,9 @@ set -x
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
 timeout 300 python tools/profile_step.py --mode d --warm 1 > gpurun_out/plain_d.log 2>&1 && \
-$NCU --metrics gpu__time_duration.sum -s 440 -c 3000 --csv --log-file gpurun_out/launches_d.csv python tools/profile_step.py --mode d --warm 1 > gpurun_out/ncu_d.log 2>&1
+$NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_d.csv python tools/profile_step.py --mode d --warm 1 > gpurun_out/ncu_d.log 2>&1
 timeout 300 python tools/profile_step.py --mode g --warm 1 > gpurun_out/plain_g.log 2>&1 && \
-$NCU --metrics gpu__time_duration.sum -s 440 -c 3000 --csv --log-file gpurun_out/launches_g.csv python tools/profile_step.py --mode g --warm 1 > gpurun_out/ncu_g.log 2>&1
+$NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_g.csv python tools/profile_step.py --mode g --warm 1 > gpurun_out/ncu_g.log 2>&1
 timeout 300 python tools/profile_step.py --mode d > gpurun_out/plain_d0.log 2>&1 && \
 
 

@@ -35,7 +35,11 @@ if a.mode == "d":
     GAN_HYPER["iter"] = {"generator": 0, "discriminator": 1}
 elif a.mode == "g":
     GAN_HYPER["iter"] = {"generator": 1, "discriminator": 0}
-for _ in range(a.warm + 1):
-    out = train_gan.train_step(model, opt, batch)
+for _ in range(a.warm):
+    train_gan.train_step(model, opt, batch)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off: only the update below is captured
+out = train_gan.train_step(model, opt, batch)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", {k: (float(v) if v is not None else None) for k, v in out.items() if k != "loss"})
