@@ -218,6 +218,20 @@ int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, i
 int mcgm_split_tf32(const float* x, float* big, float* small, long n, void* stream);
 int mcgm_split_bf16x3(const float* x, void* p1, void* p2, void* p3, long n, void* stream);
 
+/* ---- BatchNorm statistics from the producing conv (src/models/mcgan.py:15,20,56: BatchNorm2d of a tensor that
+ * a Conv2d has just written).  mcgm_conv_fwd_bnstats = mcgm_conv_fwd_ex on bf16 with a linear epilogue (bias,
+ * residual) whose epilogue also accumulates, per CTA warp row, the per-channel sum and sum of squares of the
+ * values it stores: stats_partial [slots][2][Cout] with *stat_slots_host slots (<= 4 * SM count; buffer size from
+ * mcgm_conv_fwd_bnstats_bytes).  mcgm_bn_finalize turns such partials (or mcgm_bn_stats' own) into mean / rstd
+ * and the running statistics, in fp64 and a fixed order — the BN gate then needs no statistics pass over the
+ * tensor.  Supported: Cout = 256. */
+size_t mcgm_conv_fwd_bnstats_bytes(int Cout);
+int mcgm_conv_fwd_bnstats(int kind, const void* x, const void* w, void* out, int N, int H, int W, int Cin, int Cout,
+                          int R, int S, const float* bias, const void* res, int flags, float* stats_partial,
+                          int* stat_slots_host, void* stream);
+int mcgm_bn_finalize(const float* partial, int nblocks, int C, long count, float* mean, float* rstd,
+                     float* running_mean, float* running_var, float momentum, float eps, void* stream);
+
 /* ---- Glow flow step, few-channel part (fp32 NHWC [P = N*H*W, C], C a multiple of 4, C <= 64)
  * front = ActNorm(C) -> InvConv2dLU (src/models/mcglow.py:24-55, 76-116):
  *     y = W (scale * (x + loc)),  W = [C_out][C_in] row-major (calc_weight(), mcglow.py:104-110);

@@ -60,6 +60,11 @@ SIGNATURES = {
                                  c_void_p]),
     "mcgm_pool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mcgm_unpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mcgm_conv_fwd_bnstats_bytes": (c_size_t, [c_int]),
+    "mcgm_conv_fwd_bnstats": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcgm_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                 c_void_p]),
     "mcgm_flow_front_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int,
                                     c_void_p]),
     "mcgm_flow_front_bwd_workspace_bytes": (c_size_t, [c_int]),

@@ -174,6 +174,7 @@ struct ConvFwdParams {
   int words;
   int flags;
   int quad;                                  // 4 consecutive tile pixels never straddle a tile row (TW % 4 == 0)
+  float* stats;                              // STATS kernels: [4 * gridDim][2][Cout] per-warp-row sum / sum of squares
   void* out;
 };
 
@@ -221,6 +222,22 @@ __device__ __forceinline__ void quad_transpose(uint4 (&u)[4], const int lane) {
   }
 }
 
+// Column sums of a 32 x 32 tile held one ROW per lane: after five exchange-and-add steps lane l holds the
+// sum over the 32 rows of column l (31 shuffles instead of 32 x 5 for per-column butterflies).
+__device__ __forceinline__ float warp_column_sums(float (&s)[32], const int lane) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const bool hi = lane & m;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float send = hi ? s[i] : s[i + m];
+      const float keep = hi ? s[i + m] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  return s[0];
+}
+
 // One chunk (CW <= 32 consecutive output channels of one pixel) of the fused epilogue.  Executed by ALL
 // lanes of the warp (quad shuffles inside); `row_ok` only predicates the global accesses of this row.
 //   acc    fp32 bit patterns from TMEM
@@ -231,11 +248,14 @@ __device__ __forceinline__ void quad_transpose(uint4 (&u)[4], const int lane) {
 //          read in place; the fp32 parity pipeline (TF32) reads everything in place.
 //   QUAD   bf16 rows move as quad-transposed 64-byte runs (needs CW == 32 and quads that do not straddle a
 //          tile row: p.quad)
-template <int CW, bool GENERIC_STORE, bool QUAD, typename OutT, bool TF32>
+//   STATS  also return this chunk's per-column sum and sum of squares over the warp's 32 rows (lane l:
+//          column col0 + l) of the values AS STORED (bf16-rounded) — the batch statistics of the BatchNorm that
+//          consumes this tensor (src/models/mcgan.py:15,20,56), so that gate needs no statistics pass of its own
+template <int CW, bool GENERIC_STORE, bool QUAD, bool STATS, typename OutT, bool TF32>
 __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int flags, uint32_t (&acc)[32],
                                                const int pix, const int rpix, const int col0, const bool row_ok,
                                                const float* sbias, const uint32_t mbits, uint4 (&sd)[4],
-                                               const int lane) {
+                                               const int lane, float& col_sum, float& col_sq) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(acc[i]);
@@ -331,6 +351,18 @@ __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int
       }
       o[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if constexpr (STATS) {
+      float t[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack16<__nv_bfloat16>(o[i], t + 8 * i);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = row_ok ? t[i] : 0.0f;
+      float t2[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t2[i] = t[i] * t[i];
+      col_sum = warp_column_sums(t, lane);
+      col_sq = warp_column_sums(t2, lane);
+    }
     quad_transpose(o, lane);
     const uint32_t okb = __ballot_sync(0xffffffffu, row_ok);
     const int base = lane & ~3;
@@ -390,7 +422,7 @@ __device__ __forceinline__ void side_load(const __nv_bfloat16* base, const int p
   }
 }
 
-template <int BN, int MT, typename OutT, bool TF32>
+template <int BN, int MT, typename OutT, bool TF32, bool STATS = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const ConvFwdParams p) {
@@ -512,6 +544,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const __nv_bfloat16* side = TF32 ? nullptr : (res_on ? p.res : ((flags & MCGM_EPI_POSMASK) ? p.aux : nullptr));
     auto tile_loop = [&](auto quad_tag) {
       constexpr bool QUAD = decltype(quad_tag)::value;
+      static_assert(!STATS || (CW == 32 && sizeof(OutT) == 2 && !TF32), "STATS: bf16 output, 32-column chunks");
+      float st_sum[NCH], st_sq[NCH];                           // STATS: per-lane column accumulators (n_tiles == 1)
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) st_sum[k] = st_sq[k] = 0.0f;
       int it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
@@ -551,11 +587,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         };
         auto run = [&](int q, uint32_t (&a)[32], uint4 (&sd)[4], uint32_t mwd) {
           const int j = q / NCH, col = cl0 + (q % NCH) * CW;
-          if (col < p.Cout)                                    // warp-uniform
-            epilogue_chunk<CW, BN == 16, QUAD, OutT, TF32>(p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0],
-                                                           (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
-                                                           (MT == 2 && j) ? valid[MT - 1] : valid[0],
-                                                           sbias + col, mwd, sd, lane);
+          if (col < p.Cout) {                                  // warp-uniform
+            float cs = 0.0f, cq = 0.0f;
+            epilogue_chunk<CW, BN == 16, QUAD, STATS && QUAD, OutT, TF32>(
+                p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0], (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
+                (MT == 2 && j) ? valid[MT - 1] : valid[0], sbias + col, mwd, sd, lane, cs, cq);
+            if constexpr (STATS) {
+              const int ci = q % NCH;
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                st_sum[k] += (k == ci) ? cs : 0.0f;
+                st_sq[k] += (k == ci) ? cq : 0.0f;
+              }
+            }
+          }
         };
         uint32_t acc[2][32];
         uint4 sd[2][4];
@@ -587,8 +632,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
       }
+      if constexpr (STATS) {
+        if (works) {
+          float* sp = p.stats + (size_t)(blockIdx.x * 4 + quad) * 2 * p.Cout + half * HALF + lane;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            sp[k * CW] = st_sum[k];
+            sp[p.Cout + k * CW] = st_sq[k];
+          }
+        }
+      }
     };
-    if constexpr (kQuadOk) {
+    if constexpr (STATS) {
+      tile_loop(std::true_type{});                             // host guarantees p.quad
+    } else if constexpr (kQuadOk) {
       if (p.quad) tile_loop(std::true_type{});
       else tile_loop(std::false_type{});
     } else {
@@ -907,10 +964,10 @@ static bool pick_pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return true;
 }
 
-template <int BN, int MT, typename OutT, bool TF32 = false>
+template <int BN, int MT, typename OutT, bool TF32 = false, bool STATS = false>
 static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParams p, cudaStream_t st) {
   using Cfg = FwdCfg<BN, MT>;
-  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32>;
+  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32, STATS>;
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -1047,7 +1104,8 @@ extern "C" int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int 
 // TF32 (kind::tf32, K = 8 per instruction) — the fp32 parity pipeline; out_dtype must be fp32.
 static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
                          int Cin, int Cout, int R, int S, const float* bias, const void* res, const void* aux,
-                         const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream) {
+                         const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream,
+                         float* stats = nullptr, int* stat_slots_host = nullptr) {
   MCGM_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv_fwd: bad arguments");
   MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "conv_fwd: out_dtype %d unsupported", out_dtype);
   MCGM_CHECK_ARG(in_dtype == MCGM_BF16 || in_dtype == MCGM_F32, "conv_fwd: in_dtype %d unsupported", in_dtype);
@@ -1131,6 +1189,16 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   if (sms <= 0) sms = 148;
   const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles * p.PH > sms);
   p.m_super = m_tiles;           // launch_fwd turns this into ceil(m_tiles / MT)
+  if (stats != nullptr) {
+    // batch statistics of the output for the BatchNorm that consumes it, accumulated by the epilogue
+    if (!(BN == 256 && p.n_tiles == 1 && !tf32 && !f32 && p.quad) || (flags & (MCGM_EPI_RELU | MCGM_EPI_MASK | MCGM_EPI_POSMASK | MCGM_EPI_TANH)))
+      return fail(MCGM_E_UNSUPPORTED, "conv_fwd_bnstats: needs Cout = 256, bf16 operands and output, a linear epilogue and tile rows of >= 4 pixels");
+    MCGM_CHECK_ARG(stat_slots_host, "conv_fwd_bnstats: stat_slots_host is NULL");
+    const long total = (long)m_tiles * p.n_tiles * p.PH;
+    *stat_slots_host = 4 * (int)(total < sms ? total : sms);
+    p.stats = stats;
+    return launch_fwd<256, 1, __nv_bfloat16, false, true>(mx, mw, p, st);
+  }
   switch (BN) {
     case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(mx, mw, p, f32, st) : launch_fwd_t<256, 1>(mx, mw, p, f32, st);
     case 128: return pair ? launch_fwd_t<128, 2>(mx, mw, p, f32, st) : launch_fwd_t<128, 1>(mx, mw, p, f32, st);
@@ -1151,6 +1219,20 @@ extern "C" int mcgm_conv_fwd_ex(int kind, int in_dtype, const void* x, const voi
                                 const void* res, const void* aux, const int32_t* labels, const uint32_t* bits,
                                 int M, int flags, void* stream) {
   return conv_fwd_impl(kind, in_dtype, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
+}
+
+extern "C" size_t mcgm_conv_fwd_bnstats_bytes(int Cout) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  return (size_t)4 * sms * 2 * Cout * sizeof(float);
+}
+
+extern "C" int mcgm_conv_fwd_bnstats(int kind, const void* x, const void* w, void* out, int N, int H, int W, int Cin,
+                                     int Cout, int R, int S, const float* bias, const void* res, int flags,
+                                     float* stats_partial, int* stat_slots_host, void* stream) {
+  MCGM_CHECK_ARG(stats_partial && stat_slots_host, "conv_fwd_bnstats: stats_partial / stat_slots_host are NULL");
+  return conv_fwd_impl(kind, MCGM_BF16, x, w, out, MCGM_BF16, N, H, W, Cin, Cout, R, S, bias, res, nullptr, nullptr, nullptr,
+                       0, flags, stream, stats_partial, stat_slots_host);
 }
 
 static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Cin, int Cout, int R, int S) {

@@ -614,6 +614,16 @@ extern "C" int mcgm_bn_stats(const void* x, int dtype, long P_total, int C, floa
   return 0;
 }
 
+extern "C" int mcgm_bn_finalize(const float* partial, int nblocks, int C, long count, float* mean, float* rstd,
+                                float* running_mean, float* running_var, float momentum, float eps, void* stream) {
+  MCGM_CHECK_ARG(partial && mean && rstd && nblocks > 0 && C > 0 && count > 0, "bn_finalize: bad arguments");
+  MCGM_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must come in pairs");
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, nblocks, C, (double)count, mean, rstd,
+                                                                    running_mean, running_var, momentum, eps);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
 static GateGeom make_geom(int N, int H, int W, int C, int TP) {
   GateGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C;

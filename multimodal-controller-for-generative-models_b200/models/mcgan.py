@@ -130,21 +130,23 @@ def _up2_packs(weight):
     return packs
 
 
-def _conv(x, conv, ctx, res=None, res_up=False, gate=None, premask_dx=False, grad_premasked=False):
+def _conv(x, conv, ctx, res=None, res_up=False, gate=None, premask_dx=False, grad_premasked=False, want_stats=False):
     """tcgen05 conv through ``conv`` (an nn.Conv2d container, possibly spectral-normed: then
     ``ctx.sn[conv]`` holds this forward's [1/sigma | u | v] and the weight is packed as W/sigma)."""
     if hasattr(conv, 'weight_orig'):
         return ops.ConvFn.apply(x, conv.weight_orig, conv.bias, res, res_up, gate, premask_dx, grad_premasked,
                                 None, ctx.sn[conv])
     w = conv.weight
-    return ops.ConvFn.apply(x, w, conv.bias, res, res_up, gate, premask_dx, grad_premasked, _packs(w), None)
+    return ops.ConvFn.apply(x, w, conv.bias, res, res_up, gate, premask_dx, grad_premasked, _packs(w), None, False,
+                            want_stats)
 
 
-def _bn_gate(x, bn, mc, ctx, training, up=False, want_raw=False):
+def _bn_gate(x, bn, mc, ctx, training, up=False, want_raw=False, pre_stats=None):
+    """pre_stats: ops.ConvStats of x from the epilogue of the conv that produced it (training only)."""
     flags = GATE_BN | GATE_RELU | GATE_MASK | (GATE_UP2 if up else 0)
     if training:
         y, raw = ops.GateFn.apply(x, bn.weight, bn.bias, ctx.labels, mc.packed(), flags, bn.running_mean,
-                                  bn.running_var, bn.momentum, bn.eps, want_raw)
+                                  bn.running_var, bn.momentum, bn.eps, want_raw, pre_stats)
         bn.num_batches_tracked += 1
         return y, raw
     # eval: running statistics (inference path; no autograd through the gate)
@@ -176,16 +178,24 @@ class GenResBlock(nn.Module):
         else:
             self.shortcut = nn.Sequential()
 
-    def fused(self, x, ctx):
+    def fused(self, x, ctx, x_stats=None):
+        """x_stats: batch statistics of x from the conv that produced it.  Returns (out, stats of out): every
+        BatchNorm of the generator but the first reads a tensor a conv has just written, and that conv's
+        epilogue accumulates the statistics (no separate pass over the tensor)."""
         if self.stride != 2:
             raise ValueError('Not valid stride (the fused generator block upsamples by 2)')
         t = self.training
-        a, s = _bn_gate(x, self.conv[0].module, self.mc_1, ctx, t, want_raw=True)    # both at LOW resolution
+        # epilogue statistics are OFF by default: with the thread-per-row TMEM layout the column reduction costs
+        # the 256-wide convs more (+2.6 ms / iteration) than the statistics passes it removes (-1.7 ms) — measured,
+        # DESIGN.md §7.  cfg['bn_stats_in_conv'] = True switches them on (parity-tested either way).
+        ws = t and bool(cfg.get('bn_stats_in_conv', False))
+        a, s = _bn_gate(x, self.conv[0].module, self.mc_1, ctx, t, want_raw=True, pre_stats=x_stats)   # LOW resolution
         sc = _conv(s, self.shortcut[2].module, ctx)                      # 1x1 commutes with the upsample
         c1m = self.conv[4].module                                        # Up(2) -> Conv3x3 as a 4-phase 2x2 conv
-        c1 = ops.ConvUp2Fn.apply(a, c1m.weight, c1m.bias, _up2_packs(c1m.weight))
-        h2, _ = _bn_gate(c1, self.conv[5].module, self.mc_2, ctx, t)
-        return _conv(h2, self.conv[8].module, ctx, res=sc, res_up=True)
+        c1 = ops.ConvUp2Fn.apply(a, c1m.weight, c1m.bias, _up2_packs(c1m.weight), ws)
+        h2, _ = _bn_gate(c1, self.conv[5].module, self.mc_2, ctx, t, pre_stats=ops.take_stats())
+        out = _conv(h2, self.conv[8].module, ctx, res=sc, res_up=True, want_stats=ws)
+        return out, ops.take_stats()
 
 
 class Generator(nn.Module):
@@ -211,10 +221,11 @@ class Generator(nn.Module):
         c0 = lin.out_features // 16
         x = F.linear(input, lin.weight, lin.bias)                        # [N, C0*16]  (tiny GEMM, cuBLAS)
         x = x.view(-1, c0, 4, 4).permute(0, 2, 3, 1).to(ops.ACT_DTYPE).contiguous()
+        st = None
         for i in range(n_res):
-            x = self.blocks[i].fused(x, ctx)
+            x, st = self.blocks[i].fused(x, ctx, st)
         bn, mc, conv = self.blocks[n_res].module, self.blocks[n_res + 2], self.blocks[n_res + 3].module
-        h, _ = _bn_gate(x, bn, mc, ctx, self.training)
+        h, _ = _bn_gate(x, bn, mc, ctx, self.training, pre_stats=st)
         img = ops.ThinFromWideFn.apply(h, conv.weight, conv.bias, True)   # 3x3 -> RGB, tanh fused
         return img.permute(0, 3, 1, 2)
 

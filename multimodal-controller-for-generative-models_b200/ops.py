@@ -136,6 +136,67 @@ def bn_stats(x, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
     return mean, rstd
 
 
+class ConvStats:
+    """Per-channel sum / sum-of-squares partials of a tensor, written by the epilogue of the conv that produced
+    it (``conv_fwd_bnstats``): the BatchNorm gate that consumes the tensor finalises them instead of reading
+    the tensor once more for its batch statistics."""
+    __slots__ = ("partial", "slots", "count")
+
+    def __init__(self, partial, slots, count):
+        self.partial, self.slots, self.count = partial, slots, count
+
+
+# statistics of the most recent conv output (set by ConvFn / ConvUp2Fn when asked; consumed by take_stats)
+_last_stats = None
+
+
+def take_stats():
+    global _last_stats
+    st, _last_stats = _last_stats, None
+    return st
+
+
+def stats_supported(x, Cout, res=None):
+    """The epilogue-statistics conv variant exists for bf16 tensors with 256 output channels and rows >= 4 px."""
+    return x.dtype == torch.bfloat16 and Cout == 256 and x.shape[2] >= 4
+
+
+def bn_finalize(stats, C, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
+    """(mean, rstd) + running-stat update from conv-epilogue partials (no pass over the tensor)."""
+    dev = stats.partial.device
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    rstd = torch.empty(C, dtype=torch.float32, device=dev)
+    ev = _prof_begin()
+    _lib.call("mcgm_bn_finalize", stats.partial.data_ptr(), stats.slots, C, stats.count, mean.data_ptr(), rstd.data_ptr(),
+              _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), _stream())
+    _prof_end(ev, "gate", 0, f"bn_finalize slots{stats.slots} C{C}")
+    return mean, rstd
+
+
+def conv_fwd_bnstats(kind, x, w, bias=None, res=None, flags=0):
+    """conv_fwd / conv_fwd_ex (bf16, linear epilogue) that also returns the ConvStats of its output."""
+    import ctypes
+    _check_cuda(x, w, bias, res)
+    N, H, W, Cin = x.shape
+    if kind == CONV_S1:
+        Cout, R, S, Ho, Wo, taps = w.shape[0], w.shape[1], w.shape[2], H, W, w.shape[1] * w.shape[2]
+    elif kind == CONV_PHASE2:
+        Cout, R, S, Ho, Wo, taps = w.shape[1], 0, 0, 2 * H, 2 * W, 9
+    else:
+        raise ValueError("Not valid conv kind for epilogue statistics")
+    out = torch.empty(N, Ho, Wo, Cout, dtype=torch.bfloat16, device=x.device)
+    partial = torch.empty(_lib.query("mcgm_conv_fwd_bnstats_bytes", Cout) // 4, dtype=torch.float32, device=x.device)
+    slots = ctypes.c_int(0)
+    if bias is not None:
+        flags |= EPI_BIAS
+    ev = _prof_begin()
+    _lib.call("mcgm_conv_fwd_bnstats", kind, x.data_ptr(), w.data_ptr(), out.data_ptr(), N, H, W, Cin, Cout, R, S,
+              _ptr(bias), _ptr(res), flags, partial.data_ptr(), ctypes.byref(slots), _stream())
+    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * taps,
+              f"conv+bnstats kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}")
+    return out, ConvStats(partial, slots.value, N * Ho * Wo)
+
+
 def gate_fwd(x, flags, labels=None, packed=None, mean=None, rstd=None, gamma=None, beta=None, want_raw=False):
     _check_cuda(x, labels, mean, rstd, gamma, beta)
     N, H, W, C = x.shape
@@ -478,10 +539,14 @@ class GateFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, labels, packed, flags, running_mean, running_var, momentum, eps, want_raw):
+    def forward(ctx, x, gamma, beta, labels, packed, flags, running_mean, running_var, momentum, eps, want_raw,
+                pre_stats=None):
         mean = rstd = None
         if flags & GATE_BN:
-            mean, rstd = bn_stats(x, running_mean, running_var, momentum, eps)
+            if pre_stats is not None:            # statistics already accumulated by the producing conv's epilogue
+                mean, rstd = bn_finalize(pre_stats, x.shape[-1], running_mean, running_var, momentum, eps)
+            else:
+                mean, rstd = bn_stats(x, running_mean, running_var, momentum, eps)
         y, y_raw = gate_fwd(x, flags, labels, packed, mean, rstd, gamma, beta, want_raw)
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.labels, ctx.packed, ctx.flags, ctx.want_raw = labels, packed, flags, want_raw
@@ -496,13 +561,13 @@ class GateFn(torch.autograd.Function):
         dy = dy.contiguous() if dy is not None else None
         d_raw = d_raw.contiguous() if d_raw is not None else None
         if dy is None and d_raw is None:
-            return (None,) * 11
+            return (None,) * 12
         if dy is None and (ctx.flags & GATE_BN):
             up = 2 if ctx.flags & GATE_UP2 else 1
             N, H, W, C = x.shape
             dy = torch.zeros(N, H * up, W * up, C, dtype=x.dtype, device=x.device)
         dx, dgamma, dbeta = gate_bwd(dy, d_raw, x, ctx.flags, ctx.labels, ctx.packed, mean, rstd, gamma, beta)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class ActNormGateFn(torch.autograd.Function):
@@ -541,7 +606,8 @@ class ConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn, out_f32=False):
+    def forward(ctx, x, w, bias, res, res_up, gate, premask_dx, grad_premasked, packs, sn, out_f32=False,
+                want_stats=False):
         # sn: [1/sigma | u | v] snapshot of a spectral-normed layer (w is then weight_orig)
         f32 = x.dtype == torch.float32           # fp32 parity pipeline (cfg['compute_dtype'] = 'fp32')
         if f32:
@@ -562,7 +628,11 @@ class ConvFn(torch.autograd.Function):
         else:
             if res is not None:
                 flags |= EPI_RES_UP2 if res_up else EPI_RES
-            out = conv_fwd(x, wf, torch.float32 if out_f32 else torch.bfloat16, bias, res, None, labels, packed, flags)
+            global _last_stats
+            if want_stats and gate is None and not out_f32 and stats_supported(x, w.shape[0]):
+                out, _last_stats = conv_fwd_bnstats(CONV_S1, x, wf, bias, res, flags)
+            else:
+                out = conv_fwd(x, wf, torch.float32 if out_f32 else torch.bfloat16, bias, res, None, labels, packed, flags)
         ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn)
         ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
         ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
@@ -601,7 +671,7 @@ class ConvFn(torch.autograd.Function):
                 dw = dw_krsc.permute(0, 3, 1, 2)      # KRSC -> OIHW view
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = pool2(dout, 1.0) if ctx.res_up else dout
-        return dx, dw, db, dres, None, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None, None
 
 
 def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None, dtype=torch.bfloat16):
@@ -680,13 +750,17 @@ class ConvUp2Fn(torch.autograd.Function):
     folded back onto the 3x3 kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, packs):
+    def forward(ctx, x, w, bias, packs, want_stats=False):
         if x.dtype == torch.float32:             # fp32 parity pipeline
             wp, kd = up2_conv_packs(w.detach(), torch.float32)
             out = conv_f32(CONV_PHASE2, x, wp, bias=bias)
         else:
             wp, kd = packs if packs is not None else up2_conv_packs(w.detach())
-            out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
+            global _last_stats
+            if want_stats and stats_supported(x, w.shape[0]):
+                out, _last_stats = conv_fwd_bnstats(CONV_PHASE2, x, wp, bias)
+            else:
+                out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
         ctx.save_for_backward(x)
         ctx.kd, ctx.has_bias, ctx.dev = kd, bias is not None, w.device
         return out
@@ -704,16 +778,27 @@ class ConvUp2Fn(torch.autograd.Function):
                       else conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias))     # [K,4,4,C]
             _, qm = _up2_mats(ctx.dev)
             dw = torch.einsum('xr,ys,kxyc->kcrs', qm, qm, dk)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 _PIDX = ((3, 1), (2, 0))     # kernel index of (phase ph, tap a): p = 3 - 2a - ph
 
 
+_pidx_cache = {}
+
+
+def _pidx_tensor(device):
+    """Device copy of _PIDX, made once per device (a host->device copy is not allowed during graph capture)."""
+    t = _pidx_cache.get(device)
+    if t is None:
+        t = _pidx_cache[device] = torch.tensor(_PIDX, device=device)
+    return t
+
+
 def _phase_weights(w_oc_ic_44):
     """[O, I, 4, 4] (O = output channels of the PHASE conv) -> [4, O, 2, 2, I] with
     out[ph*2+pw, o, a, b, i] = w[o, i, 3-2a-ph, 3-2b-pw]."""
-    idx = torch.tensor(_PIDX, device=w_oc_ic_44.device)
+    idx = _pidx_tensor(w_oc_ic_44.device)
     parts = [w_oc_ic_44[:, :, idx[ph]][:, :, :, idx[pw]] for ph in range(2) for pw in range(2)]   # [O,I,2,2] each
     return torch.stack(parts).permute(0, 1, 3, 4, 2).contiguous()
 

@@ -27,3 +27,51 @@ def train_step(model, optimizer, input, eps=None):
         torch.nn.utils.clip_grad_norm_(model.parameters(), VAE_HYPER["clip"])
     optimizer.step()
     return output
+
+
+class GraphedTrainStep:
+    """``train_step`` of MCVAE / MCGlow captured ONCE into a CUDA graph and replayed per batch.
+
+    A Glow step is ~48 flow steps x ~40 launches forward and as many backward, a VAE step a few hundred
+    launches of 5-50 us kernels: issued eagerly both are bound by the host, not the B200.  The step has
+    static shapes and — with ``optim.FusedAdam`` (device-side step counter and clip coefficient) — never
+    synchronises with the host, so it is captured after a few eager warm-up steps (which also run Glow's
+    data-dependent ActNorm initialisation, build every workspace, packed codebook and TMA descriptor) and
+    replayed with new data copied into static input buffers.  ``noise``: optional static buffer for the
+    injected reparameterisation (VAE) / dequantisation (Glow) noise of parity runs; otherwise the noise is
+    drawn inside the graph (torch's graph-safe Philox stream).  No autograd graph of an earlier eager step on
+    another stream may still be alive (drop the step's output dict first): its AccumulateGrad nodes would tie
+    the capture to that stream.
+    """
+
+    def __init__(self, model, optimizer, example_input, warmup=3, inject_noise=None):
+        if not hasattr(optimizer, "flat"):
+            raise ValueError("Not valid optimizer: graph capture needs optim.FusedAdam (no host sync in the step)")
+        self.img = example_input["img"].detach().clone()
+        self.label = example_input["label"].detach().clone()
+        self.noise = inject_noise.detach().clone() if inject_noise is not None else None
+        self.model, self.optimizer = model, optimizer
+        batch = {"img": self.img, "label": self.label}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_step(model, optimizer, batch, self.noise)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        c0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = train_step(model, optimizer, batch, self.noise)
+        self.native_launches = _lib.launch_count - c0
+
+    def __call__(self, input, noise=None):
+        """input: {'img','label'} on the host (pinned) or the device; returns the output dict of device
+        tensors, overwritten by the next call."""
+        self.img.copy_(input["img"], non_blocking=True)
+        self.label.copy_(input["label"], non_blocking=True)
+        if self.noise is not None and noise is not None:
+            self.noise.copy_(noise, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -560,3 +560,39 @@ def check_flow():
         rows.append((tag + " dnet", rel(nd.grad, nr.grad), F32_TOL))
         rows.append((tag + " dzscale", rel(zd.grad, zr.grad), F32_TOL))
     return rows
+
+
+# ----------------------------------------------------------------------------- BN statistics in the conv epilogue
+def check_conv_bnstats():
+    """mcgm_conv_fwd_bnstats: the output must be bit-identical to the plain conv's, and the finalised
+    epilogue partials must equal the statistics pass over that output (mcgm_bn_stats) — same values
+    (the bf16-rounded stores), different summation order."""
+    from mcgm_b200._lib import CONV_PHASE2, CONV_S1, EPI_BIAS
+    rows = []
+    for (kind, N, H, Cin, res_up) in [(CONV_S1, 4, 16, 256, True), (CONV_S1, 5, 8, 256, False), (CONV_S1, 3, 32, 128, True),
+                                      (CONV_PHASE2, 4, 8, 256, False), (CONV_PHASE2, 5, 4, 256, False)]:
+        g = torch.Generator().manual_seed(31 + H + N)
+        x = torch.randn(N, H, H, Cin, generator=g).to(DEV).to(torch.bfloat16)
+        bias = torch.randn(256, generator=g).to(DEV)
+        if kind == CONV_S1:
+            w = (torch.randn(256, 3, 3, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            res = torch.randn(N, H // 2, H // 2, 256, generator=g).to(DEV).to(torch.bfloat16) if res_up else None
+            fl = EPI_RES_UP2 if res_up else 0
+            ref = ops.conv_fwd(x, w, torch.bfloat16, bias, res, None, None, None, fl)
+            out, st = ops.conv_fwd_bnstats(kind, x, w, bias, res, fl)
+        else:
+            w = (torch.randn(4, 256, 2, 2, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            ref = ops.conv_fwd_ex(kind, x, w, torch.bfloat16, bias)
+            out, st = ops.conv_fwd_bnstats(kind, x, w, bias)
+        tag = f"conv+bnstats kind={kind} N={N} H={H} Cin={Cin}"
+        rows.append((tag + " output identical", float((out.float() != ref.float()).sum()), EXACT))
+        rm0, rv0 = torch.zeros(256, device=DEV), torch.ones(256, device=DEV)
+        rm1, rv1 = rm0.clone(), rv0.clone()
+        mean, rstd = ops.bn_finalize(st, 256, rm0, rv0, 0.1, 1e-5)
+        mref, rref = ops.bn_stats(ref, rm1, rv1, 0.1, 1e-5)
+        rows.append((tag + " count", float(abs(st.count - ref.numel() // 256)), EXACT))
+        rows.append((tag + " mean", rel(mean, mref), F32_TOL))
+        rows.append((tag + " rstd", rel(rstd, rref), F32_TOL))
+        rows.append((tag + " running_mean", rel(rm0, rm1), F32_TOL))
+        rows.append((tag + " running_var", rel(rv0, rv1), F32_TOL))
+    return rows

@@ -172,6 +172,42 @@ def test_config1_full_width_gradients_vs_oracle():
     assert errs[len(errs) // 2][0] < GRAD_MEDIAN_TOL
 
 
+def test_bn_stats_in_conv_epilogue_equals_stats_pass():
+    """cfg['bn_stats_in_conv']: the generator's BatchNorm statistics accumulated by the producing conv's
+    epilogue give the same image, running statistics and gradients as the separate statistics pass
+    (same stored values, different summation order)."""
+    from mcgm_b200 import cfg
+    case = {"data_name": "CIFAR10", "classes": 10, "seed": 0}
+    model = build_model(case, device="cuda").to("cuda")
+    model.train(True)
+    g = torch.Generator().manual_seed(3)
+    label, z = torch.randint(0, 10, (16,), generator=g).cuda(), torch.randn(16, 128, generator=g).cuda()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    outs = []
+    for flag in (False, True):
+        model.load_state_dict(sd0)
+        model.zero_grad()
+        cfg["bn_stats_in_conv"] = flag
+        try:
+            img = model.generate(label, z)
+            img.square().mean().backward()
+        finally:
+            cfg["bn_stats_in_conv"] = False
+        outs.append((img.detach().float().cpu(), {k: v.clone() for k, v in model.state_dict().items()},
+                     {k: p.grad.float().cpu().clone() for k, p in model.generator.named_parameters()}))
+    (img_a, sd_a, gr_a), (img_b, sd_b, gr_b) = outs
+    assert rel_err(img_b, img_a) < 2e-3
+    for k in sd_a:
+        if "running_" in k:
+            assert rel_err(sd_b[k].float().cpu(), sd_a[k].float().cpu()) < 1e-4, k
+    # conv biases that feed a BatchNorm have an analytically zero gradient (pure rounding noise): skip them
+    worst = max((rel_err(gr_b[k], gr_a[k]), k) for k in gr_a
+                if float(gr_a[k].norm()) > 1e-6 and not (k.endswith(".bias") and ".conv." in k and "module" in k and gr_a[k].dim() == 1
+                                                        and "blocks" in k and ("conv.4." in k or "conv.8." in k or "shortcut" in k)))
+    print("bn_stats_in_conv worst gradient difference:", worst)
+    assert worst[0] < 2e-2, worst
+
+
 def test_graph_replay_equals_eager(golden):
     """The CUDA-graph captured iteration is the same computation as the eager one: from identical
     weights, optimiser state, data and injected noise both must land on the same parameters."""

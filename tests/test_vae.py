@@ -101,3 +101,30 @@ def test_vae_train_step_matches_golden(golden):
     with torch.no_grad():
         gen = model.generate(arr["label"].cuda(), arr["eps"].cuda())
     assert tuple(gen.shape) == (16, 3, 32, 32) and float(gen.abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_vae_graph_replay_equals_eager(golden):
+    """train_vae.GraphedTrainStep (CUDA-graph replay, FusedAdam with the clip folded in) is the same
+    computation as the eager step: same weights, data and injected noise -> same losses and parameters."""
+    import copy
+    from mcgm_b200 import train_vae
+    arr = load_arrays("vae_full")
+    m_e = _build("cuda").to("cuda")
+    m_g = copy.deepcopy(m_e)
+    m_e.train(True)
+    m_g.train(True)
+    inp = {"img": arr["img"].cuda(), "label": arr["label"].cuda()}
+    eps = arr["eps"].cuda()
+    opt_g = train_vae.make_optimizer(m_g)
+    graphed = train_vae.GraphedTrainStep(m_g, opt_g, inp, warmup=1, inject_noise=eps)
+    m_g.load_state_dict(m_e.state_dict())            # warm-up + capture already trained m_g: restart both
+    opt_g.reset_state()
+    opt_e = train_vae.make_optimizer(m_e)
+    for _ in range(2):
+        out_e = train_vae.train_step(m_e, opt_e, inp, eps)
+        out_g = graphed(inp, eps)
+    assert abs(float(out_e["loss"]) - float(out_g["loss"])) < 1e-5
+    sd_e, sd_g = m_e.state_dict(), m_g.state_dict()
+    worst = max(rel_err(sd_g[k].float().cpu(), sd_e[k].float().cpu()) for k in sd_e if sd_e[k].is_floating_point())
+    assert worst < 1e-5, worst
