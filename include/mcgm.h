@@ -144,6 +144,17 @@ size_t mcgm_sn_weight_bwd_workspace_bytes(void);
 int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const float* W_oihw,
                        const float* sn_state, int K, int C, int R, int S, float* dW_oihw,
                        void* workspace, void* stream);
+
+/* Batched form for one whole backward pass (n <= 32 items; the *_host arrays are HOST arrays of device pointers /
+ * sizes, read during the call): item i is (dwbar_i, row_stride_i, krsc_i, W_i, state_i, K_i, C_i, R_i*S_i) as in
+ * mcgm_sn_weight_bwd, and its result is ADDED to grad_i (fp32 OIHW, the parameter's gradient).  Items that share
+ * grad_i (the real- and fake-batch passes of one layer) are applied by the same threads in order: two launches in
+ * total, deterministic. */
+size_t mcgm_sn_weight_bwd_batched_workspace_bytes(void);
+int mcgm_sn_weight_bwd_batched(int n, const float* const* dwbar_host, const long* row_stride_host, const int* krsc_host,
+                               const float* const* W_host, const float* const* state_host, const int* K_host,
+                               const int* C_host, const int* RS_host, float* const* grad_host, void* workspace,
+                               void* stream);
 /* bf16 [K][row_stride] <- W[k,c,r,s] * inv_sigma with columns in (r,s,c) order, zero padded: the
  * weight matrix of the im2col'd thin convolution (row_stride = 64). */
 int mcgm_pack_weight_padded(const float* w_oihw, int K, int C, int R, int S, const float* inv_sigma,

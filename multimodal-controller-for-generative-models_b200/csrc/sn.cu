@@ -165,6 +165,75 @@ sn_bwd_apply_kernel(const float* __restrict__ dwbar, long row_stride, int krsc, 
   }
 }
 
+// ---- batched form: every spectral-normed layer of one backward pass in TWO launches ---------------
+// A D update runs D twice (real / fake batch) with different (sigma, u, v) snapshots: 22 items, which as
+// per-layer launches were 44 kernels of ~150 k elements each (launch-bound: 6 % of a D update).  Items are
+// grouped by the parameter they belong to; a group's items are applied by the same threads, one after the
+// other, and ADDED to the parameter's gradient (grad += dW: the AccumulateGrad pass is fused away too).
+static constexpr int kSnMaxItems = 32;
+static constexpr int kSnMaxGroupItems = 4;
+static constexpr int kSnBatchBlocks = 32;     // dot-product blocks per item / apply blocks per group
+
+struct SnBwdBatch {
+  const float* dwbar[kSnMaxItems];
+  const float* W[kSnMaxItems];
+  const float* st[kSnMaxItems];
+  long row_stride[kSnMaxItems];
+  int krsc[kSnMaxItems], K[kSnMaxItems], C[kSnMaxItems], RS[kSnMaxItems];
+  float* grad[kSnMaxItems];                   // per group
+  int group_items[kSnMaxItems][kSnMaxGroupItems];
+  int group_n[kSnMaxItems];
+};
+
+__global__ void __launch_bounds__(kSnBwdThreads)
+sn_bwd_dot_batched_kernel(const SnBwdBatch b, float* __restrict__ partial) {
+  __shared__ float red[40];
+  const int it = blockIdx.y;
+  const int C = b.C[it], RS = b.RS[it], CRS = C * RS;
+  const long total = (long)b.K[it] * CRS;
+  const float* __restrict__ dw = b.dwbar[it];
+  const float* __restrict__ W = b.W[it];
+  float acc = 0.0f;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x)
+    acc = fmaf(dw[sn_src_index(o, CRS, C, RS, b.row_stride[it], b.krsc[it])], W[o], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[it * kSnBatchBlocks + blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kSnBwdThreads)
+sn_bwd_apply_batched_kernel(const SnBwdBatch b, const float* __restrict__ partial) {
+  const int g = blockIdx.y, n = b.group_n[g];
+  const int i0 = b.group_items[g][0];
+  const int K = b.K[i0], C = b.C[i0], RS = b.RS[i0], CRS = C * RS;
+  const long total = (long)K * CRS;
+  float s[kSnMaxGroupItems], inv[kSnMaxGroupItems];
+#pragma unroll
+  for (int q = 0; q < kSnMaxGroupItems; ++q) {
+    s[q] = 0.0f; inv[q] = 0.0f;
+    if (q < n) {
+      const int it = b.group_items[g][q];
+      float a = 0.0f;
+      for (int i = 0; i < kSnBatchBlocks; ++i) a += partial[it * kSnBatchBlocks + i];
+      inv[q] = b.st[it][0];
+      s[q] = a * inv[q];
+    }
+  }
+  float* __restrict__ grad = b.grad[g];
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(o / CRS), rem = (int)(o - (long)k * CRS);
+    float acc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kSnMaxGroupItems; ++q) {
+      if (q < n) {
+        const int it = b.group_items[g][q];
+        const float* st = b.st[it];
+        acc += (b.dwbar[it][sn_src_index(o, CRS, C, RS, b.row_stride[it], b.krsc[it])] - s[q] * st[1 + k] * st[1 + K + rem]) * inv[q];
+      }
+    }
+    grad[o] += acc;
+  }
+}
+
 // bf16 [K][row_stride] <- W[k,c,r,s] * inv_sigma in (r,s,c) order, zero padded (im2col GEMM weights)
 __global__ void pack_weight_padded_kernel(const float* __restrict__ w, int K, int C, int R, int S,
                                           const float* __restrict__ inv_sigma, __nv_bfloat16* __restrict__ out,
@@ -229,6 +298,38 @@ extern "C" int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc,
   sn_bwd_dot_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, W_oihw, K, C, R * S, partial);
   MCGM_LAUNCH_CHECK();
   sn_bwd_apply_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, sn_state, partial, blocks, K, C, R * S, dW_oihw);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t mcgm_sn_weight_bwd_batched_workspace_bytes(void) { return (size_t)kSnMaxItems * kSnBatchBlocks * sizeof(float); }
+
+extern "C" int mcgm_sn_weight_bwd_batched(int n, const float* const* dwbar_host, const long* row_stride_host,
+                                          const int* krsc_host, const float* const* W_host,
+                                          const float* const* state_host, const int* K_host, const int* C_host,
+                                          const int* RS_host, float* const* grad_host, void* workspace, void* stream) {
+  MCGM_CHECK_ARG(n > 0 && n <= kSnMaxItems, "sn_weight_bwd_batched: 1..%d items per call (got %d)", kSnMaxItems, n);
+  MCGM_CHECK_ARG(dwbar_host && row_stride_host && krsc_host && W_host && state_host && K_host && C_host && RS_host && grad_host && workspace,
+                 "sn_weight_bwd_batched: bad arguments");
+  SnBwdBatch b{};
+  int groups = 0;
+  for (int i = 0; i < n; ++i) {
+    MCGM_CHECK_ARG(dwbar_host[i] && W_host[i] && state_host[i] && grad_host[i] && K_host[i] > 0 && C_host[i] > 0 && RS_host[i] > 0 &&
+                       row_stride_host[i] >= (long)C_host[i] * RS_host[i], "sn_weight_bwd_batched: item %d invalid", i);
+    b.dwbar[i] = dwbar_host[i]; b.W[i] = W_host[i]; b.st[i] = state_host[i]; b.row_stride[i] = row_stride_host[i];
+    b.krsc[i] = krsc_host[i]; b.K[i] = K_host[i]; b.C[i] = C_host[i]; b.RS[i] = RS_host[i];
+    int g = 0;
+    while (g < groups && b.grad[g] != grad_host[i]) ++g;
+    if (g == groups) { b.grad[g] = grad_host[i]; b.group_n[g] = 0; ++groups; }
+    else MCGM_CHECK_ARG(b.K[b.group_items[g][0]] == K_host[i] && b.C[b.group_items[g][0]] == C_host[i] && b.RS[b.group_items[g][0]] == RS_host[i],
+                        "sn_weight_bwd_batched: items of one gradient differ in shape");
+    MCGM_CHECK_ARG(b.group_n[g] < kSnMaxGroupItems, "sn_weight_bwd_batched: more than %d items for one gradient", kSnMaxGroupItems);
+    b.group_items[g][b.group_n[g]++] = i;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  sn_bwd_dot_batched_kernel<<<dim3(kSnBatchBlocks, n), kSnBwdThreads, 0, st>>>(b, (float*)workspace);
+  MCGM_LAUNCH_CHECK();
+  sn_bwd_apply_batched_kernel<<<dim3(kSnBatchBlocks, groups), kSnBwdThreads, 0, st>>>(b, (const float*)workspace);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

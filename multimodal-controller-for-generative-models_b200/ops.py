@@ -304,9 +304,51 @@ class SNBatch:
         return {m: state[o:o + 1 + k + crs] for m, o, (k, crs) in zip(self.modules, self.offs, self.shapes)}
 
 
+# Deferred, batched spectral-norm backward.  With SN_DEFER set (train_gan's update functions do), the
+# weight-gradient paths of spectral-normed layers do not launch their own two small kernels: they queue
+# (dW_bar, layout, weight_orig, state) and one pair of launches at the END of the backward pass handles every
+# layer and adds the results to ``weight_orig.grad`` in place (autograd sees ``None`` for those inputs).  Only
+# valid for ``loss.backward()`` on leaf parameters — which is what the training step does.
+SN_DEFER = False
+_sn_pending = []
+
+
+def _sn_flush():
+    import ctypes as c
+    items, _sn_pending[:] = list(_sn_pending), []
+    if not items:
+        return
+    dev = items[0][3].device
+    for start in range(0, len(items), 32):
+        chunk = items[start:start + 32]
+        n = len(chunk)
+        grads = []
+        for (_, _, _, w, _) in chunk:
+            if w.grad is None:
+                w.grad = torch.zeros_like(w)
+            if not w.grad.is_contiguous():
+                raise ValueError("Not valid gradient layout: spectral-normed weights need contiguous .grad")
+            grads.append(w.grad)
+        shp = [(w.shape if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1)) for (_, _, _, w, _) in chunk]
+        ws = _workspace("sn_bwd_batched", _lib.query("mcgm_sn_weight_bwd_batched_workspace_bytes"), dev)
+        _lib.call("mcgm_sn_weight_bwd_batched", n,
+                  (c.c_void_p * n)(*[it[0].data_ptr() for it in chunk]), (c.c_long * n)(*[it[1] for it in chunk]),
+                  (c.c_int * n)(*[int(it[2]) for it in chunk]), (c.c_void_p * n)(*[it[3].data_ptr() for it in chunk]),
+                  (c.c_void_p * n)(*[it[4].data_ptr() for it in chunk]), (c.c_int * n)(*[s_[0] for s_ in shp]),
+                  (c.c_int * n)(*[s_[1] for s_ in shp]), (c.c_int * n)(*[s_[2] * s_[3] for s_ in shp]),
+                  (c.c_void_p * n)(*[g.data_ptr() for g in grads]), ws.data_ptr(), _stream())
+        _lib.launch_count += 1
+
+
 def sn_weight_bwd(dwbar, row_stride, krsc, w, state):
-    """dW (OIHW, fp32) = (dW_bar - <dW_bar, W_bar> u v^T) / sigma."""
+    """dW (OIHW, fp32) = (dW_bar - <dW_bar, W_bar> u v^T) / sigma.  With SN_DEFER: queued for the batched
+    end-of-backward launch (returns None: the result goes straight into ``w.grad``)."""
     _check_cuda(w, state)
+    if SN_DEFER and w.is_leaf and w.requires_grad:
+        if not _sn_pending:
+            torch.autograd.Variable._execution_engine.queue_callback(_sn_flush)
+        _sn_pending.append((dwbar, row_stride, krsc, w, state))
+        return None
     K, C, R, S = w.shape if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1)
     dw = torch.empty_like(w)
     ws = _workspace("sn_bwd", _lib.query("mcgm_sn_weight_bwd_workspace_bytes"), w.device)

@@ -123,12 +123,17 @@ def hinge_d(d_real, d_fake):
 def d_forward_backward(model, img, label, z):
     """Forward + backward of one D update (src/train_gan.py:143-157); returns the hinge loss.
     G(z) is detached by the reference (:148), so the generator runs without an autograd tape."""
+    from . import ops
     d_x = model.discriminate(img, label)
     with torch.no_grad():
         generated = model.generate(label, z)
     d_g = model.discriminate(generated, label)
     d_loss = hinge_d(d_x, d_g)
-    d_loss.backward()
+    ops.SN_DEFER = True            # all 22 spectral-norm weight backwards of this pass: two launches at its end
+    try:
+        d_loss.backward()
+    finally:
+        ops.SN_DEFER = False
     return d_loss
 
 
