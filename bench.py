@@ -30,11 +30,12 @@ WORKLOAD = "MCGAN CIFAR10-shaped 32x32x3, 10 modes, control 0.5, one iteration =
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm")
+    ap.add_argument("--ref-batch", type=int, default=64, help="images per step of the CPU reference arm (BASELINE configs[0])")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="time budget of the CPU reference arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
@@ -90,9 +91,10 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference(batch, steps, warmup, threads=None):
+def cpu_reference(batch, steps, warmup, threads=None, budget_s=None):
     """The reference algorithm (oracle port: same torch CPU ops as the reference modules) on the
-    host cores: `steps` iterations of 5D+1G at `batch` images.  Returns (img/s, cores, s/iter)."""
+    host cores: up to `steps` iterations of 5D+1G at `batch` images (fewer if `budget_s` would be exceeded,
+    judged from the first timed iteration).  Returns (img/s, cores, s/iter, iterations timed)."""
     import torch
     from mcgm_b200 import cfg, models, process_control
     from oracle import mcgan_oracle as O
@@ -108,15 +110,19 @@ def cpu_reference(batch, steps, warmup, threads=None):
     img = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
     label = torch.randint(0, 10, (batch,), generator=g)
     times = []
-    for i in range(warmup + steps):
+    i = 0
+    while i < warmup + steps:
         zs = [torch.randn(batch, 128, generator=g) for _ in range(6)]
         t0 = time.perf_counter()
         O.train_iteration(sd, opt, img, label, zs, 10, [2, 1, 1])
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+            if budget_s is not None and sum(times) + dt > budget_s:
+                break
+        i += 1
     per = sum(times) / len(times)
-    return batch / per, torch.get_num_threads(), per
+    return batch / per, torch.get_num_threads(), per, len(times)
 
 
 def run_reference(args):
@@ -124,13 +130,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    value, cores, per = cpu_reference(args.ref_batch, steps, warmup)
-    sample = (f"{steps} iterations (5D+1G) at batch {args.ref_batch} after {warmup} warm-up, oracle port of the "
-              f"reference modules (torch CPU fp32 ops), {cores} threads")
+    value, cores, per, done = cpu_reference(args.ref_batch, steps, warmup, budget_s=args.ref_seconds)
+    sample = (f"{done} iterations (5D+1G) at batch {args.ref_batch} (BASELINE configs[0]) after {warmup} warm-up, oracle port "
+              f"of the reference modules (the reference's own torch CPU fp32 ops), {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "steps": done, "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": args.ref_batch, "parallelism": "cpu"},
+            "config": {"workload": WORKLOAD, "global_batch": args.ref_batch, "parallelism": "cpu",
+                       "sample": "bounded sample of the workload: same network and schedule, batch 64 per step"},
             "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -244,47 +251,67 @@ def run_native(args):
                 peaks.update(json.load(f)); peaks["_src"] = "measured"
         except Exception:
             pass
+        # one untimed eager iteration first: it grows the caching allocator to the eager working set (the timed
+        # runs above lived in the CUDA graph's private pool), so the measured pass below issues no cudaMalloc
+        train_gan.train_step(model, opt, {"img": dev_img[0], "label": dev_lab[0]}, reducers=reducers)
+        torch.cuda.synchronize()
         ops.PROFILE = {}
         # eager (un-graphed) iteration so that CUDA events can bracket each native call.  Eager issue is
         # host-bound (the GPU would idle between launches and the idle time would land inside the event
         # pairs of the small kernels), so the stream is first held back by a spin kernel long enough for the
         # host to enqueue the whole iteration: the events then see back-to-back device execution.
-        torch.cuda._sleep(int(0.12 * 1.9e9))
+        torch.cuda._sleep(int(0.25 * 1.9e9))
         train_gan.train_step(model, opt, {"img": dev_img[0], "label": dev_lab[0]}, reducers=reducers)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
 
-        def agg(tag):
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                ncu_traffic = json.load(f)            # per-launch DRAM bytes of the dominant shapes (ncu --set full)
+        except Exception:
+            ncu_traffic = {}
+        step_s = ms / args.steps * 1e-3
+
+        def agg(tag, scale):
+            """-> (launches, seconds, work, top shapes) of one kernel family in the profiled iteration."""
             recs = prof.get(tag, [])
             t = sum(r[0].elapsed_time(r[1]) for r in recs) * 1e-3
-            return len(recs), t, sum(r[2] for r in recs)
-        n, t, fl = agg("conv")
-        if n:
-            peak = peaks["bf16_tflops_sustained"]
-            roof = {"kernel": "conv_fwd_kernel (tcgen05 implicit GEMM; forward + dgrad launches)", "bound": "tensor",
-                    "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak,
-                    "traffic": None, "launches": n, "avg_us": t / n * 1e6, "share_of_step": t / (ms / args.steps * 1e-3),
-                    "peak_source": peaks["_src"] + " (cuBLAS bf16 sustained)"}
-        n, t, fl = agg("wgrad")
-        if n:
-            peak = peaks["bf16_tflops_sustained"]
-            roof_wgrad = {"kernel": "conv_wgrad_kernel (+split-K reduce, bias-grad)", "bound": "tensor",
-                          "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak,
-                          "launches": n, "avg_us": t / n * 1e6, "share_of_step": t / (ms / args.steps * 1e-3)}
-        n, t, by = agg("gate")
-        if n:
-            peak = peaks["hbm_gbs"]
-            roof_gate = {"kernel": "MC gate kernels (bn_partial, gate_fwd, gate_bwd_reduce/apply)", "bound": "hbm",
-                         "achieved": by / t / 1e9, "peak": peak, "unit": "GB/s", "frac": by / t / 1e9 / peak,
-                         "traffic": None, "launches": n, "avg_us": t / n * 1e6,
-                         "share_of_step": t / (ms / args.steps * 1e-3), "peak_source": peaks["_src"] + " (copy)"}
+            shapes = {}
+            for r in recs:
+                e = shapes.setdefault(r[3], [0, 0.0, 0.0])
+                e[0] += 1; e[1] += r[0].elapsed_time(r[1]) * 1e-3; e[2] += r[2]
+            top = []
+            for desc, (n, ts, w) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:3]:
+                tr = ncu_traffic.get(desc)
+                top.append({"shape": desc, "launches": n, "avg_us": ts / n * 1e6, "achieved": w / ts / scale,
+                            "share_of_step": ts / step_s,
+                            "traffic": (tr["dram_read_bytes"] + tr["dram_write_bytes"]) if tr else None,
+                            "ncu_tensor_pipe_active_pct": tr["tensor_pipe_active_pct"] if tr else None})
+            return len(recs), t, sum(r[2] for r in recs), top
+
+        def roof_obj(kernel, bound, tag, peak, unit, scale, src):
+            n, t, work, top = agg(tag, scale)
+            if not n:
+                return None
+            return {"kernel": kernel, "bound": bound, "achieved": work / t / scale, "peak": peak, "unit": unit,
+                    "frac": work / t / scale / peak,
+                    # DRAM bytes of ONE launch of the family's top shape (profiles/r01_traffic.json, ncu --set full)
+                    "traffic": top[0]["traffic"] if top else None, "traffic_shape": top[0]["shape"] if top else None,
+                    "launches": n, "avg_us": t / n * 1e6, "share_of_step": t / step_s, "peak_source": src,
+                    "top_shapes": top}
+        roof = roof_obj("conv_fwd_kernel (tcgen05 implicit GEMM; forward + dgrad launches)", "tensor", "conv",
+                        peaks["bf16_tflops_sustained"], "TFLOP/s", 1e12, peaks["_src"] + " (cuBLAS bf16 sustained)")
+        roof_wgrad = roof_obj("conv_wgrad_kernel (+split-K reduce, bias-grad)", "tensor", "wgrad",
+                              peaks["bf16_tflops_sustained"], "TFLOP/s", 1e12, peaks["_src"] + " (cuBLAS bf16 sustained)")
+        roof_gate = roof_obj("MC gate kernels (bn_partial/finalize, gate_fwd, gate_bwd_reduce/apply)", "hbm", "gate",
+                             peaks["hbm_gbs"], "GB/s", 1e9, peaks["_src"] + " (copy)")
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, per = cpu_reference(8, 2, 1)
+        v, cores, per, done = cpu_reference(64, 2, 1, budget_s=25.0)
         cpu_base = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
-                    "sample": f"2 iterations (5D+1G) at batch 8 after 1 warm-up ({per:.2f} s/iteration), oracle port "
-                              f"of the reference modules (torch CPU fp32)"}
+                    "sample": f"{done} iteration(s) (5D+1G) at batch 64 (BASELINE configs[0]) after 1 warm-up "
+                              f"({per:.2f} s/iteration), oracle port of the reference modules (torch CPU fp32)"}
 
     if rank == 0:
         per = ms / args.steps
@@ -298,7 +325,7 @@ def run_native(args):
                                        "CUDA graph per D/G forward+backward, NCCL all-reduce + Adam between graphs")
                                       if use_graph else "eager, bucketed all-reduce overlapped with backward"),
                            "l2": "no flush needed: each step streams >10 GB of activations (>> 126 MB L2)",
-                           "kernel_profile": "one extra eager iteration after the timed region behind a 120 ms spin kernel (no host-induced gaps), CUDA events per native call"},
+                           "kernel_profile": "one extra eager iteration after the timed region after an untimed one, behind a 250 ms spin kernel (no host-induced gaps), CUDA events per native call"},
                 "e2e": {"value": B * world / (ms_e2e / args.steps * 1e-3), "unit": "img/s",
                         "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 + B * 8, "d2h_bytes_per_step": 12,
                         "ms_per_step": ms_e2e / args.steps, "loss_D": loss_host[1], "loss_G": loss_host[2]},

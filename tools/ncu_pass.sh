@@ -8,7 +8,7 @@ timeout 300 python tools/profile_step.py --mode d --warm 1 > gpurun_out/plain_d.
 $NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_d.csv python tools/profile_step.py --mode d --warm 1 > gpurun_out/ncu_d.log 2>&1
 timeout 300 python tools/profile_step.py --mode g --warm 1 > gpurun_out/plain_g.log 2>&1 && \
 $NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_g.csv python tools/profile_step.py --mode g --warm 1 > gpurun_out/ncu_g.log 2>&1
-timeout 300 python tools/profile_step.py --mode d > gpurun_out/plain_d0.log 2>&1 && \
+timeout 300 python tools/profile_step.py --mode d > gpurun_out/plain_d0.log 2>&1
 
 
 $NCU --set full --import-source on -k regex:"gate_fwd_kernel|bn_partial_kernel" -s 12 -c 6 -o gpurun_out/prof_gate_fwd python tools/profile_step.py --mode d > gpurun_out/ncu_full2.log 2>&1

@@ -83,6 +83,39 @@ for name, title in (("prof_conv_fwd.ncu-rep", "`--set full`: conv_fwd_kernel, ge
     p = os.path.join(SRC, name)
     if os.path.exists(p):
         parts.append(full_table(p, title))
+
+# per-launch DRAM traffic of the dominant shapes (bench.py attaches it to its roofline objects):
+# (report, index of the launch inside the report) -> shape descriptor used by ops.PROFILE / bench.py
+TRAFFIC = {"conv 512x32x32 256->256 k3 f0x5 bf16": ("prof_conv_fwd.ncu-rep", 1),
+           "conv_ex kind2 512x16x16 256->256 f0x1": ("prof_conv_fwd.ncu-rep", 0),
+           "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", 2),
+           "gate_fwd 512x32x32x256 f0xb raw0": ("prof_gate_fwd.ncu-rep", 3),
+           "bn_stats P524288 C256": ("prof_gate_fwd.ncu-rep", 2),
+           "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", 0)}
+import json
+traffic = {}
+for desc, (rep, idx) in TRAFFIC.items():
+    pth = os.path.join(SRC, rep)
+    if not os.path.exists(pth):
+        continue
+    raw = subprocess.run(["ncu", "-i", pth, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(raw)))
+    if len(rd) < 3 + idx:
+        continue
+    hdr, units, row = rd[0], rd[1], rd[2 + idx]
+
+    def val(m):
+        i = hdr.index(m)
+        v, u = float(row[i].replace(",", "")), units[i].lower()
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9,
+                    "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}.get(u, 1.0)
+    traffic[desc] = {"kernel": row[hdr.index("Kernel Name")][:60], "ncu_duration_us": val("gpu__time_duration.sum") * 1e6,
+                     "dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
+                     "tensor_pipe_active_pct": float(row[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]),
+                     "source": f"{rep} launch {idx}, ncu --set full --clock-control none"}
+with open(os.path.join(OUT, f"{tag}_traffic.json"), "w") as f:
+    json.dump(traffic, f, indent=1)
+print("wrote", os.path.join(OUT, f"{tag}_traffic.json"))
 with open(os.path.join(OUT, f"{tag}_ncu_summary.md"), "w") as f:
     f.write("\n".join(parts))
 print("wrote", os.path.join(OUT, f"{tag}_ncu_summary.md"))
