@@ -222,6 +222,22 @@ int mcgm_thin_im2col(const float* thin, void* U, int out_dtype, int N, int H, in
 int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int H, int W, int Ct, int R, int S,
                      const float* bias, int flags, void* stream);
 
+/* ---- thin convolutions WITHOUT an im2col buffer: Conv2d(Ct<=4 -> Cout, RxS in {1x1, 3x3}, stride 1, same padding)
+ * on an fp32 NHWC image (src/models/mcgan.py:77-79 Conv2d(3,128,3,1,1) -> ReLU -> MC, :87 Conv2d(3,128,1,1,0)).
+ * The patch matrix (<= 32 columns, k = (r*S + s)*Ct + j) lives in shared memory only; warp-level bf16 MMAs with
+ * fp32 accumulation; the wide tensor is written (forward) / read (weight gradient) exactly once.
+ *   w_bf16: [Cout][w_row_stride] bf16, first R*S*Ct columns of a row = the filter in (r,s,c) order
+ *           (mcgm_pack_weight_padded with row_stride >= 32), the rest zero.
+ *   forward epilogue: + bias, ReLU (relu != 0), x codebook[label[n], c] (labels/bits non-NULL), bf16 NHWC out.
+ *   wgrad: dwm fp32 [Cout][32]: columns < R*S*Ct = dW in (r,s,c) order, column R*S*Ct = dbias (the patch matrix
+ *          carries a column of ones), remaining columns zero.  Deterministic two-level reduction. */
+int mcgm_thin_conv_fwd(const float* img, const void* w_bf16, int w_row_stride, const float* bias,
+                       const int32_t* labels, const uint32_t* bits, int M, int relu, void* out_bf16, int N, int H,
+                       int W, int Ct, int R, int S, int Cout, void* stream);
+size_t mcgm_thin_conv_wgrad_workspace_bytes(int Cout);
+int mcgm_thin_conv_wgrad(const float* img, const void* dy_bf16, float* dwm, int N, int H, int W, int Ct, int R, int S,
+                         int Cout, void* workspace, void* stream);
+
 /* ---- operand splitting for the fp32 parity pipeline (cfg['compute_dtype'] = 'fp32'):
  *   split_tf32   : x = big + small (+ O(2^-21 |x|)), both exactly TF32-representable — three
  *                  kind::tf32 convolutions big*big + big*small + small*big recover an fp32 product

@@ -57,6 +57,11 @@ SIGNATURES = {
                                 c_int, c_int, c_void_p, c_void_p]),
     "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "mcgm_thin_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcgm_thin_conv_wgrad_workspace_bytes": (c_size_t, [c_int]),
+    "mcgm_thin_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
     "mcgm_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "mcgm_split_bf16x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "mcgm_thin_col2im": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "reduce.cuh"
 #include "umma.cuh"
 
 namespace mcgm {
@@ -861,43 +862,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 // split, lane w of a column sums splits w, w+8, ... with four loads in flight, and the eight lane sums are
 // combined through shared memory in lane order — a fixed order, hence deterministic.  (One thread per output
 // walking all splits was a chain of up to 148 dependent L2 round trips on 8..144 blocks: 13-16 us a call.)
-static constexpr int kRedLanes = 8;
-
-template <typename V>
-__device__ __forceinline__ V red_zero();
-template <> __device__ __forceinline__ float4 red_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-template <> __device__ __forceinline__ float red_zero<float>() { return 0.f; }
-__device__ __forceinline__ void red_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-__device__ __forceinline__ void red_add(float& a, const float& b) { a += b; }
-
-template <typename V>
-__device__ __forceinline__ void reduce_columns(const V* __restrict__ src, int rows, size_t row_stride, size_t n,
-                                               size_t i0, V* __restrict__ dst, V (*sm)[32]) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t i = i0 + lane;
-  V a = red_zero<V>();
-  if (i < n) {
-    int s = w;
-    for (; s + 3 * kRedLanes < rows; s += 4 * kRedLanes) {
-      V b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) b[u] = src[(size_t)(s + u * kRedLanes) * row_stride + i];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) red_add(a, b[u]);
-    }
-    for (; s < rows; s += kRedLanes) red_add(a, src[(size_t)s * row_stride + i]);
-  }
-  sm[w][lane] = a;
-  __syncthreads();
-  if (w == 0 && i < n) {
-    V t = sm[0][lane];
-#pragma unroll
-    for (int k = 1; k < kRedLanes; ++k) red_add(t, sm[k][lane]);
-    dst[i] = t;
-  }
-  __syncthreads();
-}
-
 __global__ void __launch_bounds__(32 * kRedLanes)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/, float* __restrict__ dw,
                     const float* __restrict__ bias_partial, int bias_rows, int Cout, float* __restrict__ dbias,

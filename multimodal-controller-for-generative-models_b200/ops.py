@@ -754,6 +754,7 @@ def _pad_cols(m, cols):
 
 
 ACT_DTYPE = torch.bfloat16      # storage type of activations; torch.float32 selects the fp32 parity pipeline
+_TK = 32          # patch columns of the direct thin-conv kernels (csrc/thin_mma.cu)
 _KU = 64          # im2col width of the thin tensor (R*S*Ct <= 36 taps*channels, padded to one 64-wide K block)
 
 
@@ -925,10 +926,25 @@ class WideFromThinFn(torch.autograd.Function):
         if stride != 1 and thin.requires_grad:
             raise ValueError("Not valid: the strided thin conv has no image gradient (first encoder layer only)")
         f32 = ACT_DTYPE == torch.float32
+        labels, packed = gate if gate is not None else (None, None)
+        if (not f32 and stride == 1 and pad is None and R == S and R in (1, 3) and R * S * C <= _TK - 1 and K % 16 == 0
+                and 128 % thin.shape[2] == 0 and (thin.shape[1] * thin.shape[2]) % 128 == 0):
+            # direct path (csrc/thin_mma.cu): the patch matrix never leaves shared memory
+            wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _TK)
+            N, H, Wd, _ = thin.shape
+            out = torch.empty(N, H, Wd, K, dtype=torch.bfloat16, device=thin.device)
+            ev = _prof_begin()
+            _lib.call("mcgm_thin_conv_fwd", thin.data_ptr(), wm.data_ptr(), _TK, _ptr(bias), _ptr(labels),
+                      _ptr(packed.bits if packed else None), packed.M if packed else 0, int(gate is not None),
+                      out.data_ptr(), N, H, Wd, C, R, S, K, _stream())
+            _prof_end(ev, "conv", 2.0 * N * H * Wd * K * C * R * S, f"thin_conv {N}x{H}x{Wd} {C}->{K} k{R} gate{int(gate is not None)}")
+            ctx.save_for_backward(thin, w, out if gate is not None else None, sn)
+            ctx.gated, ctx.has_bias, ctx.grad_premasked, ctx.direct = gate is not None, bias is not None, grad_premasked, True
+            return out
+        ctx.direct = False
         U = thin_im2col(thin, R, S, False, _KU, stride, pad, ACT_DTYPE)
-        flags, labels, packed = 0, None, None
+        flags = 0
         if gate is not None:
-            labels, packed = gate
             flags = EPI_RELU | EPI_MASK
         if f32:
             weff = w.detach() * sn[0] if sn is not None else w.detach()
@@ -960,14 +976,28 @@ class WideFromThinFn(torch.autograd.Function):
                 T = conv_fwd(dout, wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous(), torch.float32)
             dthin = thin_col2im(T, C, R, S)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            if dout.dtype == torch.float32:
-                dwm, db = wgrad_f32(CONV_S1, U, dout, 1, 1, want_bias=ctx.has_bias)
+            if ctx.direct:
+                thin = U                                       # the direct path saved the image itself
+                N, H, Wd, _ = thin.shape
+                dwm = torch.empty(K, _TK, dtype=torch.float32, device=thin.device)
+                ws = _workspace("thin_wgrad", _lib.query("mcgm_thin_conv_wgrad_workspace_bytes", K), thin.device)
+                ev = _prof_begin()
+                _lib.call("mcgm_thin_conv_wgrad", thin.data_ptr(), dout.data_ptr(), dwm.data_ptr(), N, H, Wd, C, R, S, K,
+                          ws.data_ptr(), _stream())
+                _lib.launch_count += 1
+                _prof_end(ev, "wgrad", 2.0 * N * H * Wd * K * C * R * S, f"thin_wgrad {N}x{H}x{Wd} {C}->{K} k{R}")
+                db = dwm[:, R * S * C].contiguous() if ctx.has_bias else None
+                ku = _TK
             else:
-                dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)   # [K,1,1,KU], columns (r,s,c)
+                if dout.dtype == torch.float32:
+                    dwm, db = wgrad_f32(CONV_S1, U, dout, 1, 1, want_bias=ctx.has_bias)
+                else:
+                    dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)   # [K,1,1,KU], columns (r,s,c)
+                ku = _KU
             if sn is not None:
-                dw = sn_weight_bwd(dwm, _KU, 1, w, sn)
+                dw = sn_weight_bwd(dwm, ku, 1, w, sn)
             else:
-                dw = dwm.reshape(K, _KU)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
+                dw = dwm.reshape(K, ku)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
         return dthin, dw, db, None, None, None, None, None
 
 

@@ -64,6 +64,24 @@ if "epi" in which:
         fl_ = 2.0 * N * H * H * Cin * Cout * R * R
         by = (x.numel() + N * H * H * Cout + (res.numel() if res is not None else 0) + (aux.numel() if aux is not None else 0)) * 2
         print(f"conv_epi N{N} {H}x{H} {Cin}->{Cout} k{R} f{fl:#x}: {t * 1e6:8.1f} us  {fl_ / t / 1e12:7.1f} TFLOP/s  {by / t / 1e9:7.0f} GB/s", flush=True)
+if "thin" in which:
+    M = 10
+    labels = torch.randint(0, M, (N,), device=dev).to(torch.int32)
+    packed = ops.PackedCodebook((torch.rand(M, 128) > 0.5).float().to(dev))
+    img = torch.randn(N, 32, 32, 3, device=dev)
+    for R in (3, 1):
+        w = torch.nn.Parameter(torch.randn(128, 3, R, R, device=dev) * 0.1)
+        b = torch.nn.Parameter(torch.zeros(128, device=dev))
+        gate = (labels, packed) if R == 3 else None
+        t = timeit(lambda: ops.WideFromThinFn.apply(img, w, b, gate, True, None))
+        print(f"thin_conv fwd k{R}: {t * 1e6:7.1f} us  {(img.numel() * 4 + N * 1024 * 128 * 2) / t / 1e9:7.0f} GB/s", flush=True)
+        out = ops.WideFromThinFn.apply(img, w, b, gate, True, None)
+        dout = torch.randn_like(out)
+        def bw():
+            w.grad = None; b.grad = None
+            out.backward(dout, retain_graph=True)
+        t = timeit(bw)
+        print(f"thin_conv wgrad k{R}: {t * 1e6:7.1f} us  {(img.numel() * 4 + N * 1024 * 128 * 2) / t / 1e9:7.0f} GB/s", flush=True)
 if "wgrad" in which:
     for (H, Cin, Cout, R) in [(32, 256, 256, 3), (16, 256, 256, 3), (8, 256, 256, 3), (32, 128, 128, 3), (16, 128, 128, 3),
                               (8, 128, 128, 3), (16, 256, 256, 1), (32, 64, 128, 1), (32, 256, 64, 1)]:
