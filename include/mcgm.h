@@ -150,6 +150,15 @@ int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc, const floa
  * mcgm_sn_weight_bwd, and its result is ADDED to grad_i (fp32 OIHW, the parameter's gradient).  Items that share
  * grad_i (the real- and fake-batch passes of one layer) are applied by the same threads in order: two launches in
  * total, deterministic. */
+/* Batched mcgm_pack_weight / mcgm_pack_weight_padded for all spectral-normed conv layers of one forward (n <= 16;
+ * *_host = HOST arrays): layer i is W_i (fp32 OIHW) scaled by inv_sigma_i[0] (device scalar, may be NULL).
+ * mode_i = 0: out0_i = bf16 KRSC, out1_i = bf16 CRSK with flipped taps; mode_i = 1: out0_i = bf16
+ * [K][row_stride_i] rows in (r,s,c) order, zero padded.  One launch. */
+int mcgm_pack_weight_batched(int n, const float* const* W_host, const float* const* inv_sigma_host, const int* K_host,
+                             const int* C_host, const int* R_host, const int* S_host, const int* mode_host,
+                             const int* row_stride_host, void* const* out0_host, void* const* out1_host,
+                             void* stream);
+
 size_t mcgm_sn_weight_bwd_batched_workspace_bytes(void);
 int mcgm_sn_weight_bwd_batched(int n, const float* const* dwbar_host, const long* row_stride_host, const int* krsc_host,
                                const float* const* W_host, const float* const* state_host, const int* K_host,

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mcgm_sn_weight_bwd_workspace_bytes": (c_size_t, []),
     "mcgm_sn_weight_bwd": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p]),
+    "mcgm_pack_weight_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "mcgm_sn_weight_bwd_batched_workspace_bytes": (c_size_t, []),
     "mcgm_sn_weight_bwd_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -252,6 +252,53 @@ __global__ void pack_weight_padded_kernel(const float* __restrict__ w, int K, in
   }
 }
 
+// ---- batched weight packing of all spectral-normed conv layers of one forward: W/sigma -> bf16 operand layouts.
+// mode 0: KRSC (forward) + CRSK with flipped taps (dgrad); mode 1: [K][row_stride] rows in (r,s,c) order, zero
+// padded (thin layers).  One launch instead of one per layer (11 per D forward, 11 forwards per iteration).
+struct PackBatch {
+  const float* W[kSnMaxLayers];
+  const float* inv_sigma[kSnMaxLayers];
+  __nv_bfloat16* out0[kSnMaxLayers];      // KRSC / padded rows
+  __nv_bfloat16* out1[kSnMaxLayers];      // flipped CRSK (mode 0)
+  int K[kSnMaxLayers], C[kSnMaxLayers], R[kSnMaxLayers], S[kSnMaxLayers], mode[kSnMaxLayers], row_stride[kSnMaxLayers];
+};
+
+__global__ void __launch_bounds__(256)
+pack_weight_batched_kernel(const PackBatch b) {
+  const int L = blockIdx.y;
+  const int K = b.K[L], C = b.C[L], R = b.R[L], S = b.S[L];
+  const float* __restrict__ w = b.W[L];
+  const float sc = b.inv_sigma[L] ? __ldg(b.inv_sigma[L]) : 1.0f;
+  if (b.mode[L] == 0) {
+    const long total = (long)K * C * R * S;
+    __nv_bfloat16* krsc = b.out0[L];
+    __nv_bfloat16* flip = b.out1[L];
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      long t = i;                                        // i indexes the KRSC destination: coalesced bf16 writes
+      const int c = (int)(t % C); t /= C;
+      const int s_ = (int)(t % S); t /= S;
+      const int r = (int)(t % R);
+      const int k = (int)(t / R);
+      const __nv_bfloat16 v = __float2bfloat16(w[(((long)k * C + c) * R + r) * S + s_] * sc);
+      krsc[i] = v;
+      flip[(((long)c * R + (R - 1 - r)) * S + (S - 1 - s_)) * K + k] = v;
+    }
+  } else {
+    const int rs = b.row_stride[L], RSC = R * S * C;
+    const long total = (long)K * rs;
+    __nv_bfloat16* out = b.out0[L];
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const int k = (int)(i / rs), col = (int)(i - (long)k * rs);
+      float v = 0.0f;
+      if (col < RSC) {
+        const int c = col % C, t = col / C;
+        v = w[((long)k * C + c) * (R * S) + t] * sc;
+      }
+      out[i] = __float2bfloat16(v);
+    }
+  }
+}
+
 }  // namespace mcgm
 
 using namespace mcgm;
@@ -298,6 +345,27 @@ extern "C" int mcgm_sn_weight_bwd(const float* dwbar, long row_stride, int krsc,
   sn_bwd_dot_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, W_oihw, K, C, R * S, partial);
   MCGM_LAUNCH_CHECK();
   sn_bwd_apply_kernel<<<blocks, kSnBwdThreads, 0, st>>>(dwbar, row_stride, krsc, sn_state, partial, blocks, K, C, R * S, dW_oihw);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_pack_weight_batched(int n, const float* const* W_host, const float* const* inv_sigma_host,
+                                        const int* K_host, const int* C_host, const int* R_host, const int* S_host,
+                                        const int* mode_host, const int* row_stride_host, void* const* out0_host,
+                                        void* const* out1_host, void* stream) {
+  MCGM_CHECK_ARG(n > 0 && n <= kSnMaxLayers, "pack_weight_batched: 1..%d layers per call (got %d)", kSnMaxLayers, n);
+  MCGM_CHECK_ARG(W_host && inv_sigma_host && K_host && C_host && R_host && S_host && mode_host && row_stride_host && out0_host && out1_host,
+                 "pack_weight_batched: bad arguments");
+  PackBatch b{};
+  for (int i = 0; i < n; ++i) {
+    MCGM_CHECK_ARG(W_host[i] && out0_host[i] && K_host[i] > 0 && C_host[i] > 0 && R_host[i] > 0 && S_host[i] > 0, "pack_weight_batched: layer %d invalid", i);
+    MCGM_CHECK_ARG(mode_host[i] == 0 ? out1_host[i] != nullptr : row_stride_host[i] >= C_host[i] * R_host[i] * S_host[i],
+                   "pack_weight_batched: layer %d: mode 0 needs the flipped output, mode 1 a row stride >= C*R*S", i);
+    b.W[i] = W_host[i]; b.inv_sigma[i] = inv_sigma_host[i]; b.K[i] = K_host[i]; b.C[i] = C_host[i]; b.R[i] = R_host[i]; b.S[i] = S_host[i];
+    b.mode[i] = mode_host[i]; b.row_stride[i] = row_stride_host[i];
+    b.out0[i] = (__nv_bfloat16*)out0_host[i]; b.out1[i] = (__nv_bfloat16*)out1_host[i];
+  }
+  pack_weight_batched_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(b);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

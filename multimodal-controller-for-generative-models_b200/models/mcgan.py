@@ -78,9 +78,10 @@ class GlobalSumPooling(nn.Module):
 class _Ctx:
     """Per-forward context: int32 mode labels on the device."""
 
-    def __init__(self, labels, sn=None):
+    def __init__(self, labels, sn=None, sn_packs=None):
         self.labels = ops.as_labels(labels).contiguous()
         self.sn = sn            # {module: spectral-norm snapshot} for this forward
+        self.sn_packs = sn_packs or {}      # {module: bf16 operand copies of W/sigma} (ops.sn_pack_all)
 
 
 def _labels_from_indicator(indicator):
@@ -135,7 +136,7 @@ def _conv(x, conv, ctx, res=None, res_up=False, gate=None, premask_dx=False, gra
     ``ctx.sn[conv]`` holds this forward's [1/sigma | u | v] and the weight is packed as W/sigma)."""
     if hasattr(conv, 'weight_orig'):
         return ops.ConvFn.apply(x, conv.weight_orig, conv.bias, res, res_up, gate, premask_dx, grad_premasked,
-                                None, ctx.sn[conv])
+                                ctx.sn_packs.get(conv), ctx.sn[conv])
     w = conv.weight
     return ops.ConvFn.apply(x, w, conv.bias, res, res_up, gate, premask_dx, grad_premasked, _packs(w), None, False,
                             want_stats)
@@ -243,8 +244,9 @@ class FirstDisResBlock(nn.Module):
         """img: fp32 NHWC [N,H,W,3] (mcgan.py:72-93).  AvgPool is linear, so conv2 + shortcut are
         summed at full resolution in conv2's epilogue and pooled once."""
         c1, c2, sc = self.conv[0].module, self.conv[3].module, self.shortcut[0].module
-        h = ops.WideFromThinFn.apply(img, c1.weight_orig, c1.bias, (ctx.labels, self.mc_1.packed()), True, ctx.sn[c1])
-        s = ops.WideFromThinFn.apply(img, sc.weight_orig, sc.bias, None, False, ctx.sn[sc])
+        h = ops.WideFromThinFn.apply(img, c1.weight_orig, c1.bias, (ctx.labels, self.mc_1.packed()), True, ctx.sn[c1],
+                                     1, None, ctx.sn_packs.get(c1))
+        s = ops.WideFromThinFn.apply(img, sc.weight_orig, sc.bias, None, False, ctx.sn[sc], 1, None, ctx.sn_packs.get(sc))
         y = _conv(h, c2, ctx, res=s, premask_dx=True)
         return ops.Pool2Fn.apply(y)
 
@@ -301,8 +303,9 @@ class Discriminator(nn.Module):
         sn = {}
         for batch in self._sn_batch:      # one launch per <= 16 layers: power iteration + [1/sigma|u|v] snapshot
             sn.update(batch.run(self.training))
-        ctx = _Ctx(_labels_from_indicator(indicator), sn)
         _sync_act_dtype()
+        packs = ops.sn_pack_all(sn) if ops.ACT_DTYPE == torch.bfloat16 else None     # one launch for all conv layers
+        ctx = _Ctx(_labels_from_indicator(indicator), sn, packs)
         img = input.permute(0, 2, 3, 1).contiguous().float()
         n_res = len(self.blocks) - 4
         x = self.blocks[0].fused(img, ctx)

@@ -340,6 +340,50 @@ def _sn_flush():
         _lib.launch_count += 1
 
 
+def sn_pack_all(states):
+    """Operand copies of every spectral-normed CONV layer of one forward in one launch.
+    states: {module: [1/sigma | u | v]} from SNBatch.run.  -> {module: (KRSC, flipped CRSK)} for wide layers,
+    {module: padded [K,1,1,32|64]} for thin (Cin <= 4) layers.  Linear layers are left to SNScaleFn."""
+    import ctypes as c
+    mods = [m for m in states if m.weight_orig.dim() == 4]
+    if not mods:
+        return {}
+    dev = mods[0].weight_orig.device
+    sizes, metas = [], []
+    for m in mods:
+        K, C, R, S = m.weight_orig.shape
+        if C <= 4:
+            rs = _TK if R * S * C <= _TK - 1 else _KU
+            sizes.append(K * rs)
+            metas.append((1, rs))
+        else:
+            sizes.append(2 * K * C * R * S)
+            metas.append((0, 0))
+    offs, off = [], 0
+    for n_ in sizes:
+        offs.append(off)
+        off += (n_ + 63) // 64 * 64
+    flat = torch.empty(off, dtype=torch.bfloat16, device=dev)
+    out, o0, o1 = {}, [], []
+    for m, o, (mode, rs) in zip(mods, offs, metas):
+        K, C, R, S = m.weight_orig.shape
+        if mode == 1:
+            out[m] = flat[o:o + K * rs].view(K, 1, 1, rs)
+            o0.append(out[m].data_ptr()); o1.append(None)
+        else:
+            n_ = K * C * R * S
+            out[m] = (flat[o:o + n_].view(K, R, S, C), flat[o + n_:o + 2 * n_].view(C, R, S, K))
+            o0.append(out[m][0].data_ptr()); o1.append(out[m][1].data_ptr())
+    n = len(mods)
+    shp = [m.weight_orig.shape for m in mods]
+    _lib.call("mcgm_pack_weight_batched", n, (c.c_void_p * n)(*[m.weight_orig.data_ptr() for m in mods]),
+              (c.c_void_p * n)(*[states[m].data_ptr() for m in mods]), (c.c_int * n)(*[s_[0] for s_ in shp]),
+              (c.c_int * n)(*[s_[1] for s_ in shp]), (c.c_int * n)(*[s_[2] for s_ in shp]), (c.c_int * n)(*[s_[3] for s_ in shp]),
+              (c.c_int * n)(*[mt[0] for mt in metas]), (c.c_int * n)(*[mt[1] for mt in metas]),
+              (c.c_void_p * n)(*o0), (c.c_void_p * n)(*o1), _stream())
+    return out
+
+
 def sn_weight_bwd(dwbar, row_stride, krsc, w, state):
     """dW (OIHW, fp32) = (dW_bar - <dW_bar, W_bar> u v^T) / sigma.  With SN_DEFER: queued for the batched
     end-of-backward launch (returns None: the result goes straight into ``w.grad``)."""
@@ -921,7 +965,7 @@ class WideFromThinFn(torch.autograd.Function):
     gradient (needed in the G update) is a 1x1 GEMM to [P, 32] followed by col2im."""
 
     @staticmethod
-    def forward(ctx, thin, w, bias, gate, grad_premasked, sn, stride=1, pad=None):
+    def forward(ctx, thin, w, bias, gate, grad_premasked, sn, stride=1, pad=None, wm_packed=None):
         K, C, R, S = w.shape                                   # OIHW: K = Cw, C = Ct
         if stride != 1 and thin.requires_grad:
             raise ValueError("Not valid: the strided thin conv has no image gradient (first encoder layer only)")
@@ -930,7 +974,8 @@ class WideFromThinFn(torch.autograd.Function):
         if (not f32 and stride == 1 and pad is None and R == S and R in (1, 3) and R * S * C <= _TK - 1 and K % 16 == 0
                 and 128 % thin.shape[2] == 0 and (thin.shape[1] * thin.shape[2]) % 128 == 0):
             # direct path (csrc/thin_mma.cu): the patch matrix never leaves shared memory
-            wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _TK)
+            wm = wm_packed if (wm_packed is not None and wm_packed.shape[-1] == _TK) else \
+                pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _TK)
             N, H, Wd, _ = thin.shape
             out = torch.empty(N, H, Wd, K, dtype=torch.bfloat16, device=thin.device)
             ev = _prof_begin()
@@ -998,7 +1043,7 @@ class WideFromThinFn(torch.autograd.Function):
                 dw = sn_weight_bwd(dwm, ku, 1, w, sn)
             else:
                 dw = dwm.reshape(K, ku)[:, :R * S * C].reshape(K, R, S, C).permute(0, 3, 1, 2)
-        return dthin, dw, db, None, None, None, None, None
+        return dthin, dw, db, None, None, None, None, None, None
 
 
 class ThinFromWideFn(torch.autograd.Function):
