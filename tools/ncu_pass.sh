@@ -11,8 +11,8 @@ $NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --l
 timeout 300 python tools/profile_step.py --mode d > gpurun_out/plain_d0.log 2>&1
 
 
-$NCU --set full --import-source on -k regex:"gate_fwd_kernel|bn_partial_kernel" -s 12 -c 6 -o gpurun_out/prof_gate_fwd python tools/profile_step.py --mode d > gpurun_out/ncu_full2.log 2>&1
+$NCU --set full -k regex:"gate_fwd_kernel|bn_partial_kernel" -s 12 -c 4 -o gpurun_out/prof_gate_fwd python tools/profile_step.py --mode d > gpurun_out/ncu_full2.log 2>&1
 timeout 300 python tools/profile_step.py --mode g > gpurun_out/plain_g0.log 2>&1 && \
 bash tools/ncu_conv.sh
-$NCU --set full --import-source on -k regex:"gate_bwd_reduce_kernel|gate_bwd_apply_kernel" -s 4 -c 4 -o gpurun_out/prof_gate_bwd python tools/profile_step.py --mode g > gpurun_out/ncu_full4.log 2>&1
+$NCU --set full -k regex:"gate_bwd_reduce_kernel|gate_bwd_apply_kernel" -s 4 -c 2 -o gpurun_out/prof_gate_bwd python tools/profile_step.py --mode g > gpurun_out/ncu_full4.log 2>&1
 ls -la gpurun_out | head -30

@@ -79,7 +79,9 @@ for name, title in (("prof_conv_fwd.ncu-rep", "`--set full`: conv_fwd_kernel, ge
                     ("prof_conv_fwd_d.ncu-rep", "`--set full`: conv_fwd_kernel, discriminator 128->128 launches"),
                     ("prof_wgrad.ncu-rep", "`--set full`: conv_wgrad_kernel, generator launches"),
                     ("prof_gate_fwd.ncu-rep", "`--set full`: bn_partial_kernel / gate_fwd_kernel, generator launches"),
-                    ("prof_gate_bwd.ncu-rep", "`--set full`: gate_bwd_reduce_kernel / gate_bwd_apply_kernel")):
+                    ("prof_gate_bwd.ncu-rep", "`--set full`: gate_bwd_reduce_kernel / gate_bwd_apply_kernel"),
+                    ("prof_thin.ncu-rep", "`--set full`: thin_conv_fwd_kernel (Conv2d(3,128,3,1,1) + ReLU + MC, no im2col buffer; microbench launches)"),
+                    ("prof_thin_wg.ncu-rep", "`--set full`: thin_conv_wgrad_kernel + its partial reduce (microbench launches)")):
     p = os.path.join(SRC, name)
     if os.path.exists(p):
         parts.append(full_table(p, title))
@@ -88,7 +90,8 @@ for name, title in (("prof_conv_fwd.ncu-rep", "`--set full`: conv_fwd_kernel, ge
 # (report, index of the launch inside the report) -> shape descriptor used by ops.PROFILE / bench.py
 TRAFFIC = {"conv 512x32x32 256->256 k3 f0x5 bf16": ("prof_conv_fwd.ncu-rep", 1),
            "conv_ex kind2 512x16x16 256->256 f0x1": ("prof_conv_fwd.ncu-rep", 0),
-           "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", 2),
+           "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", 0),
+           "thin_conv 512x32x32 3->128 k3 gate1": ("prof_thin.ncu-rep", 0),
            "gate_fwd 512x32x32x256 f0xb raw0": ("prof_gate_fwd.ncu-rep", 3),
            "bn_stats P524288 C256": ("prof_gate_fwd.ncu-rep", 2),
            "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", 0)}
