@@ -213,6 +213,14 @@ int mcgm_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias,
  *   MCGM_CONV_S2K4  : dy [N,H/2,W/2,Cout]; dw[k,p,q,c] = sum dy[n,i,j,k] * x[n,2i+p-1,2j+q-1,c]
  *   MCGM_CONV_PHASE2: dy [N,2H,2W,Cout];   dw[k,p,q,c] = sum dy[n,2i+p-1,2j+q-1,k] * x[n,i,j,c]
  *                     (phase ph, tap a of the forward weight is p = 3 - 2a - ph; same for q). */
+/* Grouped form: n <= 4 independent stride-1 weight gradients of IDENTICAL geometry (the layers of one backward
+ * pass that share a shape) in one launch pair.  x_host / dy_host / dw_host / dbias_host are HOST arrays of n device
+ * pointers (dbias_host may be NULL).  Alone, a small-spatial layer fills the machine only through ~29-way split-K
+ * whose partials dominate its cost; side by side each group needs a fraction of the splits. */
+size_t mcgm_conv_wgrad_grouped_workspace_bytes(int n, int N, int H, int W, int Cin, int Cout, int R, int S);
+int mcgm_conv_wgrad_grouped(int n, const void* const* x_host, const void* const* dy_host, float* const* dw_host,
+                            float* const* dbias_host, int N, int H, int W, int Cin, int Cout, int R, int S,
+                            void* workspace, void* stream);
 size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int in_dtype, int N, int H, int W, int Cin, int Cout,
                                           int R, int S);
 int mcgm_conv_wgrad_ex(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias,

@@ -682,6 +682,15 @@ struct WgradParams {
   float* partial;                       // [splits][Cout*R*S*Cin]
   float* bias_partial;                  // [splits][bias_slots][Cout] or nullptr
   int bias_taps[4], bias_slots;         // taps whose dY pixels tile dY exactly once (stride-2 dY: 4 parity classes)
+  // grouped launch: `groups` independent problems of identical geometry share one grid (CTA -> group by index)
+  int groups, ctas_per_group;
+  size_t group_partial_stride, group_bias_stride;      // floats between the groups' partial / bias-partial blocks
+};
+
+static constexpr int kWgMaxGroups = 4;
+struct WgMaps {
+  CUtensorMap dy[kWgMaxGroups];
+  CUtensorMap x[kWgMaxGroups];
 };
 
 // NT = number of filter taps one CTA accumulates against the SAME dY tile (A operand):
@@ -700,9 +709,17 @@ struct WgCfg {
 
 template <int BN, int NT>
 __global__ void __launch_bounds__(kWgradThreads, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
-                  const WgradParams p) {
+conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
   using Cfg = WgCfg<BN, NT>;
+  // Several independent weight gradients of identical geometry (the layers of one backward pass that share a
+  // shape) can share one launch: alone, a small-spatial layer fills 148 SMs only through ~29-way split-K, whose
+  // partials then dominate its cost; two to four of them side by side need a quarter of the splits each.
+  const int grp = blockIdx.x / pin.ctas_per_group;
+  const CUtensorMap& tmap_dy = maps.dy[grp];
+  const CUtensorMap& tmap_x = maps.x[grp];
+  const WgradParams& p = pin;
+  float* const partial = pin.partial + (size_t)grp * pin.group_partial_stride;
+  float* const bias_partial = pin.bias_partial ? pin.bias_partial + (size_t)grp * pin.group_bias_stride : nullptr;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ones_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -714,7 +731,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  int id = blockIdx.x;
+  int id = blockIdx.x % p.ctas_per_group;
   const int split = id % p.splits; id /= p.splits;
   const int tap0 = (id % p.tap_groups) * NT; id /= p.tap_groups;
   const int cin_t = id % p.cin_tiles;
@@ -728,7 +745,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (i < p.bias_slots && p.bias_taps[i] == tap0) bias_slot = i;
-  const bool do_bias = p.bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
+  const bool do_bias = bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
   if (do_bias && warp >= 2) {
     const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
     for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
@@ -826,11 +843,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kBiasCol, acc);
       tmem_ld_wait();
       if (co < p.Cout)
-        p.bias_partial[((size_t)split * p.bias_slots + bias_slot) * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
+        bias_partial[((size_t)split * p.bias_slots + bias_slot) * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
     }
     for (int q = 0; q < ntaps; ++q) {
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + q * BN;
-      float* dst = p.partial + (size_t)split * per_split + ((size_t)co * p.taps + tap0 + q) * p.Cin + ci0;
+      float* dst = partial + (size_t)split * per_split + ((size_t)co * p.taps + tap0 + q) * p.Cin + ci0;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t acc[32];
@@ -862,17 +879,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 // split, lane w of a column sums splits w, w+8, ... with four loads in flight, and the eight lane sums are
 // combined through shared memory in lane order — a fixed order, hence deterministic.  (One thread per output
 // walking all splits was a chain of up to 148 dependent L2 round trips on 8..144 blocks: 13-16 us a call.)
+struct WgReduceOut {
+  float* dw[kWgMaxGroups];
+  float* dbias[kWgMaxGroups];
+};
+
 __global__ void __launch_bounds__(32 * kRedLanes)
-wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/, float* __restrict__ dw,
-                    const float* __restrict__ bias_partial, int bias_rows, int Cout, float* __restrict__ dbias,
-                    int wblocks) {
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4 /*float4 count*/, const WgReduceOut out,
+                    const float* __restrict__ bias_partial, int bias_rows, int Cout, int wblocks,
+                    size_t group_partial_stride, size_t group_bias_stride) {
   __shared__ float4 sm4[kRedLanes][32];
+  const int g = blockIdx.y;
+  partial += (size_t)g * group_partial_stride;
   if ((int)blockIdx.x < wblocks) {
     for (size_t i0 = (size_t)blockIdx.x * 32; i0 < n4; i0 += (size_t)wblocks * 32)
-      reduce_columns<float4>(reinterpret_cast<const float4*>(partial), splits, n4, n4, i0, reinterpret_cast<float4*>(dw), sm4);
+      reduce_columns<float4>(reinterpret_cast<const float4*>(partial), splits, n4, n4, i0, reinterpret_cast<float4*>(out.dw[g]), sm4);
   } else {
     float (*sm1)[32] = reinterpret_cast<float (*)[32]>(&sm4[0][0]);
-    reduce_columns<float>(bias_partial, bias_rows, (size_t)Cout, (size_t)Cout, (size_t)(blockIdx.x - wblocks) * 32, dbias, sm1);
+    reduce_columns<float>(bias_partial + (size_t)g * group_bias_stride, bias_rows, (size_t)Cout, (size_t)Cout,
+                          (size_t)(blockIdx.x - wblocks) * 32, out.dbias[g], sm1);
   }
 }
 
@@ -954,8 +979,7 @@ static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const Conv
 }
 
 template <int BN, int NT>
-static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradParams& p, int grid,
-                        cudaStream_t st) {
+static int launch_wgrad(const WgMaps& maps, const WgradParams& p, int grid, cudaStream_t st) {
   using Cfg = WgCfg<BN, NT>;
   auto kern = conv_wgrad_kernel<BN, NT>;
   static bool configured = false;
@@ -963,7 +987,7 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const Wgr
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, kWgradThreads, Cfg::kSmemBytes, st>>>(mdy, mx, p);
+  kern<<<grid, kWgradThreads, Cfg::kSmemBytes, st>>>(maps, p);
   MCGM_LAUNCH_CHECK();
   return 0;
 }
@@ -976,7 +1000,7 @@ struct WgradPlan {
 };
 
 // H, W are the dims of X
-static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl) {
+static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl, int groups = 1) {
   if (Cin % 64 || Cout % 64) return fail(MCGM_E_UNSUPPORTED, "wgrad: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
   pl->AS = pl->BS = 1;
   pl->a_shift = false;
@@ -1004,7 +1028,7 @@ static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout
   const int tiles = pl->cout_tiles * pl->cin_tiles * pl->tap_groups;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int splits = sms / tiles;                        // at most one wave of CTAs
+  int splits = sms / (tiles * groups);             // at most one wave of CTAs (all groups of a grouped launch together)
   if (g_knobs.wg_splits) splits = (int)g_knobs.wg_splits;
   if (splits > pl->total_kb) splits = pl->total_kb;
   // one wave of CTAs; the cap only binds for single-tile problems (thin / 1x1 weight gradients), whose
@@ -1207,16 +1231,20 @@ static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Ci
   return bytes;
 }
 
-static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
-                           int W, int Cin, int Cout, int R, int S, void* workspace, void* stream) {
-  MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
+static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* const* xs, const void* const* dys,
+                                   float* const* dws, float* const* dbs, int N, int H, int W, int Cin, int Cout, int R, int S,
+                                   void* workspace, void* stream) {
+  MCGM_CHECK_ARG(n >= 1 && n <= kWgMaxGroups && xs && dys && dws && workspace && N > 0, "conv_wgrad: bad arguments (1..%d groups)", kWgMaxGroups);
   // MN-major TF32 operands need the 128B/32B-atom swizzle on both the TMA and the UMMA side; with the plain
   // 128B swizzle used here the tensor cores return zeros (measured).  The fp32 parity pipeline therefore
   // computes weight gradients from bf16x3 operand pieces on this (bf16) kernel instead.
   if (in_dtype != MCGM_BF16) return fail(MCGM_E_UNSUPPORTED, "conv_wgrad: only bf16 operands (fp32 parity mode uses bf16x3 pieces)");
   const int tf32 = 0;
+  const bool want_bias = dbs != nullptr && dbs[0] != nullptr;
+  for (int g = 0; g < n; ++g)
+    MCGM_CHECK_ARG(xs[g] && dys[g] && dws[g] && (!want_bias || dbs[g]), "conv_wgrad: group %d has a NULL pointer", g);
   WgradPlan pl;
-  if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl)) return e;
+  if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl, n)) return e;
   WgradParams p{};
   p.N = N; p.Cin = Cin; p.Cout = Cout; p.AS = pl.AS; p.BS = pl.BS;
   for (int t = 0; t < pl.taps; ++t) {
@@ -1230,43 +1258,75 @@ static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy
   p.desc_templ = make_smem_desc_hi_lbo(tf32 ? 4096 : g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1, tf32);
   p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1, tf32);
-  p.partial = (float*)workspace;
-  p.bias_partial = dbias ? p.partial + (size_t)pl.splits * pl.per_split : nullptr;
   p.bias_slots = 1; p.bias_taps[0] = 0;
   if (kind == MCGM_CONV_PHASE2) {          // dY is read with stride 2: the four offsets in {0,1}^2 cover it once
     p.bias_slots = 4; p.bias_taps[0] = 5; p.bias_taps[1] = 6; p.bias_taps[2] = 9; p.bias_taps[3] = 10;
   }
+  // workspace: [groups][splits][per_split] weight partials, then [groups][splits * bias_slots][Cout] bias partials
+  p.groups = n;
+  p.ctas_per_group = pl.cout_tiles * pl.cin_tiles * pl.tap_groups * pl.splits;
+  p.group_partial_stride = (size_t)pl.splits * pl.per_split;
+  p.group_bias_stride = (size_t)pl.splits * p.bias_slots * Cout;
+  p.partial = (float*)workspace;
+  p.bias_partial = want_bias ? p.partial + (size_t)n * p.group_partial_stride : nullptr;
 
   // dims of dY and X: the grid scaled by the traversal strides
   const int Hdy = pl.Hg * pl.AS, Wdy = pl.Wg * pl.AS;
-  CUtensorMap mdy, mx;
-  {
-    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
-    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
-    if (int e = make_tmap(&mdy, dy, 4, dims, box, pl.AS, tf32)) return e;
+  WgMaps maps{};
+  WgReduceOut out{};
+  for (int g = 0; g < n; ++g) {
+    {
+      const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
+      const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
+      if (int e = make_tmap(&maps.dy[g], dys[g], 4, dims, box, pl.AS, tf32)) return e;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
+      if (int e = make_tmap(&maps.x[g], xs[g], 4, dims, box, pl.BS, tf32)) return e;
+    }
+    out.dw[g] = dws[g];
+    out.dbias[g] = want_bias ? dbs[g] : nullptr;
   }
-  {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
-    if (int e = make_tmap(&mx, x, 4, dims, box, pl.BS, tf32)) return e;
-  }
+  for (int g = n; g < kWgMaxGroups; ++g) { maps.dy[g] = maps.dy[0]; maps.x[g] = maps.x[0]; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = pl.cout_tiles * pl.cin_tiles * pl.tap_groups * pl.splits;
+  const int grid = p.ctas_per_group * n;
   int e;
   switch (pl.BN) {
-    case 256: e = launch_wgrad<256, 1>(mdy, mx, p, grid, st); break;
-    case 128: e = pl.NT == 2 ? launch_wgrad<128, 2>(mdy, mx, p, grid, st) : launch_wgrad<128, 1>(mdy, mx, p, grid, st); break;
-    default: e = pl.NT == 2 ? launch_wgrad<64, 2>(mdy, mx, p, grid, st) : launch_wgrad<64, 1>(mdy, mx, p, grid, st); break;
+    case 256: e = launch_wgrad<256, 1>(maps, p, grid, st); break;
+    case 128: e = pl.NT == 2 ? launch_wgrad<128, 2>(maps, p, grid, st) : launch_wgrad<128, 1>(maps, p, grid, st); break;
+    default: e = pl.NT == 2 ? launch_wgrad<64, 2>(maps, p, grid, st) : launch_wgrad<64, 1>(maps, p, grid, st); break;
   }
   if (e) return e;
   const size_t n4 = pl.per_split / 4;
   long wblocks = (long)((n4 + 31) / 32);
   if (wblocks > 148 * 16) wblocks = 148 * 16;
-  const int bblocks = (dbias && p.bias_partial) ? (Cout + 31) / 32 : 0;
-  wgrad_reduce_kernel<<<(int)wblocks + bblocks, 32 * kRedLanes, 0, st>>>(p.partial, pl.splits, n4, dw, p.bias_partial,
-                                                                        pl.splits * p.bias_slots, Cout, dbias, (int)wblocks);
+  const int bblocks = want_bias ? (Cout + 31) / 32 : 0;
+  wgrad_reduce_kernel<<<dim3((unsigned)(wblocks + bblocks), n), 32 * kRedLanes, 0, st>>>(
+      p.partial, pl.splits, n4, out, p.bias_partial, pl.splits * p.bias_slots, Cout, (int)wblocks, p.group_partial_stride,
+      p.group_bias_stride);
   MCGM_LAUNCH_CHECK();
   return 0;
+}
+
+static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias, int N, int H,
+                           int W, int Cin, int Cout, int R, int S, void* workspace, void* stream) {
+  MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad: bad arguments");
+  return conv_wgrad_grouped_impl(kind, in_dtype, 1, &x, &dy, &dw, dbias ? &dbias : nullptr, N, H, W, Cin, Cout, R, S, workspace, stream);
+}
+
+// Grouped form: n <= 4 independent weight gradients of IDENTICAL geometry in one launch pair (host arrays of
+// device pointers).  Workspace: mcgm_conv_wgrad_grouped_workspace_bytes.
+extern "C" size_t mcgm_conv_wgrad_grouped_workspace_bytes(int n, int N, int H, int W, int Cin, int Cout, int R, int S) {
+  WgradPlan pl;
+  if (n < 1 || n > kWgMaxGroups || plan_wgrad(MCGM_CONV_S1, 0, N, H, W, Cin, Cout, R, S, &pl, n)) return 0;
+  return ((size_t)n * pl.splits * pl.per_split + (size_t)n * pl.splits * 4 * Cout) * sizeof(float);
+}
+extern "C" int mcgm_conv_wgrad_grouped(int n, const void* const* x_host, const void* const* dy_host, float* const* dw_host,
+                                       float* const* dbias_host, int N, int H, int W, int Cin, int Cout, int R, int S,
+                                       void* workspace, void* stream) {
+  return conv_wgrad_grouped_impl(MCGM_CONV_S1, MCGM_BF16, n, x_host, dy_host, dw_host, dbias_host, N, H, W, Cin, Cout, R, S,
+                                 workspace, stream);
 }
 
 extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {

@@ -6,6 +6,8 @@ autograd bookkeeping only; every kernel launched here comes from libmcgm.so.
 Shape / dtype / contiguity problems raise ``ValueError`` (the reference's error
 style, e.g. src/utils.py:126); a failing native call raises ``RuntimeError``.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -304,13 +306,84 @@ class SNBatch:
         return {m: state[o:o + 1 + k + crs] for m, o, (k, crs) in zip(self.modules, self.offs, self.shapes)}
 
 
-# Deferred, batched spectral-norm backward.  With SN_DEFER set (train_gan's update functions do), the
-# weight-gradient paths of spectral-normed layers do not launch their own two small kernels: they queue
-# (dW_bar, layout, weight_orig, state) and one pair of launches at the END of the backward pass handles every
-# layer and adds the results to ``weight_orig.grad`` in place (autograd sees ``None`` for those inputs).  Only
-# valid for ``loss.backward()`` on leaf parameters — which is what the training step does.
+# Deferred end-of-backward work.  With SN_DEFER set (train_gan's D update does), two kinds of parameter-gradient
+# work do not run where autograd reaches them but are queued and flushed by ONE engine callback at the end of the
+# backward pass (autograd sees ``None`` for those inputs; the results are added to ``param.grad`` in place):
+#   * the weight gradients of the small-spatial (H*W <= 256) spectral-normed convs — independent of the rest of
+#     the pass, run as grouped launches of up to four same-shape layers (``mcgm_conv_wgrad_grouped``);
+#   * the spectral-norm backward of every layer — one pair of launches for all of them.
+# Only valid for ``loss.backward()`` on leaf parameters, which is what the training step does.
 SN_DEFER = False
+WGRAD_GROUP = os.environ.get("MCGM_NO_WGRAD_GROUP") is None      # developer A/B knob (tools/): grouped small-layer wgrads
 _sn_pending = []
+_wg_pending = []
+_flush_queued = False
+
+
+def _queue_flush():
+    global _flush_queued
+    if not _flush_queued:
+        _flush_queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(_deferred_flush)
+
+
+def _deferred_flush():
+    global _flush_queued
+    _flush_queued = False
+    _wgrad_flush()
+    _sn_flush()
+
+
+def _wgrad_flush():
+    """Grouped weight gradients of the queued (x, dout, R, S, weight_orig, bias, sn_state) items."""
+    import ctypes as c
+    items, _wg_pending[:] = list(_wg_pending), []
+    groups = {}
+    for it in items:
+        x, dout, R, S = it[0], it[1], it[2], it[3]
+        groups.setdefault((tuple(x.shape), dout.shape[-1], R, S, it[5] is not None), []).append(it)
+    for (xs, Cout, R, S, has_bias), its in groups.items():
+        N, H, W, Cin = xs
+        chunks = []                       # <= 4 items each, no parameter twice in a chunk (its bias gradient is
+        for it in its:                    # accumulated by one multi-tensor add per chunk)
+            for ch in chunks:
+                if len(ch) < 4 and all(o[4] is not it[4] for o in ch):
+                    ch.append(it)
+                    break
+            else:
+                chunks.append([it])
+        for chunk in chunks:
+            n = len(chunk)
+            dev = chunk[0][0].device
+            dw = torch.empty(n, Cout, R, S, Cin, dtype=torch.float32, device=dev)
+            db = torch.empty(n, Cout, dtype=torch.float32, device=dev) if has_bias else None
+            nbytes = _lib.query("mcgm_conv_wgrad_grouped_workspace_bytes", n, N, H, W, Cin, Cout, R, S)
+            if nbytes == 0:
+                raise ValueError(f"Not valid grouped wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} R={R}")
+            ws = _workspace("wgrad_grouped", nbytes, dev)
+            ev = _prof_begin()
+            _lib.call("mcgm_conv_wgrad_grouped", n, (c.c_void_p * n)(*[it[0].data_ptr() for it in chunk]),
+                      (c.c_void_p * n)(*[it[1].data_ptr() for it in chunk]), (c.c_void_p * n)(*[dw[i].data_ptr() for i in range(n)]),
+                      (c.c_void_p * n)(*[db[i].data_ptr() for i in range(n)]) if has_bias else None,
+                      N, H, W, Cin, Cout, R, S, ws.data_ptr(), _stream())
+            _lib.launch_count += 1
+            _prof_end(ev, "wgrad", 2.0 * n * N * H * W * Cout * Cin * R * S, f"wgrad_grouped x{n} {N}x{H}x{W} {Cin}->{Cout} k{R}")
+            for i, it in enumerate(chunk):
+                _sn_pending.append((dw[i], R * S * Cin, 1, it[4], it[6]))
+            if has_bias:
+                grads = []
+                for it in chunk:
+                    b = it[5]
+                    if b.grad is None:
+                        b.grad = torch.zeros_like(b)
+                    grads.append(b.grad)
+                torch._foreach_add_(grads, list(db.unbind(0)))
+
+
+def defer_wgrad(x, dout, R, S, w, bias, sn_state):
+    """Queue a small-spatial SN conv's weight gradient for the grouped end-of-backward launch."""
+    _wg_pending.append((x, dout, R, S, w, bias, sn_state))
+    _queue_flush()
 
 
 def _sn_flush():
@@ -389,9 +462,8 @@ def sn_weight_bwd(dwbar, row_stride, krsc, w, state):
     end-of-backward launch (returns None: the result goes straight into ``w.grad``)."""
     _check_cuda(w, state)
     if SN_DEFER and w.is_leaf and w.requires_grad:
-        if not _sn_pending:
-            torch.autograd.Variable._execution_engine.queue_callback(_sn_flush)
         _sn_pending.append((dwbar, row_stride, krsc, w, state))
+        _queue_flush()
         return None
     K, C, R, S = w.shape if w.dim() == 4 else (w.shape[0], w.shape[1], 1, 1)
     dw = torch.empty_like(w)
@@ -719,7 +791,8 @@ class ConvFn(torch.autograd.Function):
                 out, _last_stats = conv_fwd_bnstats(CONV_S1, x, wf, bias, res, flags)
             else:
                 out = conv_fwd(x, wf, torch.float32 if out_f32 else torch.bfloat16, bias, res, None, labels, packed, flags)
-        ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn)
+        ctx.save_for_backward(x, out if gate is not None else None, w if sn is not None else None, sn,
+                              bias if sn is not None else None)
         ctx.wflip, ctx.wshape = wflip, tuple(w.shape)
         ctx.has_bias, ctx.has_res, ctx.res_up = bias is not None, res is not None, res_up
         ctx.gated, ctx.premask_dx, ctx.grad_premasked = gate is not None, premask_dx, grad_premasked
@@ -727,7 +800,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, out, w_orig, sn = ctx.saved_tensors
+        x, out, w_orig, sn, bias_p = ctx.saved_tensors
         dout = dout.contiguous()
         if dout.dtype != x.dtype:
             dout = dout.to(x.dtype)                 # fp32-output convs: gradients re-enter the bf16 pipeline
@@ -745,7 +818,11 @@ class ConvFn(torch.autograd.Function):
                 dx = conv_fwd(dout, ctx.wflip, torch.bfloat16, None, None, x, None, None, EPI_POSMASK)
             else:
                 dx = conv_fwd(dout, ctx.wflip, torch.bfloat16)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if (SN_DEFER and WGRAD_GROUP and not f32 and sn is not None and ctx.needs_input_grad[1] and x.shape[1] * x.shape[2] <= 256
+                and w_orig.is_leaf and (bias_p is None or (bias_p.is_leaf and ctx.needs_input_grad[2]))):
+            # small-spatial layer: its weight gradient joins the grouped launch at the end of the backward pass
+            defer_wgrad(x, dout, R, S, w_orig, bias_p if ctx.has_bias else None, sn)
+        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             if f32:
                 dw_krsc, db = wgrad_f32(CONV_S1, x, dout, R, S, want_bias=ctx.has_bias)
                 dw_krsc = dw_krsc.reshape(K, R, S, C)
