@@ -596,3 +596,80 @@ def check_conv_bnstats():
         rows.append((tag + " running_mean", rel(rm0, rm1), F32_TOL))
         rows.append((tag + " running_var", rel(rv0, rv1), F32_TOL))
     return rows
+
+
+# ----------------------------------------------------------------------------- batched / grouped launch forms
+def check_batched_paths():
+    """The batched forms against their per-layer forms on identical inputs:
+    mcgm_conv_wgrad_grouped vs mcgm_conv_wgrad (different split-K factor: F32 tolerance),
+    mcgm_sn_weight_bwd_batched vs mcgm_sn_weight_bwd, mcgm_pack_weight_batched vs mcgm_pack_weight(_padded)."""
+    import ctypes as c
+    rows = []
+    g = torch.Generator().manual_seed(5)
+    # grouped weight gradients: 3 same-shape problems
+    for (N, H, Cin, Cout, R) in [(32, 8, 128, 128, 3), (16, 16, 128, 128, 1)]:
+        xs = [torch.randn(N, H, H, Cin, generator=g).to(DEV).to(torch.bfloat16) for _ in range(3)]
+        dys = [torch.randn(N, H, H, Cout, generator=g).to(DEV).to(torch.bfloat16) for _ in range(3)]
+        ref = [ops.conv_wgrad(x, dy, R, R, want_bias=True) for x, dy in zip(xs, dys)]
+        n = 3
+        dw = torch.empty(n, Cout, R, R, Cin, device=DEV)
+        db = torch.empty(n, Cout, device=DEV)
+        ws = torch.empty(_lib.query("mcgm_conv_wgrad_grouped_workspace_bytes", n, N, H, H, Cin, Cout, R, R) // 4, device=DEV)
+        _lib.call("mcgm_conv_wgrad_grouped", n, (c.c_void_p * n)(*[t.data_ptr() for t in xs]),
+                  (c.c_void_p * n)(*[t.data_ptr() for t in dys]), (c.c_void_p * n)(*[dw[i].data_ptr() for i in range(n)]),
+                  (c.c_void_p * n)(*[db[i].data_ptr() for i in range(n)]), N, H, H, Cin, Cout, R, R, ws.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+        for i in range(n):
+            rows.append((f"wgrad_grouped {N}x{H}x{H} {Cin}->{Cout} k{R} group {i}: dw", rel(dw[i], ref[i][0]), F32_TOL))
+            rows.append((f"wgrad_grouped {N}x{H}x{H} {Cin}->{Cout} k{R} group {i}: dbias", rel(db[i], ref[i][1]), F32_TOL))
+    # spectral-norm backward, batched (two items share one gradient) vs per layer
+    class _M:            # the minimum of a spectral-normed module that ops.SNBatch / sn_pack_all look at
+        pass
+    layers = []
+    for (K, C, R) in [(128, 128, 3), (128, 128, 1), (128, 3, 3)]:
+        w = torch.nn.Parameter((torch.randn(K, C, R, R, generator=g) * 0.1).to(DEV))
+        state = torch.cat([torch.rand(1, generator=g) + 0.5, torch.randn(K, generator=g), torch.randn(C * R * R, generator=g)]).to(DEV)
+        layers.append((w, state))
+    ops.SN_DEFER = True
+    try:
+        want = []
+        items = []
+        for (w, state) in layers:
+            K, C, R, _ = w.shape
+            for rep in range(2):
+                dwbar = torch.randn(K, R, R, C, generator=g).to(DEV)
+                items.append((dwbar, w, state))
+        ops.SN_DEFER = False
+        for (w, state) in layers:
+            acc = torch.zeros_like(w)
+            for (dwbar, w2, st) in items:
+                if w2 is w:
+                    acc += ops.sn_weight_bwd(dwbar, dwbar.shape[1] * dwbar.shape[2] * dwbar.shape[3], 1, w, st)
+            want.append(acc)
+        for (w, _) in layers:
+            w.grad = None
+        for (dwbar, w, st) in items:
+            ops._sn_pending.append((dwbar, dwbar.shape[1] * dwbar.shape[2] * dwbar.shape[3], 1, w, st))
+        ops._sn_flush()
+        for (w, _), ref_g in zip(layers, want):
+            rows.append((f"sn_weight_bwd_batched {tuple(w.shape)} (2 items, grad +=)", rel(w.grad, ref_g), F32_TOL))
+    finally:
+        ops.SN_DEFER = False
+    # batched packing
+    mods, states = [], {}
+    for (w, state) in layers:
+        m = _M()
+        m.weight_orig = w
+        mods.append(m)
+        states[m] = state
+    packs = ops.sn_pack_all(states)
+    for m in mods:
+        w, st = m.weight_orig, states[m]
+        if w.shape[1] <= 4:
+            ref_p = ops.pack_weight_padded(w.detach(), st[0:1], packs[m].shape[-1])
+            rows.append((f"pack_weight_batched padded {tuple(w.shape)}", float((packs[m].float() != ref_p.float()).sum()), EXACT))
+        else:
+            rf, rb = ops.pack_weight(w.detach(), st[0:1])
+            rows.append((f"pack_weight_batched KRSC {tuple(w.shape)}", float((packs[m][0].float() != rf.float()).sum()), EXACT))
+            rows.append((f"pack_weight_batched flipped {tuple(w.shape)}", float((packs[m][1].float() != rb.float()).sum()), EXACT))
+    return rows
