@@ -320,6 +320,14 @@ _wg_pending = []
 _flush_queued = False
 
 
+def reset_deferred():
+    """Drop queued end-of-backward work (left behind only when an earlier backward pass raised)."""
+    global _flush_queued
+    _sn_pending.clear()
+    _wg_pending.clear()
+    _flush_queued = False
+
+
 def _queue_flush():
     global _flush_queued
     if not _flush_queued:

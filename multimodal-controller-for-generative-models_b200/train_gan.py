@@ -129,7 +129,8 @@ def d_forward_backward(model, img, label, z):
         generated = model.generate(label, z)
     d_g = model.discriminate(generated, label)
     d_loss = hinge_d(d_x, d_g)
-    ops.SN_DEFER = True            # all 22 spectral-norm weight backwards of this pass: two launches at its end
+    ops.reset_deferred()
+    ops.SN_DEFER = True            # spectral-norm backwards and small-layer weight gradients: batched at the end of the pass
     try:
         d_loss.backward()
     finally:
