@@ -47,7 +47,7 @@ def launch_table(path, title):
         out.append(f"| `{k}` | {n} | {t / 1e6:.3f} | {100 * t / tot:.1f} % |")
     mine = sum(t for k, (n, t) in agg.items() if k.startswith("mcgm::"))
     out += ["", f"libmcgm kernels: {100 * mine / tot:.1f} % of kernel time; the rest are torch launches "
-            "(Adam multi-tensor, tiny reductions, casts, cuBLAS GEMV/GEMM of the two Linear layers).", ""]
+            "(gradient accumulation adds, layout copies, tiny reductions of the losses, cuBLAS GEMMs of the two Linear layers and of the upsample-conv weight transforms).", ""]
     return "\n".join(out)
 
 
