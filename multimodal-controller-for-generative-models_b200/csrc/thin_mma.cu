@@ -131,6 +131,7 @@ __device__ __forceinline__ void build_patches(const float* sImg, __nv_bfloat16* 
 // ---- forward: out[p, co] = epilogue(sum_k U[p,k] Wm[co,k]) -------------------------------------------
 // block = 8 warps; tile = 128 pixels x 128 output channels (loop over 128-channel slabs); warp w owns pixel
 // rows [16w, 16w+16).  smem: sU [128][40], sW [128][40], sOut [8][16][136] (bf16).
+template <bool GATE>
 __global__ void __launch_bounds__(kThinThreads, 3)
 thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ Wm, int w_stride,
                      const float* __restrict__ bias, const int32_t* __restrict__ labels,
@@ -182,7 +183,7 @@ thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restr
       // codebook words of the two rows this thread holds (requested before the MMAs, used after)
       const int r0 = lane >> 2, cq = (lane & 3) * 2;
       uint32_t m0[4] = {~0u, ~0u, ~0u, ~0u}, m1[4] = {~0u, ~0u, ~0u, ~0u};
-      if (bits != nullptr) {
+      if constexpr (GATE) {
         const long pa = p0 + warp * 16 + r0, pb = pa + 8;
         const int la = pa < P ? __ldg(labels + g.dhw.div((uint32_t)pa)) : 0;
         const int lb = pb < P ? __ldg(labels + g.dhw.div((uint32_t)pb)) : 0;
@@ -213,21 +214,31 @@ thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restr
           const float2 bb = *reinterpret_cast<const float2*>(sBias + col);
           float v00 = acc[n][0] + bb.x, v01 = acc[n][1] + bb.y, v10 = acc[n][2] + bb.x, v11 = acc[n][3] + bb.y;
           if (relu) { v00 = fmaxf(v00, 0.f); v01 = fmaxf(v01, 0.f); v10 = fmaxf(v10, 0.f); v11 = fmaxf(v11, 0.f); }
-          const uint32_t wa = m0[(nh + n) >> 2] >> (col & 31), wb = m1[(nh + n) >> 2] >> (col & 31);
-          v00 = (wa & 1u) ? v00 : 0.f; v01 = (wa & 2u) ? v01 : 0.f;
-          v10 = (wb & 1u) ? v10 : 0.f; v11 = (wb & 2u) ? v11 : 0.f;
+          if constexpr (GATE) {
+            const uint32_t wa = m0[(nh + n) >> 2] >> (col & 31), wb = m1[(nh + n) >> 2] >> (col & 31);
+            v00 = (wa & 1u) ? v00 : 0.f; v01 = (wa & 2u) ? v01 : 0.f;
+            v10 = (wb & 1u) ? v10 : 0.f; v11 = (wb & 2u) ? v11 : 0.f;
+          }
           *reinterpret_cast<__nv_bfloat162*>(so + r0 * 136 + col) = __floats2bfloat162_rn(v00, v01);
           *reinterpret_cast<__nv_bfloat162*>(so + (r0 + 8) * 136 + col) = __floats2bfloat162_rn(v10, v11);
         }
       }
       __syncwarp();
       // 16 rows x 256 B: one instruction writes two full rows
+      {
+        const int row0 = lane >> 4, c16 = lane & 15;
+        __nv_bfloat16* op = out + (p0 + warp * 16 + row0) * g.Cout + c0 + c16 * 8;
+        const __nv_bfloat16* sp = so + row0 * 136 + c16 * 8;
+        if (p0 + kThinTileP <= P && c0 + 128 <= g.Cout) {              // full tile: no per-row predicates
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int u = i * 32 + lane, row = u >> 4, c16 = u & 15;
-        const long p = p0 + warp * 16 + row;
-        if (p < P && c0 + c16 * 8 < g.Cout)
-          *reinterpret_cast<uint4*>(out + p * g.Cout + c0 + c16 * 8) = *reinterpret_cast<const uint4*>(so + row * 136 + c16 * 8);
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(op + (size_t)i * 2 * g.Cout) = *reinterpret_cast<const uint4*>(sp + i * 2 * 136);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (p0 + warp * 16 + row0 + 2 * i < P && c0 + c16 * 8 < g.Cout)
+              *reinterpret_cast<uint4*>(op + (size_t)i * 2 * g.Cout) = *reinterpret_cast<const uint4*>(sp + i * 2 * 136);
+        }
       }
       __syncwarp();
     }
@@ -359,15 +370,20 @@ extern "C" int mcgm_thin_conv_fwd(const float* img, const void* w_bf16, int w_ro
   if (int e = thin_geom(&g, N, H, W, Ct, R, S, Cout, kThinTileP)) return e;
   static bool configured = false;
   if (!configured) {
-    MCGM_CUDA(cudaFuncSetAttribute(thin_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kThinFwdSmem));
+    MCGM_CUDA(cudaFuncSetAttribute(thin_conv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThinFwdSmem));
+    MCGM_CUDA(cudaFuncSetAttribute(thin_conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThinFwdSmem));
     configured = true;
   }
   const long P = (long)N * H * W, tiles = (P + kThinTileP - 1) / kThinTileP;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   const long grid = tiles < (long)sms * 3 ? tiles : (long)sms * 3;      // three resident blocks per SM
-  thin_conv_fwd_kernel<<<(int)grid, kThinThreads, kThinFwdSmem, (cudaStream_t)stream>>>(
-      img, (const __nv_bfloat16*)w_bf16, w_row_stride, bias, labels, bits, (Cout + 31) / 32, relu, (__nv_bfloat16*)out_bf16, g, P, tiles);
+  if (bits != nullptr)
+    thin_conv_fwd_kernel<true><<<(int)grid, kThinThreads, kThinFwdSmem, (cudaStream_t)stream>>>(
+        img, (const __nv_bfloat16*)w_bf16, w_row_stride, bias, labels, bits, (Cout + 31) / 32, relu, (__nv_bfloat16*)out_bf16, g, P, tiles);
+  else
+    thin_conv_fwd_kernel<false><<<(int)grid, kThinThreads, kThinFwdSmem, (cudaStream_t)stream>>>(
+        img, (const __nv_bfloat16*)w_bf16, w_row_stride, bias, labels, bits, (Cout + 31) / 32, relu, (__nv_bfloat16*)out_bf16, g, P, tiles);
   MCGM_LAUNCH_CHECK();
   return 0;
 }
