@@ -163,6 +163,13 @@ thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restr
   fetch_window(img, g, (long)blockIdx.x * kThinTileP, P, kThinTileP, plan, win);
   for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
     const long p0 = t * kThinTileP;
+    int lab = 0;
+    uint32_t mw0[4] = {~0u, ~0u, ~0u, ~0u};
+    if constexpr (GATE) {                                // this tile's label and first codebook words: in flight early
+      lab = __ldg(labels + g.dhw.div((uint32_t)p0));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mw0[q] = (32 * q < g.Cout) ? __ldg(bits + (size_t)lab * words + q) : 0u;
+    }
     store_window(sImg, win);
     __syncthreads();                                     // window staged (and, first pass, the weight slab)
     build_patches(sImg, sU, plan);
@@ -180,17 +187,17 @@ thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restr
         ldsm_x4(a[0], sU + row * kThinKP + kofs);
         ldsm_x4(a[1], sU + row * kThinKP + 16 + kofs);
       }
-      // codebook words of the two rows this thread holds (requested before the MMAs, used after)
       const int r0 = lane >> 2, cq = (lane & 3) * 2;
-      uint32_t m0[4] = {~0u, ~0u, ~0u, ~0u}, m1[4] = {~0u, ~0u, ~0u, ~0u};
+      // a tile lies inside ONE image (checked on the host), so one label and one set of codebook words serve all
+      // of its rows; they were requested at the top of the tile (mw0), long before this point
+      uint32_t m0[4] = {~0u, ~0u, ~0u, ~0u};
       if constexpr (GATE) {
-        const long pa = p0 + warp * 16 + r0, pb = pa + 8;
-        const int la = pa < P ? __ldg(labels + g.dhw.div((uint32_t)pa)) : 0;
-        const int lb = pb < P ? __ldg(labels + g.dhw.div((uint32_t)pb)) : 0;
+        if (c0 == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          m0[q] = (c0 + 32 * q < g.Cout) ? __ldg(bits + (size_t)la * words + (c0 >> 5) + q) : 0u;
-          m1[q] = (c0 + 32 * q < g.Cout) ? __ldg(bits + (size_t)lb * words + (c0 >> 5) + q) : 0u;
+          for (int q = 0; q < 4; ++q) m0[q] = mw0[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m0[q] = (c0 + 32 * q < g.Cout) ? __ldg(bits + (size_t)lab * words + (c0 >> 5) + q) : 0u;
         }
       }
       // two halves of 8 n-tiles: 32 accumulator registers live instead of 64 (three blocks per SM); unrolled, so
@@ -215,9 +222,9 @@ thin_conv_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restr
           float v00 = acc[n][0] + bb.x, v01 = acc[n][1] + bb.y, v10 = acc[n][2] + bb.x, v11 = acc[n][3] + bb.y;
           if (relu) { v00 = fmaxf(v00, 0.f); v01 = fmaxf(v01, 0.f); v10 = fmaxf(v10, 0.f); v11 = fmaxf(v11, 0.f); }
           if constexpr (GATE) {
-            const uint32_t wa = m0[(nh + n) >> 2] >> (col & 31), wb = m1[(nh + n) >> 2] >> (col & 31);
+            const uint32_t wa = m0[(nh + n) >> 2] >> (col & 31);
             v00 = (wa & 1u) ? v00 : 0.f; v01 = (wa & 2u) ? v01 : 0.f;
-            v10 = (wb & 1u) ? v10 : 0.f; v11 = (wb & 2u) ? v11 : 0.f;
+            v10 = (wa & 1u) ? v10 : 0.f; v11 = (wa & 2u) ? v11 : 0.f;
           }
           *reinterpret_cast<__nv_bfloat162*>(so + r0 * 136 + col) = __floats2bfloat162_rn(v00, v01);
           *reinterpret_cast<__nv_bfloat162*>(so + (r0 + 8) * 136 + col) = __floats2bfloat162_rn(v10, v11);
