@@ -342,6 +342,20 @@ def _deferred_flush():
     _sn_flush()
 
 
+def _wgrad_chunks(items, limit=4):
+    """Split same-shape deferred items into launches of <= `limit`, never the same parameter (item[4]) twice in
+    one launch: its bias gradient is accumulated by ONE multi-tensor add per launch, which must not alias."""
+    chunks = []
+    for it in items:
+        for ch in chunks:
+            if len(ch) < limit and all(o[4] is not it[4] for o in ch):
+                ch.append(it)
+                break
+        else:
+            chunks.append([it])
+    return chunks
+
+
 def _wgrad_flush():
     """Grouped weight gradients of the queued (x, dout, R, S, weight_orig, bias, sn_state) items."""
     import ctypes as c
@@ -352,15 +366,7 @@ def _wgrad_flush():
         groups.setdefault((tuple(x.shape), dout.shape[-1], R, S, it[5] is not None), []).append(it)
     for (xs, Cout, R, S, has_bias), its in groups.items():
         N, H, W, Cin = xs
-        chunks = []                       # <= 4 items each, no parameter twice in a chunk (its bias gradient is
-        for it in its:                    # accumulated by one multi-tensor add per chunk)
-            for ch in chunks:
-                if len(ch) < 4 and all(o[4] is not it[4] for o in ch):
-                    ch.append(it)
-                    break
-            else:
-                chunks.append([it])
-        for chunk in chunks:
+        for chunk in _wgrad_chunks(its):
             n = len(chunk)
             dev = chunk[0][0].device
             dw = torch.empty(n, Cout, R, S, Cin, dtype=torch.float32, device=dev)

@@ -56,3 +56,19 @@ def test_fused_adam_has_no_cpu_path():
     from mcgm_b200 import train_gan
     opt = train_gan.make_optimizer(_net(), 2e-4, (0.0, 0.9))                # CPU parameters -> torch.optim.Adam
     assert isinstance(opt, torch.optim.Adam)
+
+
+def test_deferred_wgrad_chunking_never_aliases_a_parameter():
+    """ops._wgrad_chunks: launches of <= 4 same-shape items; the two passes (real / fake batch) of one layer
+    never share a launch, whatever order the backward pass queued them in."""
+    from mcgm_b200 import ops
+    params = [object() for _ in range(3)]
+    items = [(None, None, 3, 3, p, None, None) for p in params] + [(None, None, 3, 3, p, None, None) for p in params]
+    chunks = ops._wgrad_chunks(items)
+    assert sum(len(c) for c in chunks) == 6 and all(len(c) <= 4 for c in chunks)
+    for c in chunks:
+        assert len({id(it[4]) for it in c}) == len(c)
+    # 8 items of 4 layers (the 8x8 convs of a D update): two full launches
+    params = [object() for _ in range(4)]
+    chunks = ops._wgrad_chunks([(None, None, 3, 3, p, None, None) for p in params * 2])
+    assert [len(c) for c in chunks] == [4, 4]
