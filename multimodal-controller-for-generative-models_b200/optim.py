@@ -8,7 +8,9 @@ step is two or four kernel launches, never synchronises with the host and can be
 graph.  torch's multi-tensor path needs ~10 launches per step (plus a host round trip for the clip).
 
 The parameters stay the reference's ``nn.Parameter`` objects with the reference's names and shapes
-(``state_dict`` is unchanged); only their storage moves into the flat buffer.
+(``state_dict`` is unchanged, ``load_state_dict`` copies into the views); only their storage moves into
+the flat buffer.  Build the optimiser AFTER the model is on its device: ``model.to(...)`` afterwards
+would re-allocate the parameters and detach them from the buffers.
 """
 import torch
 
