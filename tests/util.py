@@ -35,7 +35,7 @@ def build_model(case, device="cpu"):
 
 def load_arrays(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    return {k: torch.from_numpy(z[k]) for k in z.files}
+    return {k: torch.from_numpy(z[k]) for k in z.files if z[k].dtype.kind != "U"}      # string arrays: read with numpy
 
 
 def d_strides(case):
