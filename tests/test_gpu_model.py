@@ -172,6 +172,41 @@ def test_config1_full_width_gradients_vs_oracle():
     assert errs[len(errs) // 2][0] < GRAD_MEDIAN_TOL
 
 
+def test_generate_after_create_and_transit_matches_oracle(golden):
+    """The reference's sampling utilities swap every controller's ``codebook`` buffer (create(): even to a
+    different number of modes; transit(): towards a root mode).  The kernels must pick the new rows up (the
+    packed device copy is re-derived) and the generator must still match the oracle run on the new codebooks."""
+    from mcgm_b200 import cfg
+    from mcgm_b200.models import utils as U
+    O, case, arr, model, _ = _setup(golden, "tiny_cifar")
+    model.train(True)
+    z = arr["zs"][0].cuda()
+    with torch.no_grad():
+        model.generate(arr["label"].cuda(), z)                      # packs the trained codebooks first
+    for mode in ("create", "transit"):
+        if mode == "create":
+            torch.manual_seed(5)
+            cfg["classes_size"] = 6
+            U.create(model)
+            n_modes = 6
+        else:
+            cfg["classes_size"] = case["classes"]
+            model = build_model(case, device="cuda").to("cuda")
+            model.train(True)
+            with torch.no_grad():
+                model.generate(arr["label"].cuda(), z)
+            U.transit(model, 3, 0.5)
+            n_modes = case["classes"]
+        cfg["classes_size"] = n_modes
+        label = arr["label"] % n_modes
+        sd = O.make_trainable({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        with torch.no_grad():
+            got = model.generate(label.cuda(), z)
+            want = O.generator(arr["zs"][0], O.one_hot(label, n_modes), sd)
+        assert rel_err(got.float().cpu(), want) < OUT_TOL, mode
+    cfg["classes_size"] = case["classes"]
+
+
 def test_bn_stats_in_conv_epilogue_equals_stats_pass():
     """cfg['bn_stats_in_conv']: the generator's BatchNorm statistics accumulated by the producing conv's
     epilogue give the same image, running statistics and gradients as the separate statistics pass
