@@ -38,6 +38,8 @@ extern "C" {
 #define MCGM_CONV_S2K4 1      /* 4x4 kernel, stride 2, pad 1: output = input / 2  (mcvae.py:41-49)   */
 #define MCGM_CONV_PHASE2 2    /* 4 output phases x 2x2 taps: output = 2 x input.  Nearest-up2 -> Conv3x3
                                  (mcgan.py:17-19) and ConvTranspose2d(4,2,1) (mcvae.py:87-92)          */
+#define MCGM_CONV_TAPS 3      /* stride 1, explicit (dh, dw) input offset per tap: the causal / cropped
+                                 vertical and horizontal stacks of the gated PixelCNN (mcpixelcnn.py:31-52) */
 
 #define MCGM_E_ARG (-1)      /* bad argument / unsupported shape */
 #define MCGM_E_CUDA (-2)     /* CUDA runtime / driver error */
@@ -226,6 +228,37 @@ size_t mcgm_conv_wgrad_ex_workspace_bytes(int kind, int in_dtype, int N, int H, 
 int mcgm_conv_wgrad_ex(int kind, int in_dtype, const void* x, const void* dy, float* dw, float* dbias,
                        int N, int H, int W, int Cin, int Cout, int R, int S, void* workspace, void* stream);
 
+/* ---- explicit-tap convolution (MCGM_CONV_TAPS) on the same tcgen05 kernels: w bf16 [Cout][n_taps][Cin],
+ *   out[n,i,j] = sum_t x[n, i + dh[t], j + dw[t]] . w[:, t, :]      (out-of-image taps read zeros)
+ * serves MCGatedMaskedConv2d (src/models/mcpixelcnn.py:23-61): a (k/2+1) x k vertical stack with padding
+ * (k/2, k/2) cropped to the first H rows is taps dh in [-k/2, 0], dw in [-k/2, k/2]; the 1 x (k/2+1) horizontal
+ * stack cropped to the first W columns is dh = 0, dw in [-k/2, 0]; the data gradient is the same call with negated
+ * offsets and the transposed weight.  taps_*_host are HOST arrays (n_taps <= 64 forward, <= 32 weight gradient).
+ * dw of the weight gradient is fp32 [Cout][n_taps][Cin]. */
+int mcgm_conv_fwd_taps(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin, int Cout,
+                       int n_taps, const signed char* taps_dh_host, const signed char* taps_dw_host,
+                       const float* bias, const void* res, const void* aux, const int32_t* labels,
+                       const uint32_t* bits, int M, int flags, void* stream);
+size_t mcgm_conv_wgrad_taps_workspace_bytes(int N, int H, int W, int Cin, int Cout, int n_taps);
+int mcgm_conv_wgrad_taps(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin, int Cout,
+                         int n_taps, const signed char* taps_dh_host, const signed char* taps_dw_host,
+                         void* workspace, void* stream);
+
+/* ---- MC-gated activation of the gated PixelCNN (MCGatedActivation, src/models/mcpixelcnn.py:9-20):
+ *   x, y = h.chunk(2, dim=1);  out = codebook[label] * relu(bn(x)) * sigmoid(y)
+ * h bf16 NHWC [N,H,W,2C] (x = channels [0,C), y = [C,2C) of each pixel row), out bf16 [N,H,W,C], HW = H*W.
+ * mcgm_sgate_stats: train-mode batch statistics of the x half (+ running-stat update: unbiased var, momentum).
+ * mcgm_sgate_bwd: dh = [dx | dy] bf16 [N,H,W,2C], dgamma / dbeta fp32 [C]; batch_stats = 1 when (mean, rstd)
+ * are this batch's statistics (training), 0 for running statistics.  workspace: mcgm_sgate_workspace_bytes(C). */
+size_t mcgm_sgate_workspace_bytes(int C);
+int mcgm_sgate_stats(const void* h, long P, int C, float* mean, float* rstd, float* running_mean, float* running_var,
+                     float momentum, float eps, void* workspace, void* stream);
+int mcgm_sgate_fwd(const void* h, void* out, int N, int HW, int C, const int32_t* labels, const uint32_t* bits, int M,
+                   const float* mean, const float* rstd, const float* gamma, const float* beta, void* stream);
+int mcgm_sgate_bwd(const void* dout, const void* h, void* dh, int N, int HW, int C, const int32_t* labels,
+                   const uint32_t* bits, int M, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, float* dgamma, float* dbeta, int batch_stats, void* workspace, void* stream);
+
 /* ---- thin convolutions on the tensor cores: im2col / col2im of the THIN tensor only.
  *   im2col : U[p, t*Ct + j] = thin[stride*p +/- off(t), j]  bf16 [N,Ho,Wo,KU], zero padded; off(t) =
  *            (r - pad, s - pad); flip: -off (stride 1 only).  stride 2 / 4x4 / pad 1 serves
@@ -302,6 +335,13 @@ int mcgm_flow_tail_bwd(const float* dout, const float* dlogdet, const float* y, 
                        const float* zscale, float* dy, float* dnet, float* dz_partial, int N, int HW, int C,
                        int net_ch, int affine, void* stream);
 
+/* The sampling direction of the coupling (AffineCoupling.reverse, src/models/mcglow.py:166-175):
+ * y = [out_a, out_b / sigmoid(net_s * exp(3 zscale_s) + 2) - net_t * exp(3 zscale_t)]   (additive: out_b - net * exp(3 zscale)).
+ * The rest of Flow.reverse (inverse 1x1 conv :114-116, ActNorm.reverse :54-55) is mcgm_flow_front_fwd with the
+ * parameters W' = diag(1/scale) W^-1, scale' = 1, loc' = -W (scale * loc) — see models/mcglow.py. */
+int mcgm_flow_tail_rev(const float* out, const float* net, const float* zscale, float* y, int N, int HW, int C,
+                       int net_ch, int affine, void* stream);
+
 /* ---- optimiser step on flat fp32 buffers (optim.Adam src/train_gan.py:223-236, eps 1e-8, no amsgrad;
  * clip_grad_norm_ + Adam src/train_vae.py:110-111, src/train_glow.py:120-121).  n must be a multiple of 4,
  * buffers 16-byte aligned.  `step` is a DEVICE int32 (number of updates applied so far; advanced by the
@@ -315,6 +355,12 @@ int mcgm_grad_clip_coef(const float* grad, long n, float max_norm, float* coef_o
 int mcgm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    const float* grad_scale_dev, void* stream);
+/* Same update with the hyper-parameters read from DEVICE memory: hyper_dev = [lr, beta1, beta2, eps,
+ * weight_decay, grad_scale] (6 floats).  A CUDA graph that captured this call follows later changes of
+ * optimizer.param_groups[0]['lr'] (ReduceLROnPlateau, src/train_vae.py:35,78-81) because the host stages the
+ * six values into that buffer before each replay. */
+int mcgm_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
+                       const float* hyper_dev, const float* grad_scale_dev, void* stream);
 
 /* ---- pooling / resampling helpers on bf16 NHWC (AvgPool2d(2) mcgan.py:81,88;
  * Upsample backward = 2x2 sum).  avgpool2: y[n,h,w,c] = scale * sum_{2x2} x;

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MCGM_LIB_PATH") or os.path.join(_HERE, "libmcgm.so")
 F32, BF16 = 0, 1
 GATE_BN, GATE_RELU, GATE_UP2, GATE_MASK, GATE_AFFINE = 1, 2, 4, 8, 16
 EPI_BIAS, EPI_RES, EPI_RES_UP2, EPI_RELU, EPI_MASK, EPI_TANH, EPI_POSMASK = 1, 2, 4, 8, 16, 32, 64
-CONV_S1, CONV_S2K4, CONV_PHASE2 = 0, 1, 2
+CONV_S1, CONV_S2K4, CONV_PHASE2, CONV_TAPS = 0, 1, 2, 3
 
 # name -> (restype, argtypes); every symbol of include/mcgm.h
 SIGNATURES = {
@@ -60,6 +60,18 @@ SIGNATURES = {
     "mcgm_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mcgm_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p]),
+    "mcgm_conv_fwd_taps": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcgm_conv_wgrad_taps_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mcgm_conv_wgrad_taps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcgm_sgate_workspace_bytes": (c_size_t, [c_int]),
+    "mcgm_sgate_stats": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                 c_void_p, c_void_p]),
+    "mcgm_sgate_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    "mcgm_sgate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mcgm_thin_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "mcgm_thin_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
@@ -87,10 +99,12 @@ SIGNATURES = {
                                    c_void_p]),
     "mcgm_flow_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcgm_flow_tail_rev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mcgm_grad_clip_workspace_bytes": (c_size_t, []),
     "mcgm_grad_clip_coef": (c_int, [c_void_p, c_long, c_float, c_void_p, c_void_p, c_void_p]),
     "mcgm_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_void_p, c_void_p]),
+    "mcgm_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcgm_debug_set": (c_int, [c_int, c_uint64]),
 }
 

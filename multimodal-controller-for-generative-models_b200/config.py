@@ -59,6 +59,8 @@ def process_control():
         cfg["vae"] = ({"hidden_size": [64, 128, 256], "latent_size": 128} if side == 32 else
                       {"hidden_size": [64, 128, 256, 512, 512], "latent_size": 256})
         cfg["vae"].update(num_res_block=2, embedding_size=32)
+    elif name in ("cpixelcnn", "mcpixelcnn"):                    # src/utils.py:139-143
+        cfg["pixelcnn"] = {"num_layer": 15, "hidden_size": 128, "num_embedding": 512}
     elif name in ("cglow", "mcglow"):
         cfg["glow"] = {"hidden_size": 512, "K": 16, "L": 3 if side == 32 else 5,
                        "affine": True, "conv_lu": True}

@@ -670,10 +670,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 //   stride-1 conv : AS = BS = 1, a = 0, b = (r-pad, s-pad)
 //   4x4 stride-2  : grid = dY grid, AS = 1, a = 0; BS = 2, b = (p-1, q-1)            (16 taps)
 //   phase conv    : grid = X grid,  AS = 2, a = (p-1, q-1); BS = 1, b = 0            (16 taps)
+static constexpr int kWgMaxTaps = 32;     // explicit-tap weight gradients (PixelCNN's 4x7 vertical stack: 28 taps)
 struct WgradParams {
   int N, Cin, Cout;
   int AS, BS;
-  signed char a_dh[kMaxTaps], a_dw[kMaxTaps], b_dh[kMaxTaps], b_dw[kMaxTaps];
+  signed char a_dh[kWgMaxTaps], a_dw[kWgMaxTaps], b_dh[kWgMaxTaps], b_dw[kWgMaxTaps];
   int KW, KH, KN, kb_w, kb_h;           // a k-block is a KN x KH x KW box of 64 grid pixels
   int total_kb, splits, kb_per_split;
   int cout_tiles, cin_tiles, taps, tap_groups;
@@ -1000,7 +1001,8 @@ struct WgradPlan {
 };
 
 // H, W are the dims of X
-static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl, int groups = 1) {
+static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout, int R, int S, WgradPlan* pl, int groups = 1,
+                      int n_taps = 0) {
   if (Cin % 64 || Cout % 64) return fail(MCGM_E_UNSUPPORTED, "wgrad: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
   pl->AS = pl->BS = 1;
   pl->a_shift = false;
@@ -1012,6 +1014,9 @@ static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout
     pl->Hg = H / 2; pl->Wg = W / 2; pl->taps = 16; pl->BS = 2;
   } else if (kind == MCGM_CONV_PHASE2) {
     pl->Hg = H; pl->Wg = W; pl->taps = 16; pl->AS = 2; pl->a_shift = true;
+  } else if (kind == MCGM_CONV_TAPS) {
+    if (n_taps < 1 || n_taps > kWgMaxTaps) return fail(MCGM_E_UNSUPPORTED, "wgrad: 1..%d explicit taps", kWgMaxTaps);
+    pl->Hg = H; pl->Wg = W; pl->taps = n_taps;
   } else {
     return fail(MCGM_E_ARG, "wgrad: unknown kind %d", kind);
   }
@@ -1093,7 +1098,8 @@ extern "C" int mcgm_unpack_wgrad(const float* dw_krsc, int K, int C, int R, int 
 static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, void* out, int out_dtype, int N, int H, int W,
                          int Cin, int Cout, int R, int S, const float* bias, const void* res, const void* aux,
                          const int32_t* labels, const uint32_t* bits, int M, int flags, void* stream,
-                         float* stats = nullptr, int* stat_slots_host = nullptr) {
+                         float* stats = nullptr, int* stat_slots_host = nullptr,
+                         const signed char* taps_dh = nullptr, const signed char* taps_dw = nullptr, int n_taps = 0) {
   MCGM_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv_fwd: bad arguments");
   MCGM_CHECK_ARG(out_dtype == MCGM_BF16 || out_dtype == MCGM_F32, "conv_fwd: out_dtype %d unsupported", out_dtype);
   MCGM_CHECK_ARG(in_dtype == MCGM_BF16 || in_dtype == MCGM_F32, "conv_fwd: in_dtype %d unsupported", in_dtype);
@@ -1126,6 +1132,12 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
         p.tap_dh[ph * kMaxTaps + t] = (signed char)(t / 2 - 1 + (ph >> 1));
         p.tap_dw[ph * kMaxTaps + t] = (signed char)(t % 2 - 1 + (ph & 1));
       }
+  } else if (kind == MCGM_CONV_TAPS) {
+    // stride-1 conv with an explicit list of (dh, dw) input offsets per tap: the causal / cropped stacks of the
+    // gated PixelCNN (src/models/mcpixelcnn.py:31-36, 48-52) — weight [Cout, n_taps, Cin]
+    MCGM_CHECK_ARG(taps_dh && taps_dw && n_taps >= 1 && n_taps <= 4 * kMaxTaps, "conv_fwd: TAPS needs 1..%d tap offsets", 4 * kMaxTaps);
+    p.Hg = H; p.Wg = W; p.Ho = H; p.Wo = W; p.T = n_taps;
+    for (int t = 0; t < n_taps; ++t) { p.tap_dh[t] = taps_dh[t]; p.tap_dw[t] = taps_dw[t]; }
   } else {
     return fail(MCGM_E_ARG, "conv_fwd: unknown kind %d", kind);
   }
@@ -1209,6 +1221,14 @@ extern "C" int mcgm_conv_fwd_ex(int kind, int in_dtype, const void* x, const voi
   return conv_fwd_impl(kind, in_dtype, x, w, out, out_dtype, N, H, W, Cin, Cout, R, S, bias, res, aux, labels, bits, M, flags, stream);
 }
 
+extern "C" int mcgm_conv_fwd_taps(const void* x, const void* w, void* out, int out_dtype, int N, int H, int W, int Cin,
+                                  int Cout, int n_taps, const signed char* taps_dh_host, const signed char* taps_dw_host,
+                                  const float* bias, const void* res, const void* aux, const int32_t* labels,
+                                  const uint32_t* bits, int M, int flags, void* stream) {
+  return conv_fwd_impl(MCGM_CONV_TAPS, MCGM_BF16, x, w, out, out_dtype, N, H, W, Cin, Cout, 0, 0, bias, res, aux, labels, bits, M,
+                       flags, stream, nullptr, nullptr, taps_dh_host, taps_dw_host, n_taps);
+}
+
 extern "C" size_t mcgm_conv_fwd_bnstats_bytes(int Cout) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
@@ -1233,7 +1253,8 @@ static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Ci
 
 static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* const* xs, const void* const* dys,
                                    float* const* dws, float* const* dbs, int N, int H, int W, int Cin, int Cout, int R, int S,
-                                   void* workspace, void* stream) {
+                                   void* workspace, void* stream, const signed char* taps_dh = nullptr,
+                                   const signed char* taps_dw = nullptr, int n_taps = 0) {
   MCGM_CHECK_ARG(n >= 1 && n <= kWgMaxGroups && xs && dys && dws && workspace && N > 0, "conv_wgrad: bad arguments (1..%d groups)", kWgMaxGroups);
   // MN-major TF32 operands need the 128B/32B-atom swizzle on both the TMA and the UMMA side; with the plain
   // 128B swizzle used here the tensor cores return zeros (measured).  The fp32 parity pipeline therefore
@@ -1244,12 +1265,14 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   for (int g = 0; g < n; ++g)
     MCGM_CHECK_ARG(xs[g] && dys[g] && dws[g] && (!want_bias || dbs[g]), "conv_wgrad: group %d has a NULL pointer", g);
   WgradPlan pl;
-  if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl, n)) return e;
+  if (int e = plan_wgrad(kind, tf32, N, H, W, Cin, Cout, R, S, &pl, n, n_taps)) return e;
+  if (kind == MCGM_CONV_TAPS) MCGM_CHECK_ARG(taps_dh && taps_dw, "conv_wgrad: TAPS needs the tap offsets");
   WgradParams p{};
   p.N = N; p.Cin = Cin; p.Cout = Cout; p.AS = pl.AS; p.BS = pl.BS;
   for (int t = 0; t < pl.taps; ++t) {
     if (kind == MCGM_CONV_S1) { p.b_dh[t] = (signed char)(t / S - (R - 1) / 2); p.b_dw[t] = (signed char)(t % S - (S - 1) / 2); }
     else if (kind == MCGM_CONV_S2K4) { p.b_dh[t] = (signed char)(t / 4 - 1); p.b_dw[t] = (signed char)(t % 4 - 1); }
+    else if (kind == MCGM_CONV_TAPS) { p.b_dh[t] = taps_dh[t]; p.b_dw[t] = taps_dw[t]; }
     else { p.a_dh[t] = (signed char)(t / 4 - 1); p.a_dw[t] = (signed char)(t % 4 - 1); }
   }
   p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = pl.Wg / pl.KW; p.kb_h = pl.Hg / pl.KH;
@@ -1327,6 +1350,20 @@ extern "C" int mcgm_conv_wgrad_grouped(int n, const void* const* x_host, const v
                                        void* workspace, void* stream) {
   return conv_wgrad_grouped_impl(MCGM_CONV_S1, MCGM_BF16, n, x_host, dy_host, dw_host, dbias_host, N, H, W, Cin, Cout, R, S,
                                  workspace, stream);
+}
+
+// Explicit-tap weight gradient: dw fp32 [Cout, n_taps, Cin], x pixel of tap t = dy pixel + (dh, dw)[t].
+extern "C" size_t mcgm_conv_wgrad_taps_workspace_bytes(int N, int H, int W, int Cin, int Cout, int n_taps) {
+  WgradPlan pl;
+  if (plan_wgrad(MCGM_CONV_TAPS, 0, N, H, W, Cin, Cout, 0, 0, &pl, 1, n_taps)) return 0;
+  return ((size_t)pl.splits * pl.per_split + (size_t)pl.splits * 4 * Cout) * sizeof(float);
+}
+extern "C" int mcgm_conv_wgrad_taps(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
+                                    int Cout, int n_taps, const signed char* taps_dh_host, const signed char* taps_dw_host,
+                                    void* workspace, void* stream) {
+  MCGM_CHECK_ARG(x && dy && dw && workspace && N > 0, "conv_wgrad_taps: bad arguments");
+  return conv_wgrad_grouped_impl(MCGM_CONV_TAPS, MCGM_BF16, 1, &x, &dy, &dw, dbias ? &dbias : nullptr, N, H, W, Cin, Cout, 0, 0,
+                                 workspace, stream, taps_dh_host, taps_dw_host, n_taps);
 }
 
 extern "C" size_t mcgm_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S) {

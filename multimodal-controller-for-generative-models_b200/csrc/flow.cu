@@ -211,6 +211,32 @@ flow_tail_fwd_kernel(const float* __restrict__ y, const float* __restrict__ net,
   if (threadIdx.x == 0 && logdet != nullptr) logdet[n] = tot;
 }
 
+// The sampling direction (AffineCoupling.reverse, src/models/mcglow.py:166-175): given the coupling's OUTPUT
+// `outp` and the network evaluated on its first half, in_b = out_b / sigmoid(log_s + 2) - t  (additive:
+// in_b = out_b - net_out); the first half passes through.
+__global__ void __launch_bounds__(kFlowThreads)
+flow_tail_rev_kernel(const float* __restrict__ outp, const float* __restrict__ net, const float* __restrict__ zscale,
+                     float* __restrict__ y, long P, int C, int net_ch, int affine) {
+  const int half = C >> 1;
+  const long total = P * half;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long p = e / half;
+    const int c = (int)(e - p * half);
+    const float out_a = outp[p * C + c], out_b = outp[p * C + half + c];
+    float ib;
+    if (affine) {
+      const float ls = net[p * net_ch + c] * expf(3.0f * zscale[c]) + 2.0f;
+      const float t = net[p * net_ch + half + c] * expf(3.0f * zscale[half + c]);
+      const float s = 1.0f / (1.0f + expf(-ls));
+      ib = out_b / s - t;
+    } else {
+      ib = out_b - net[p * net_ch + c] * expf(3.0f * zscale[c]);
+    }
+    y[p * C + c] = out_a;
+    y[p * C + half + c] = ib;
+  }
+}
+
 // dy (grad of the front's y), dnet (grad of the network output, all net_ch channels written), and the
 // per-sample partial of dzscale [N][nz] (nz = C affine, C/2 additive): dzscale[c] = 3 * sum dh*h.
 __global__ void __launch_bounds__(kFlowThreads)
@@ -329,6 +355,20 @@ extern "C" int mcgm_flow_tail_fwd(const float* y, const float* net, const float*
   MCGM_CHECK_ARG(!affine || logdet, "flow_tail_fwd: affine coupling needs a logdet output");
   if (N == 0) return 0;
   flow_tail_fwd_kernel<<<N, kFlowThreads, 0, (cudaStream_t)stream>>>(y, net, zscale, out, logdet, HW, C, net_ch, affine);
+  MCGM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcgm_flow_tail_rev(const float* out, const float* net, const float* zscale, float* y, int N, int HW, int C,
+                                  int net_ch, int affine, void* stream) {
+  MCGM_CHECK_ARG(out && net && zscale && y && N >= 0 && HW > 0, "flow_tail_rev: bad arguments");
+  if (int e = flow_check((long)N * HW, C)) return e;
+  MCGM_CHECK_ARG(net_ch >= (affine ? C : C / 2), "flow_tail_rev: network output has %d channels, need %d", net_ch, affine ? C : C / 2);
+  if (N == 0) return 0;
+  const long total = (long)N * HW * (C / 2);
+  long blocks = (total + kFlowThreads - 1) / kFlowThreads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  flow_tail_rev_kernel<<<(int)blocks, kFlowThreads, 0, (cudaStream_t)stream>>>(out, net, zscale, y, (long)N * HW, C, net_ch, affine);
   MCGM_LAUNCH_CHECK();
   return 0;
 }

@@ -54,7 +54,13 @@ __global__ void clip_coef_kernel(const float* __restrict__ partial, int nblocks,
 __global__ void __launch_bounds__(kOptThreads)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long n4, const int* __restrict__ step, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, float grad_scale, const float* __restrict__ gscale_dev) {
+                 float weight_decay, float grad_scale, const float* __restrict__ gscale_dev,
+                 const float* __restrict__ hyper_dev) {
+  if (hyper_dev != nullptr) {     // [lr, beta1, beta2, eps, weight_decay, grad_scale] in device memory: a captured
+    lr = __ldg(hyper_dev);        // graph replays with whatever the host last staged there (lr schedulers)
+    beta1 = __ldg(hyper_dev + 1); beta2 = __ldg(hyper_dev + 2); eps = __ldg(hyper_dev + 3);
+    weight_decay = __ldg(hyper_dev + 4); grad_scale = __ldg(hyper_dev + 5);
+  }
   const double t = (double)(__ldg(step) + 1);
   const float bc1 = (float)(1.0 - pow((double)beta1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
@@ -113,9 +119,9 @@ extern "C" int mcgm_grad_clip_coef(const float* grad, long n, float max_norm, fl
   return 0;
 }
 
-extern "C" int mcgm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
-                              const float* grad_scale_dev, void* stream) {
+static int adam_step_impl(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                          const float* grad_scale_dev, const float* hyper_dev, void* stream) {
   MCGM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step && n >= 0 && n % 4 == 0,
                  "adam_step: bad arguments (n must be a multiple of 4)");
   MCGM_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
@@ -123,9 +129,23 @@ extern "C" int mcgm_adam_step(float* param, const float* grad, float* exp_avg, f
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   adam_step_kernel<<<opt_grid(n / 4), kOptThreads, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n / 4, step, lr, beta1, beta2,
-                                                          eps, weight_decay, grad_scale, grad_scale_dev);
+                                                          eps, weight_decay, grad_scale, grad_scale_dev, hyper_dev);
   MCGM_LAUNCH_CHECK();
   adam_advance_kernel<<<1, 32, 0, st>>>(step);
   MCGM_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mcgm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                              const float* grad_scale_dev, void* stream) {
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                        grad_scale_dev, nullptr, stream);
+}
+
+extern "C" int mcgm_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, int* step,
+                                  const float* hyper_dev, const float* grad_scale_dev, void* stream) {
+  MCGM_CHECK_ARG(hyper_dev, "adam_step_dev: hyper_dev is NULL");
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, n, step, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, grad_scale_dev, hyper_dev,
+                        stream);
 }

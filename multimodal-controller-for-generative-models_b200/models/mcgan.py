@@ -91,6 +91,16 @@ def _labels_from_indicator(indicator):
         return indicator
     if indicator.dim() != 2:
         raise ValueError('Not valid indicator')
+    # The reference computes code = indicator @ codebook (src/modules/modules.py:73): only for a ONE-HOT
+    # indicator is that the row gather the fused blocks perform.  A soft / multi-hot indicator would silently
+    # give a different network, so it is rejected (one host sync; the training steps pass integer labels and
+    # never come here; skipped while a CUDA graph is being captured, where a sync is illegal).
+    if not (indicator.is_cuda and torch.cuda.is_current_stream_capturing()):
+        ones = (indicator == 1).sum(dim=1)
+        nonzero = (indicator != 0).sum(dim=1)
+        if not bool(((ones == 1) & (nonzero == 1)).all()):
+            raise ValueError('Not valid indicator: the fused blocks take a one-hot [N, num_mode] indicator or integer '
+                             'labels [N] (use MultimodalController.forward for a dense code)')
     return indicator.argmax(dim=1)
 
 
@@ -146,18 +156,18 @@ def _bn_gate(x, bn, mc, ctx, training, up=False, want_raw=False, pre_stats=None)
     """pre_stats: ops.ConvStats of x from the epilogue of the conv that produced it (training only)."""
     flags = GATE_BN | GATE_RELU | GATE_MASK | (GATE_UP2 if up else 0)
     if training:
-        y, raw = ops.GateFn.apply(x, bn.weight, bn.bias, ctx.labels, mc.packed(), flags, bn.running_mean,
+        y, raw = ops.GateFn.apply(x, bn.weight, bn.bias, ctx.labels, mc.packed_bits(), flags, bn.running_mean,
                                   bn.running_var, bn.momentum, bn.eps, want_raw, pre_stats)
         bn.num_batches_tracked += 1
         return y, raw
     # eval: running statistics (inference path; no autograd through the gate)
     rstd = torch.rsqrt(bn.running_var + bn.eps)
-    return ops.gate_fwd(x, flags, ctx.labels, mc.packed(), bn.running_mean, rstd, bn.weight.detach(),
+    return ops.gate_fwd(x, flags, ctx.labels, mc.packed_bits(), bn.running_mean, rstd, bn.weight.detach(),
                         bn.bias.detach(), want_raw)
 
 
 def _relu_gate(x, mc, ctx, want_raw=False):
-    return ops.GateFn.apply(x, None, None, ctx.labels, mc.packed(), GATE_RELU | GATE_MASK, None, None, 0.0, 0.0,
+    return ops.GateFn.apply(x, None, None, ctx.labels, mc.packed_bits(), GATE_RELU | GATE_MASK, None, None, 0.0, 0.0,
                             want_raw)
 
 
@@ -244,7 +254,7 @@ class FirstDisResBlock(nn.Module):
         """img: fp32 NHWC [N,H,W,3] (mcgan.py:72-93).  AvgPool is linear, so conv2 + shortcut are
         summed at full resolution in conv2's epilogue and pooled once."""
         c1, c2, sc = self.conv[0].module, self.conv[3].module, self.shortcut[0].module
-        h = ops.WideFromThinFn.apply(img, c1.weight_orig, c1.bias, (ctx.labels, self.mc_1.packed()), True, ctx.sn[c1],
+        h = ops.WideFromThinFn.apply(img, c1.weight_orig, c1.bias, (ctx.labels, self.mc_1.packed_bits()), True, ctx.sn[c1],
                                      1, None, ctx.sn_packs.get(c1))
         s = ops.WideFromThinFn.apply(img, sc.weight_orig, sc.bias, None, False, ctx.sn[sc], 1, None, ctx.sn_packs.get(sc))
         y = _conv(h, c2, ctx, res=s, premask_dx=True)
@@ -272,7 +282,7 @@ class DisResBlock(nn.Module):
     def fused(self, x, ctx):
         has_sc = len(self.shortcut) > 0
         a, s = _relu_gate(x, self.mc_1, ctx, want_raw=has_sc)
-        h = _conv(a, self.conv[2].module, ctx, gate=(ctx.labels, self.mc_2.packed()), grad_premasked=True)
+        h = _conv(a, self.conv[2].module, ctx, gate=(ctx.labels, self.mc_2.packed_bits()), grad_premasked=True)
         res = _conv(s, self.shortcut[1].module, ctx) if has_sc else x
         y = _conv(h, self.conv[5].module, ctx, res=res, premask_dx=True)
         return ops.Pool2Fn.apply(y) if self.stride > 1 else y

@@ -136,7 +136,24 @@ class ZeroConv2d(nn.Module):
         self.scale = nn.Parameter(torch.zeros(1, output_size, 1, 1))
 
     def forward(self, input):
+        """NCHW reference formulation (kept for outside callers; the model itself uses ``forward_nhwc``)."""
         return self.conv(input) * torch.exp(self.scale * 3)
+
+    def forward_nhwc(self, x):
+        """fp32 NHWC [N,H,W,Cin] (Cin <= 64) -> fp32 NHWC [N,H,W,Cout] on the tcgen05 conv: input channels
+        zero-padded to 64 (bf16 operand), output channels computed as a multiple of 64 (zero weight rows) and
+        sliced; autograd reaches conv.weight / conv.bias / scale through the pads."""
+        cout = self.conv.out_channels
+        cp = (cout + 63) // 64 * 64
+        xa = _pad_to(x, 3, 64).to(torch.bfloat16).contiguous()
+        w = _pad_to(_pad_to(self.conv.weight, 1, 64), 0, cp)
+        h = _conv(xa, w, _pad_to(self.conv.bias, 0, cp), True)[..., :cout]
+        return h * torch.exp(self.scale.view(1, 1, 1, -1) * 3)
+
+    def of_zeros(self, n, h, w):
+        """``forward(zeros)`` in NHWC without a conv: a conv of an all-zero input is its bias."""
+        v = self.conv.bias.view(1, 1, 1, -1) * torch.exp(self.scale.view(1, 1, 1, -1) * 3)
+        return v.expand(n, h, w, -1)
 
 
 def _pad_to(t, dim, size):
@@ -176,7 +193,7 @@ class AffineCoupling(nn.Module):
         if actnorm.needs_init():
             hf = h.detach().float()
             actnorm.initialize_from(hf.mean(dim=(0, 1, 2)), hf.std(dim=(0, 1, 2)))
-        return ops.ActNormGateFn.apply(h, actnorm.scale, actnorm.loc, ctx.labels, mc.packed())
+        return ops.ActNormGateFn.apply(h, actnorm.scale, actnorm.loc, ctx.labels, mc.packed_bits())
 
     def net_nhwc(self, xa, ctx):
         """xa: bf16 NHWC [N,H,W,64] (C/2 live channels) -> RAW zero-conv output fp32 NHWC [N,H,W,64]
@@ -203,6 +220,7 @@ class AffineCoupling(nn.Module):
         return out, (logdet if self.affine else None)
 
     def reverse(self, output, ctx):
+        """NCHW reference formulation (src/models/mcglow.py:166-175) on the coupling-network kernels."""
         out_a, out_b = output.chunk(2, 1)
         if self.affine:
             log_s, t = self.run_net(out_a, ctx).chunk(2, 1)
@@ -210,6 +228,11 @@ class AffineCoupling(nn.Module):
         else:
             in_b = out_b - self.run_net(out_a, ctx)
         return torch.cat([out_a, in_b], 1)
+
+    def reverse_nhwc(self, output, xa, ctx):
+        """output fp32 NHWC [N,H,W,C], xa = its first half as the network's bf16 input -> y fp32 NHWC."""
+        return ops.flow_tail_rev(output, self.net_nhwc(xa, ctx), self.net[8].module.scale.detach().reshape(-1).contiguous(),
+                                 self.affine)
 
 
 class Flow(nn.Module):
@@ -237,6 +260,18 @@ class Flow(nn.Module):
     def reverse(self, output, ctx):
         return self.actnorm.reverse(self.invconv.reverse(self.coupling.reverse(output, ctx)))
 
+    def reverse_nhwc(self, output, xa, ctx):
+        """Flow.reverse (src/models/mcglow.py:195-201) on fp32 NHWC through the native kernels (no autograd: this
+        is the sampling path).  -> (x, bf16 network input of the flow that is inverted next)."""
+        y = self.coupling.reverse_nhwc(output, xa, ctx)
+        an = self.actnorm
+        W = self.invconv.calc_weight()[:, :, 0, 0].detach()
+        scale, loc = an.scale.detach().reshape(-1), an.loc.detach().reshape(-1)
+        # x = (W^-1 y) / scale - loc  ==  W' (1 * (y + loc'))   with  W' = diag(1/scale) W^-1,  loc' = -W (scale * loc)
+        w_rev = (torch.linalg.inv(W) / scale[:, None]).contiguous()
+        loc_rev = (-(W @ (scale * loc))).contiguous()
+        return ops.flow_front(y.contiguous(), loc_rev, torch.ones_like(scale), w_rev)
+
 
 class Block(nn.Module):
     def __init__(self, input_size, hidden_size, K, split=True, affine=True, conv_lu=True, num_mode=None,
@@ -258,30 +293,32 @@ class Block(nn.Module):
             out, det = flow(out, ctx)
             logdet = logdet + det
         if self.split:
-            out, z_new = out.chunk(2, 3)
-            z_new = z_new.permute(0, 3, 1, 2)                       # NCHW views of the (small) NHWC halves
-            mean, log_sd = self.prior(out.permute(0, 3, 1, 2)).chunk(2, 1)
-            log_p = gaussian_log_p(z_new, mean, log_sd).reshape(b, -1).sum(1)
+            out, z_nhwc = out.chunk(2, 3)
+            mean, log_sd = self.prior.forward_nhwc(out).chunk(2, 3)        # ZeroConv2d on the tcgen05 conv
         else:
-            z_new = out.permute(0, 3, 1, 2)
-            mean, log_sd = self.prior(torch.zeros_like(z_new)).chunk(2, 1)
-            log_p = gaussian_log_p(z_new, mean, log_sd).reshape(b, -1).sum(1)
-        return out, logdet, log_p, z_new
+            z_nhwc = out
+            mean, log_sd = self.prior.of_zeros(b, h // 2, w // 2).chunk(2, 3)   # prior(zeros) = its bias
+        log_p = gaussian_log_p(z_nhwc, mean, log_sd).reshape(b, -1).sum(1)
+        return out, logdet, log_p, z_nhwc.permute(0, 3, 1, 2)             # z_new: NCHW view of the (small) NHWC half
 
     def reverse(self, output, ctx, eps=None, reconstruct=False):
-        input = output
+        """Block.reverse (src/models/mcglow.py:241-265) on fp32 NHWC tensors: output / eps [N,h,w,c] ->
+        [N,2h,2w,c'] (un-squeezed).  Sampling path: runs without autograd."""
+        x = output
         if reconstruct:
-            input = torch.cat([output, eps], 1) if self.split else eps
+            x = torch.cat([output, eps], 3) if self.split else eps
         elif self.split:
-            mean, log_sd = self.prior(input).chunk(2, 1)
-            input = torch.cat([output, gaussian_sample(eps, mean, log_sd)], 1)
+            mean, log_sd = self.prior.forward_nhwc(x).chunk(2, 3)
+            x = torch.cat([output, gaussian_sample(eps, mean, log_sd)], 3)
         else:
-            mean, log_sd = self.prior(torch.zeros_like(input)).chunk(2, 1)
-            input = gaussian_sample(eps, mean, log_sd)
+            mean, log_sd = self.prior.of_zeros(*x.shape[:3]).chunk(2, 3)
+            x = gaussian_sample(eps, mean, log_sd)
+        x = x.contiguous()
+        xa = _pad_to(x[..., :x.shape[3] // 2], 3, ops.FLOW_XA_CH).to(torch.bfloat16).contiguous()
         for flow in self.flows[::-1]:
-            input = flow.reverse(input, ctx)
-        b, c, h, w = input.shape
-        return input.reshape(b, c // 4, 2, 2, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b, c // 4, h * 2, w * 2)
+            x, xa = flow.reverse_nhwc(x, xa, ctx)
+        b, h, w, c = x.shape
+        return x.reshape(b, h, w, c // 4, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(b, h * 2, w * 2, c // 4)
 
 
 class MCGlow(nn.Module):
@@ -327,11 +364,15 @@ class MCGlow(nn.Module):
         return {'loss': self.loss_fn(log_p_sum, logdet), 'z': z}
 
     def reverse(self, input):
+        """{'z': [NCHW...], 'label', 'reconstruct'} -> {'img'} (src/models/mcglow.py:314-325).  The chain runs in
+        NHWC on the native kernels, without autograd (it is the sampling path)."""
         ctx = _Ctx(_labels_from_indicator(input['label']))
-        z, x = input['z'], None
-        for i, block in enumerate(self.blocks[::-1]):
-            x = block.reverse(z[-1] if i == 0 else x, ctx, eps=z[-(i + 1)], reconstruct=input['reconstruct'])
-        return {'img': torch.clamp(x, -.5, .5) * 2}
+        with torch.no_grad():
+            z = [t.detach().float().permute(0, 2, 3, 1).contiguous() for t in input['z']]
+            x = None
+            for i, block in enumerate(self.blocks[::-1]):
+                x = block.reverse(z[-1] if i == 0 else x, ctx, eps=z[-(i + 1)], reconstruct=input['reconstruct'])
+            return {'img': (torch.clamp(x, -.5, .5) * 2).permute(0, 3, 1, 2)}
 
     def make_z_shapes(self):
         C, H, W = self.data_shape

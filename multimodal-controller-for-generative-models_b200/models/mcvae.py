@@ -37,12 +37,12 @@ def _w(module):
 def _gate(x, bn, mc, ctx, training, relu=True):
     flags = GATE_BN | GATE_MASK | (GATE_RELU if relu else 0)
     if training:
-        y, _ = ops.GateFn.apply(x, bn.weight, bn.bias, ctx.labels, mc.packed(), flags, bn.running_mean,
+        y, _ = ops.GateFn.apply(x, bn.weight, bn.bias, ctx.labels, mc.packed_bits(), flags, bn.running_mean,
                                 bn.running_var, bn.momentum, bn.eps, False)
         bn.num_batches_tracked += 1
         return y
     rstd = torch.rsqrt(bn.running_var + bn.eps)
-    return ops.gate_fwd(x, flags, ctx.labels, mc.packed(), bn.running_mean, rstd, bn.weight.detach(),
+    return ops.gate_fwd(x, flags, ctx.labels, mc.packed_bits(), bn.running_mean, rstd, bn.weight.detach(),
                         bn.bias.detach(), False)[0]
 
 
@@ -135,7 +135,7 @@ class Decoder(nn.Module):
         lin, bn1 = self.linear[1].module, self.linear[2].module
         h = F.relu(bn1(F.linear(h, lin.weight, lin.bias)))                      # [N, 4096]: cuBLAS + ATen BN1d
         h = h.view(h.size(0), *self.encoded_shape).permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-        h = ops.MCMaskFn.apply(h, ctx.labels, self.blocks[0].packed(), None, False)
+        h = ops.MCMaskFn.apply(h, ctx.labels, self.blocks[0].packed_bits(), None, False)
         i = 1
         for _ in range(self.num_res_block):
             h = self.blocks[i].fused(h, ctx)

@@ -32,7 +32,7 @@ def make_SpectralNormalization(m):
 # The callers of the MultimodalController boundary that REPLACE its ``codebook`` buffer:
 # generate.py / create.py / transit.py of the reference go through src/models/utils.py:34-152.  For the
 # mc* families the only state they touch is the codebook; the packed device copy the kernels read is re-derived
-# by ``MultimodalController.packed()`` whenever the buffer object changes, so these work unchanged on the B200
+# by ``MultimodalController.packed_bits()`` whenever the buffer object changes, so these work unchanged on the B200
 # path.  (The embedding branches of the reference serve the c* baselines, which are out of scope.)
 def _is_controller(module):
     return module.__class__.__name__ == 'MultimodalController'       # by NAME, as the reference selects them

@@ -27,6 +27,7 @@ class MultimodalController(nn.Module):
         self.register_buffer('codebook', self.make_codebook())
         self._packed = None
         self._packed_key = None
+        self._packed_src = None
 
     def make_codebook(self):
         """Fixed binary codebook, bit-identical to the reference for the same RNG state.
@@ -52,8 +53,10 @@ class MultimodalController(nn.Module):
     def packed(self):
         """Bit-packed codebook on the buffer's device, rebuilt if the buffer changed."""
         cb = self.codebook
-        key = (id(cb), cb._version, tuple(cb.shape), cb.device)
-        if self._packed is None or self._packed_key != key:
+        key = (cb._version, tuple(cb.shape), cb.device)
+        # the source tensor itself is part of the key (compared with `is`): create() / transit() replace the
+        # buffer object, and the id() of a freed tensor can be handed to its successor
+        if self._packed is None or self._packed_src is not cb or self._packed_key != key:
             if cb.dtype != torch.float32:
                 raise ValueError('Not valid codebook dtype')
             if not bool(((cb == 0) | (cb == 1)).all()):
@@ -61,7 +64,16 @@ class MultimodalController(nn.Module):
             else:
                 self._packed = ops.PackedCodebook(cb.contiguous())
             self._packed_key = key
+            self._packed_src = cb
         return self._packed
+
+    def packed_bits(self):
+        """``packed()`` for the fused blocks, which gather mask rows by label from the bit-packed copy only."""
+        packed = self.packed()
+        if packed is False:
+            raise ValueError('Not valid codebook: the fused blocks need a binary {0,1} codebook (a non-binary one '
+                             'only works through MultimodalController.forward, which multiplies by the dense code)')
+        return packed
 
     def forward(self, input):
         x, indicator = input[0], input[1]

@@ -56,22 +56,29 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(ev, tag, work, desc=""):
+def _prof_end(ev, tag, work, desc="", ref_work=None):
+    """work: EXECUTED algorithmic work of the launch (flops the tensor cores run / bytes the kernel must move);
+    ref_work: the same launch booked at the reference op's count when that differs (Up2->Conv3x3 executes 4 of
+    the reference's 9 taps per output) — reported separately as ``frac_reference_op``, never as the roofline."""
     if ev is None:
         return
     end = torch.cuda.Event(enable_timing=True)
     end.record()
-    PROFILE.setdefault(tag, []).append((ev, end, work, desc))
+    PROFILE.setdefault(tag, []).append((ev, end, work, desc, work if ref_work is None else ref_work))
 
 
 _workspaces = {}
+_retired_workspaces = []      # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def _workspace(tag, nbytes, device):
-    """Persistent per-(tag, device) scratch buffer, grown on demand (never shrinks)."""
+    """Persistent per-(tag, device) scratch buffer, grown on demand (never shrinks, never freed: a CUDA graph
+    captured while a smaller buffer was current keeps replaying into that buffer's address)."""
     key = (tag, device)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired_workspaces.append(buf)
         buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
@@ -194,8 +201,9 @@ def conv_fwd_bnstats(kind, x, w, bias=None, res=None, flags=0):
     ev = _prof_begin()
     _lib.call("mcgm_conv_fwd_bnstats", kind, x.data_ptr(), w.data_ptr(), out.data_ptr(), N, H, W, Cin, Cout, R, S,
               _ptr(bias), _ptr(res), flags, partial.data_ptr(), ctypes.byref(slots), _stream())
-    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * taps,
-              f"conv+bnstats kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}")
+    ex_taps = 4 if kind == CONV_PHASE2 else taps
+    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ex_taps,
+              f"conv+bnstats kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}", 2.0 * N * Ho * Wo * Cout * Cin * taps)
     return out, ConvStats(partial, slots.value, N * Ho * Wo)
 
 
@@ -504,8 +512,11 @@ class SNScaleFn(torch.autograd.Function):
 
 
 def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None, labels=None, packed=None,
-             flags=0):
-    """Implicit-GEMM conv (tcgen05): x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> [N,H,W,Cout]."""
+             flags=0, thin=False):
+    """Implicit-GEMM conv (tcgen05): x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> [N,H,W,Cout].
+    thin: the launch is the GEMM half of an RGB-side (3-channel) conv — HBM-bound; the value is the ALGORITHMIC
+    byte count of the whole op (wide tensor once + the 3-channel image), the im2col / col2im launches around it
+    are booked with zero work in the same family."""
     _check_cuda(x, w_krsc, bias, res, aux, labels)
     if x.dtype != torch.bfloat16 or w_krsc.dtype != torch.bfloat16:
         raise ValueError("Not valid dtype: conv operands must be bfloat16")
@@ -521,13 +532,16 @@ def conv_fwd(x, w_krsc, out_dtype=torch.bfloat16, bias=None, res=None, aux=None,
               F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, R, S,
               _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
               packed.M if packed else 0, flags, _stream())
-    _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * R * S,
-              f"conv {N}x{H}x{W} {Cin}->{Cout} k{R} f{flags:#x} {'f32' if out_dtype == torch.float32 else 'bf16'}")
+    desc = f"conv {N}x{H}x{W} {Cin}->{Cout} k{R} f{flags:#x} {'f32' if out_dtype == torch.float32 else 'bf16'}"
+    if thin:
+        _prof_end(ev, "thin", float(thin), desc)
+    else:
+        _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * R * S, desc)
     return out
 
 
 def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=None, labels=None, packed=None,
-                flags=0):
+                flags=0, ref_phase_taps=4):
     """Generalised geometry on the tcgen05 conv kernel (include/mcgm.h):
     CONV_S2K4  : w [Cout,4,4,Cin]        x [N,H,W,Cin] -> [N,H/2,W/2,Cout]   (4x4, stride 2, pad 1)
     CONV_PHASE2: w [4,Cout,2,2,Cin]      x [N,H,W,Cin] -> [N,2H,2W,Cout]     (4 phases x 2x2 taps)"""
@@ -553,10 +567,11 @@ def conv_fwd_ex(kind, x, w, out_dtype=torch.bfloat16, bias=None, res=None, aux=N
               F32 if out_dtype == torch.float32 else BF16, N, H, W, Cin, Cout, 0, 0,
               _ptr(bias), _ptr(res), _ptr(aux), _ptr(labels), _ptr(packed.bits if packed else None),
               packed.M if packed else 0, flags, _stream())
-    # algorithmic flops of the REFERENCE op (3x3 on the upsampled tensor / 4x4 strided), not the executed MACs
-    ref_taps = 9 if kind == CONV_PHASE2 else 16
-    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ref_taps,
-              f"conv_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}")
+    # EXECUTED MACs: the phase conv runs 2x2 taps per output pixel (the reference op it replaces, Up2 -> Conv3x3,
+    # has 9; ConvTranspose2d(4,2,1) has 4 as well), the strided conv all 16
+    ex_taps, ref_taps = (4, ref_phase_taps) if kind == CONV_PHASE2 else (16, 16)
+    _prof_end(ev, "conv", 2.0 * N * Ho * Wo * Cout * Cin * ex_taps,
+              f"conv_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout} f{flags:#x}", 2.0 * N * Ho * Wo * Cout * Cin * ref_taps)
     return out
 
 
@@ -628,7 +643,7 @@ def wgrad_f32(kind, x, dy, R=0, S=0, want_bias=True):
     return dw, db
 
 
-def conv_wgrad_ex(kind, x, dy, want_bias=True):
+def conv_wgrad_ex(kind, x, dy, want_bias=True, ref_phase_taps=4):
     """dw fp32 [Cout, 4, 4, Cin] (tap index p*4+q, see include/mcgm.h) and dbias; x dims are [N,H,W,Cin]."""
     _check_cuda(x, dy)
     N, H, W, Cin = x.shape
@@ -643,14 +658,16 @@ def conv_wgrad_ex(kind, x, dy, want_bias=True):
     _lib.call("mcgm_conv_wgrad_ex", kind, BF16, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin,
               Cout, 0, 0, ws.data_ptr(), _stream())
     _lib.launch_count += 1
-    ref_taps = 9 if kind == CONV_PHASE2 else 16
-    _prof_end(ev, "wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * ref_taps
-              if kind == CONV_PHASE2 else 2.0 * N * (H // 2) * (W // 2) * Cout * Cin * 16,
-              f"wgrad_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout}")
+    # EXECUTED MACs.  PHASE2: 16 taps over the N*H*W input-grid pixels (= 4 per output pixel; the reference op
+    # Up2 -> Conv3x3 has 9 per output pixel); S2K4: 16 taps per output pixel
+    npix = dy.shape[0] * dy.shape[1] * dy.shape[2]
+    ex = 2.0 * npix * Cout * Cin * (4 if kind == CONV_PHASE2 else 16)
+    ref = 2.0 * npix * Cout * Cin * (ref_phase_taps if kind == CONV_PHASE2 else 16)
+    _prof_end(ev, "wgrad", ex, f"wgrad_ex kind{kind} {N}x{H}x{W} {Cin}->{Cout}", ref)
     return dw, db
 
 
-def conv_wgrad(x, dy, R, S, want_bias=True):
+def conv_wgrad(x, dy, R, S, want_bias=True, thin=False):
     """dw (fp32 KRSC [Cout,R,S,Cin]) and dbias from NHWC bf16 x and dy."""
     _check_cuda(x, dy)
     N, H, W, Cin = x.shape
@@ -665,7 +682,10 @@ def conv_wgrad(x, dy, R, S, want_bias=True):
     _lib.call("mcgm_conv_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, R, S,
               ws.data_ptr(), _stream())
     _lib.launch_count += 1                       # wgrad + split-K / bias reduce
-    _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S, f"wgrad {N}x{H}x{W} {Cin}->{Cout} k{R}")
+    if thin:
+        _prof_end(ev, "thin", float(thin), f"wgrad {N}x{H}x{W} {Cin}->{Cout} k{R}")
+    else:
+        _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * R * S, f"wgrad {N}x{H}x{W} {Cin}->{Cout} k{R}")
     return dw, db
 
 
@@ -860,8 +880,10 @@ def thin_im2col(thin, R, S, flip=False, KU=64, stride=1, pad=None, dtype=torch.b
     pad = (R - 1) // 2 if pad is None else pad
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     U = torch.empty(N, Ho, Wo, KU, dtype=dtype, device=thin.device)
+    ev = _prof_begin()
     _lib.call("mcgm_thin_im2col", thin.data_ptr(), U.data_ptr(), F32 if dtype == torch.float32 else BF16, N, H, W,
               Ct, R, S, stride, pad, int(flip), KU, _stream())
+    _prof_end(ev, "thin", 0.0, f"thin_im2col {N}x{H}x{W}x{Ct} k{R} s{stride}")
     return U
 
 
@@ -871,7 +893,9 @@ def thin_col2im(T, Ct, R, S, bias=None, tanh=False):
     N, H, W, CT = T.shape
     out = torch.empty(N, H, W, Ct, dtype=torch.float32, device=T.device)
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_TANH if tanh else 0)
+    ev = _prof_begin()
     _lib.call("mcgm_thin_col2im", T.data_ptr(), CT, out.data_ptr(), N, H, W, Ct, R, S, _ptr(bias), flags, _stream())
+    _prof_end(ev, "thin", 0.0, f"thin_col2im {N}x{H}x{W}x{Ct} k{R}")
     return out
 
 
@@ -938,7 +962,7 @@ class ConvUp2Fn(torch.autograd.Function):
             if want_stats and stats_supported(x, w.shape[0]):
                 out, _last_stats = conv_fwd_bnstats(CONV_PHASE2, x, wp, bias)
             else:
-                out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias)
+                out = conv_fwd_ex(CONV_PHASE2, x, wp, torch.bfloat16, bias, ref_phase_taps=9)
         ctx.save_for_backward(x)
         ctx.kd, ctx.has_bias, ctx.dev = kd, bias is not None, w.device
         return out
@@ -953,7 +977,7 @@ class ConvUp2Fn(torch.autograd.Function):
             dx = conv_f32(CONV_S2K4, dout, ctx.kd) if f32 else conv_fwd_ex(CONV_S2K4, dout, ctx.kd, torch.bfloat16)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dk, db = (wgrad_f32(CONV_PHASE2, x, dout, want_bias=ctx.has_bias) if f32
-                      else conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias))     # [K,4,4,C]
+                      else conv_wgrad_ex(CONV_PHASE2, x, dout, want_bias=ctx.has_bias, ref_phase_taps=9))     # [K,4,4,C]
             _, qm = _up2_mats(ctx.dev)
             dw = torch.einsum('xr,ys,kxyc->kcrs', qm, qm, dk)
         return dx, dw, db, None, None
@@ -1033,9 +1057,10 @@ class ConvT4Fn(torch.autograd.Function):
             U = thin_im2col(dout, 4, 4, False, _KU, 2, 1)                                   # [N,H,W,64], cols (p,q,j)
             if ctx.needs_input_grad[0]:
                 wm = _pad_cols(w.detach().permute(0, 2, 3, 1).reshape(C, 16 * K), _KU)
-                dx = conv_fwd(U, wm.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16)
+                dx = conv_fwd(U, wm.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16,
+                              thin=x.numel() * 2 + dout.numel() * 4)
             if ctx.needs_input_grad[1]:
-                dwm, _ = conv_wgrad(x, U, 1, 1, want_bias=False)                            # [KU,1,1,C]
+                dwm, _ = conv_wgrad(x, U, 1, 1, want_bias=False, thin=x.numel() * 2 + dout.numel() * 4)   # [KU,1,1,C]
                 dw = dwm.reshape(_KU, C)[:16 * K].reshape(4, 4, K, C).permute(3, 2, 0, 1)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = dout.sum(dim=(0, 1, 2))
@@ -1073,7 +1098,7 @@ class WideFromThinFn(torch.autograd.Function):
             _lib.call("mcgm_thin_conv_fwd", thin.data_ptr(), wm.data_ptr(), _TK, _ptr(bias), _ptr(labels),
                       _ptr(packed.bits if packed else None), packed.M if packed else 0, int(gate is not None),
                       out.data_ptr(), N, H, Wd, C, R, S, K, _stream())
-            _prof_end(ev, "conv", 2.0 * N * H * Wd * K * C * R * S, f"thin_conv {N}x{H}x{Wd} {C}->{K} k{R} gate{int(gate is not None)}")
+            _prof_end(ev, "thin", thin.numel() * 4 + out.numel() * 2, f"thin_conv {N}x{H}x{Wd} {C}->{K} k{R} gate{int(gate is not None)}")
             ctx.save_for_backward(thin, w, out if gate is not None else None, sn)
             ctx.gated, ctx.has_bias, ctx.grad_premasked, ctx.direct = gate is not None, bias is not None, grad_premasked, True
             return out
@@ -1088,7 +1113,8 @@ class WideFromThinFn(torch.autograd.Function):
             out = conv_f32(CONV_S1, U, wm, 1, 1, bias, None, False, None, labels, packed, flags)
         else:
             wm = pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
-            out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags)
+            out = conv_fwd(U, wm, torch.bfloat16, bias, None, None, labels, packed, flags,
+                           thin=thin.numel() * 4 + U.shape[0] * U.shape[1] * U.shape[2] * K * 2)
         ctx.save_for_backward(U, w, out if gate is not None else None, sn)
         ctx.gated, ctx.has_bias, ctx.grad_premasked = gate is not None, bias is not None, grad_premasked
         return out
@@ -1109,7 +1135,8 @@ class WideFromThinFn(torch.autograd.Function):
             if dout.dtype == torch.float32:
                 T = conv_f32(CONV_S1, dout, wd.reshape(CT, 1, 1, K).contiguous(), 1, 1)
             else:
-                T = conv_fwd(dout, wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous(), torch.float32)
+                T = conv_fwd(dout, wd.to(torch.bfloat16).reshape(CT, 1, 1, K).contiguous(), torch.float32,
+                             thin=dout.numel() * 2 + dout.numel() // K * C * 4)
             dthin = thin_col2im(T, C, R, S)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             if ctx.direct:
@@ -1121,14 +1148,15 @@ class WideFromThinFn(torch.autograd.Function):
                 _lib.call("mcgm_thin_conv_wgrad", thin.data_ptr(), dout.data_ptr(), dwm.data_ptr(), N, H, Wd, C, R, S, K,
                           ws.data_ptr(), _stream())
                 _lib.launch_count += 1
-                _prof_end(ev, "wgrad", 2.0 * N * H * Wd * K * C * R * S, f"thin_wgrad {N}x{H}x{Wd} {C}->{K} k{R}")
+                _prof_end(ev, "thin", thin.numel() * 4 + dout.numel() * 2, f"thin_wgrad {N}x{H}x{Wd} {C}->{K} k{R}")
                 db = dwm[:, R * S * C].contiguous() if ctx.has_bias else None
                 ku = _TK
             else:
                 if dout.dtype == torch.float32:
                     dwm, db = wgrad_f32(CONV_S1, U, dout, 1, 1, want_bias=ctx.has_bias)
                 else:
-                    dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias)   # [K,1,1,KU], columns (r,s,c)
+                    dwm, db = conv_wgrad(U, dout, 1, 1, want_bias=ctx.has_bias,           # [K,1,1,KU], columns (r,s,c)
+                                         thin=dout.numel() * 2 + dout.numel() // K * C * 4)
                 ku = _KU
             if sn is not None:
                 dw = sn_weight_bwd(dwm, ku, 1, w, sn)
@@ -1150,7 +1178,8 @@ class ThinFromWideFn(torch.autograd.Function):
         if wide.dtype == torch.float32:
             T = conv_f32(CONV_S1, wide, wm.reshape(CT, 1, 1, C).contiguous(), 1, 1)
         else:
-            T = conv_fwd(wide, wm.to(torch.bfloat16).reshape(CT, 1, 1, C).contiguous(), torch.float32)
+            T = conv_fwd(wide, wm.to(torch.bfloat16).reshape(CT, 1, 1, C).contiguous(), torch.float32,
+                         thin=wide.numel() * 2 + wide.numel() // C * K * 4)
         out = thin_col2im(T, K, R, S, bias, tanh)
         ctx.save_for_backward(wide, w, out if tanh else None)
         ctx.tanh, ctx.has_bias = tanh, bias is not None
@@ -1171,10 +1200,11 @@ class ThinFromWideFn(torch.autograd.Function):
             if f32:
                 dwide = conv_f32(CONV_S1, Ub, wb.reshape(C, 1, 1, _KU).contiguous(), 1, 1)
             else:
-                dwide = conv_fwd(Ub, wb.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16)
+                dwide = conv_fwd(Ub, wb.to(torch.bfloat16).reshape(C, 1, 1, _KU).contiguous(), torch.bfloat16,
+                                 thin=wide.numel() * 2 + dout.numel() * 4)
         if ctx.needs_input_grad[1]:
             dwm, _ = (wgrad_f32(CONV_S1, wide, Ub, 1, 1, want_bias=False) if f32
-                      else conv_wgrad(wide, Ub, 1, 1, want_bias=False))       # [KU,1,1,C]
+                      else conv_wgrad(wide, Ub, 1, 1, want_bias=False, thin=wide.numel() * 2 + dout.numel() * 4))   # [KU,1,1,C]
             dw = dwm.reshape(_KU, C)[:R * S * K].reshape(R, S, K, C).permute(2, 3, 0, 1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dout.sum(dim=(0, 1, 2))
@@ -1272,3 +1302,156 @@ class FlowTailFn(torch.autograd.Function):
                   dy.data_ptr(), dnet.data_ptr(), dzp.data_ptr(), N, H * Wd, C, net.shape[-1],
                   1 if ctx.affine else 0, _stream())
         return dy, dnet, dzp.sum(0).reshape(ctx.zshape), None
+
+
+def flow_front(x, loc, scale, W, want_xa=True):
+    """The front kernel without autograd: y = W (scale * (x + loc)) on fp32 NHWC, plus (optionally) the bf16
+    zero-padded first half of y.  Used by the sampling path, where Flow.reverse is the SAME kernel with the
+    parameters W' = diag(1/scale) W^-1, scale' = 1, loc' = -W (scale * loc)."""
+    _check_cuda(x, loc, scale, W)
+    N, H, Wd, C = x.shape
+    y = torch.empty_like(x)
+    xa = torch.empty(N, H, Wd, FLOW_XA_CH, dtype=torch.bfloat16, device=x.device) if want_xa else None
+    _lib.call("mcgm_flow_front_fwd", x.data_ptr(), loc.data_ptr(), scale.data_ptr(), W.data_ptr(), y.data_ptr(),
+              _ptr(xa), N * H * Wd, C, FLOW_XA_CH, _stream())
+    return y, xa
+
+
+def flow_tail_rev(out, net, zscale, affine):
+    """AffineCoupling.reverse around its network (src/models/mcglow.py:166-175): out fp32 NHWC [N,H,W,C], net the RAW
+    zero-conv output fp32 NHWC [N,H,W,>=C] -> y = [out_a, out_b / sigmoid(log_s + 2) - t]."""
+    _check_cuda(out, net, zscale)
+    N, H, Wd, C = out.shape
+    y = torch.empty_like(out)
+    _lib.call("mcgm_flow_tail_rev", out.data_ptr(), net.data_ptr(), zscale.data_ptr(), y.data_ptr(), N, H * Wd, C,
+              net.shape[-1], 1 if affine else 0, _stream())
+    return y
+
+
+# ----------------------------------------------------------------------------- gated PixelCNN (SURVEY.md §8 f3)
+def _tap_arrays(taps):
+    import ctypes as c
+    n = len(taps)
+    return n, (c.c_byte * n)(*[int(t[0]) for t in taps]), (c.c_byte * n)(*[int(t[1]) for t in taps])
+
+
+def conv_fwd_taps(x, w_ktc, taps, out_dtype=torch.bfloat16, bias=None, res=None, flags=0):
+    """Explicit-tap stride-1 conv on the tcgen05 kernel: x [N,H,W,Cin] bf16, w [Cout, T, Cin] bf16,
+    taps = [(dh, dw)] * T -> out[n,i,j] = sum_t x[n, i+dh_t, j+dw_t] . w[:, t, :]."""
+    _check_cuda(x, w_ktc, bias, res)
+    N, H, W, Cin = x.shape
+    Cout, T = w_ktc.shape[0], w_ktc.shape[1]
+    if T != len(taps) or w_ktc.shape[2] != Cin:
+        raise ValueError("Not valid weight for the tap list")
+    out = torch.empty(N, H, W, Cout, dtype=out_dtype, device=x.device)
+    n, dh, dw = _tap_arrays(taps)
+    if bias is not None:
+        flags |= EPI_BIAS
+    if res is not None:
+        flags |= EPI_RES
+    ev = _prof_begin()
+    _lib.call("mcgm_conv_fwd_taps", x.data_ptr(), w_ktc.data_ptr(), out.data_ptr(), F32 if out_dtype == torch.float32 else BF16,
+              N, H, W, Cin, Cout, n, dh, dw, _ptr(bias), _ptr(res), None, None, None, 0, flags, _stream())
+    _prof_end(ev, "conv", 2.0 * N * H * W * Cout * Cin * T, f"conv_taps {N}x{H}x{W} {Cin}->{Cout} t{T} f{flags:#x}")
+    return out
+
+
+def conv_wgrad_taps(x, dy, taps, want_bias=True):
+    """dw fp32 [Cout, T, Cin] (and dbias) of the explicit-tap conv."""
+    _check_cuda(x, dy)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    n, dh, dw_ = _tap_arrays(taps)
+    nbytes = _lib.query("mcgm_conv_wgrad_taps_workspace_bytes", N, H, W, Cin, Cout, n)
+    if nbytes == 0:
+        raise ValueError(f"Not valid wgrad shape N={N} H={H} W={W} Cin={Cin} Cout={Cout} taps={n}")
+    ws = _workspace("wgrad", nbytes, x.device)
+    dw = torch.empty(Cout, n, Cin, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    ev = _prof_begin()
+    _lib.call("mcgm_conv_wgrad_taps", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db), N, H, W, Cin, Cout, n, dh, dw_,
+              ws.data_ptr(), _stream())
+    _lib.launch_count += 1
+    _prof_end(ev, "wgrad", 2.0 * N * H * W * Cout * Cin * n, f"wgrad_taps {N}x{H}x{W} {Cin}->{Cout} t{n}")
+    return dw, db
+
+
+class ConvTapsFn(torch.autograd.Function):
+    """nn.Conv2d(C, K, (R, S), 1, (ph, pw)) cropped to the input's H x W — the masked / causal stacks of
+    MCGatedMaskedConv2d (src/models/mcpixelcnn.py:31-36, 48-52) — as an explicit-tap tcgen05 conv.
+    w: fp32 OIHW master weight; tap (r, s) reads input pixel (i + r - ph, j + s - pw).
+    res: optional same-shape tensor added in the epilogue (``v2h + h_horiz``)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, pad, res):
+        K, C, R, S = w.shape
+        taps = [(r - pad[0], s - pad[1]) for r in range(R) for s in range(S)]
+        wf, wflip = pack_weight(w.detach())                       # [K,R,S,C] and flipped [C,R,S,K]
+        out = conv_fwd_taps(x, wf.view(K, R * S, C), taps, torch.bfloat16, bias, res)
+        ctx.save_for_backward(x)
+        ctx.wflip, ctx.taps, ctx.wshape = wflip, taps, (K, C, R, S)
+        ctx.has_bias, ctx.has_res = bias is not None, res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        K, C, R, S = ctx.wshape
+        dout = dout.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx[q] = sum_t dout[q - off_t] . w[:, t, :]^T ; the flipped pack holds tap T-1-t at index t
+            rtaps = [(-dh, -dw_) for (dh, dw_) in reversed(ctx.taps)]
+            dx = conv_fwd_taps(dout, ctx.wflip.view(C, R * S, K), rtaps, torch.bfloat16)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dwk, db = conv_wgrad_taps(x, dout, ctx.taps, want_bias=ctx.has_bias)       # [K, T, C]
+            dw = dwk.view(K, R, S, C).permute(0, 3, 1, 2)
+        return dx, dw, db, None, (dout if ctx.has_res and ctx.needs_input_grad[4] else None)
+
+
+class SGateFn(torch.autograd.Function):
+    """MCGatedActivation (src/models/mcpixelcnn.py:9-20) on NHWC: h [N,H,W,2C] bf16 ->
+    mask * relu(bn(h[..., :C])) * sigmoid(h[..., C:]) as one kernel (plus the statistics pass in training)."""
+
+    @staticmethod
+    def forward(ctx, h, gamma, beta, labels, packed, running_mean, running_var, momentum, eps, training):
+        _check_cuda(h, gamma, beta, labels)
+        if h.dtype != torch.bfloat16:
+            raise ValueError("Not valid dtype: the gated activation takes bfloat16")
+        N, H, W, C2 = h.shape
+        C = C2 // 2
+        ws = _workspace("sgate", _lib.query("mcgm_sgate_workspace_bytes", C), h.device)
+        if training:
+            mean = torch.empty(C, dtype=torch.float32, device=h.device)
+            rstd = torch.empty(C, dtype=torch.float32, device=h.device)
+            _lib.call("mcgm_sgate_stats", h.data_ptr(), N * H * W, C, mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean),
+                      _ptr(running_var), float(momentum), float(eps), ws.data_ptr(), _stream())
+            _lib.launch_count += 1
+        else:
+            mean, rstd = running_mean, torch.rsqrt(running_var + eps)
+        out = torch.empty(N, H, W, C, dtype=torch.bfloat16, device=h.device)
+        ev = _prof_begin()
+        _lib.call("mcgm_sgate_fwd", h.data_ptr(), out.data_ptr(), N, H * W, C, labels.data_ptr(), packed.bits.data_ptr(),
+                  packed.M, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _stream())
+        _prof_end(ev, "gate", (h.numel() + out.numel()) * 2, f"sgate_fwd {N}x{H}x{W}x{C}")
+        ctx.save_for_backward(h, gamma, beta, mean, rstd)
+        ctx.labels, ctx.packed, ctx.training = labels, packed, training
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, gamma, beta, mean, rstd = ctx.saved_tensors
+        N, H, W, C2 = h.shape
+        C = C2 // 2
+        dout = dout.contiguous()
+        dh = torch.empty_like(h)
+        dgamma = torch.empty(C, dtype=torch.float32, device=h.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=h.device)
+        ws = _workspace("sgate", _lib.query("mcgm_sgate_workspace_bytes", C), h.device)
+        ev = _prof_begin()
+        _lib.call("mcgm_sgate_bwd", dout.data_ptr(), h.data_ptr(), dh.data_ptr(), N, H * W, C, ctx.labels.data_ptr(),
+                  ctx.packed.bits.data_ptr(), ctx.packed.M, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                  beta.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(ctx.training), ws.data_ptr(), _stream())
+        _lib.launch_count += 2
+        _prof_end(ev, "gate", (2 * (dout.numel() + h.numel()) + dh.numel()) * 2, f"sgate_bwd {N}x{H}x{W}x{C}")
+        return dh, dgamma, dbeta, None, None, None, None, None, None, None

@@ -70,6 +70,30 @@ def flat_buffers(params):
     return FlatBuffers(params)
 
 
+class StateGuard:
+    """Snapshot of everything a training step mutates — parameters, buffers (BatchNorm running statistics,
+    spectral-norm u / v, ActNorm flags) and the optimisers' moments / step counters — restored IN PLACE, so
+    pointers captured by a CUDA graph stay valid.  The graph-capturing step classes run their warm-up
+    iterations between ``StateGuard(...)`` and ``restore()``: the caller's model is not trained by them."""
+
+    def __init__(self, model, optimizers):
+        self.model = model
+        self.opts = [o for o in optimizers if hasattr(o, 'snapshot')]
+        with torch.no_grad():
+            self.tensors = [(t, t.detach().clone()) for t in model.state_dict().values()]
+            self.opt_snaps = [o.snapshot() for o in self.opts]
+
+    def restore(self):
+        with torch.no_grad():
+            for t, saved in self.tensors:
+                t.copy_(saved)
+            for o, snap in zip(self.opts, self.opt_snaps):
+                o.restore(snap)
+            params = [p for p in self.model.parameters()]
+            if params:
+                torch.autograd.graph.increment_version(params)       # packed-weight caches key on the version
+
+
 class FusedAdam(torch.optim.Optimizer):
     """Adam on a flat buffer through ``mcgm_adam_step`` (CUDA only; there is no CPU path).
 
@@ -96,6 +120,53 @@ class FusedAdam(torch.optim.Optimizer):
         self.clip_norm, self.grad_scale = clip_norm, float(grad_scale)
         self.clip_out = torch.zeros(2, dtype=torch.float32, device=dev)       # [coef, total_norm]
         self.clip_ws = torch.zeros(_lib.query("mcgm_grad_clip_workspace_bytes") // 4, dtype=torch.float32, device=dev)
+        # [lr, beta1, beta2, eps, weight_decay, grad_scale]: read by the update kernel from DEVICE memory, staged
+        # through a pinned host buffer by a copy that is part of every step — also of a captured one, so a CUDA
+        # graph replay follows ``param_groups[0]['lr']`` (ReduceLROnPlateau, src/train_vae.py:35,78-81)
+        self.hyper_host = torch.zeros(6, dtype=torch.float32).pin_memory()
+        self.hyper_dev = torch.zeros(6, dtype=torch.float32, device=dev)
+        self._hyper_vals = None
+        self._bind_state(0.0)
+
+    # ---- torch.optim.Adam's state layout over the flat buffers ---------------------------------------------
+    def _views(self):
+        f = self.flat
+        for p, o in zip(f.params, f.offsets):
+            yield p, self.exp_avg[o:o + p.numel()].view_as(p), self.exp_avg_sq[o:o + p.numel()].view_as(p)
+
+    def _bind_state(self, step):
+        """``self.state[p] = {'step', 'exp_avg', 'exp_avg_sq'}`` exactly as torch.optim.Adam keeps it; the moments
+        are VIEWS of the flat buffers, 'step' is a host copy of the device counter (refreshed by state_dict)."""
+        for p, m, v in self._views():
+            self.state[p] = {'step': torch.tensor(float(step)), 'exp_avg': m, 'exp_avg_sq': v}
+
+    def state_dict(self):
+        """Same structure as ``torch.optim.Adam.state_dict()`` (the reference checkpoints it as
+        'optimizer_dict' and resumes from it, src/train_vae.py:86 / resume()): loads into torch's Adam and back."""
+        self._bind_state(int(self.step_dev.item()))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts a ``torch.optim.Adam`` (or FusedAdam) state_dict: moments are copied into the flat buffers,
+        the per-parameter step counts (all equal for one-group Adam) into the device counter."""
+        super().load_state_dict(state_dict)
+        steps = set()
+        with torch.no_grad():
+            for p, m, v in self._views():
+                st = self.state.get(p, None)
+                if st and 'exp_avg' in st:
+                    m.copy_(st['exp_avg'])
+                    v.copy_(st['exp_avg_sq'])
+                    steps.add(int(float(st['step'])))
+                else:                                  # torch keeps no state for parameters that never saw a gradient
+                    m.zero_()
+                    v.zero_()
+        if len(steps) > 1:
+            raise ValueError('Not valid optimizer state: parameters carry different step counts ' + str(sorted(steps)))
+        step = steps.pop() if steps else 0
+        self.step_dev.fill_(step)
+        self._hyper_vals = None
+        self._bind_state(step)
 
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
@@ -106,26 +177,59 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq.zero_()
         self.step_dev.zero_()
 
+    def snapshot(self):
+        """Copy of the optimiser's device state (moments + step counter) — see ``restore``."""
+        return self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone()
+
+    def restore(self, snap):
+        self.exp_avg.copy_(snap[0])
+        self.exp_avg_sq.copy_(snap[1])
+        self.step_dev.copy_(snap[2])
+
     @property
     def total_norm(self):
         """Gradient norm seen by the last clipped step (device tensor)."""
         return self.clip_out[1]
 
+    def sync_hyper(self):
+        """Stage ``param_groups[0]``'s hyper-parameters for the next step / graph replay (host write only)."""
+        g = self.param_groups[0]
+        vals = (float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']), float(g['weight_decay']),
+                float(self.grad_scale))
+        if vals != self._hyper_vals:
+            if self._hyper_vals is not None and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream().synchronize()     # an earlier step's staging copy may still be in flight
+            self.hyper_host.copy_(torch.tensor(vals, dtype=torch.float32))
+            self._hyper_vals = vals
+
+    def _sync_grads(self):
+        """``p.grad`` must be the views of the flat gradient buffer.  ``model.zero_grad()`` (set_to_none) makes
+        autograd allocate fresh ``.grad`` tensors: copy those in (a missing gradient counts as zero) and rebind."""
+        f = self.flat
+        for p, g in zip(f.params, f.grad_views):
+            if p.grad is g:
+                continue
+            if p.grad is None:
+                g.zero_()
+            else:
+                g.copy_(p.grad)
+            p.grad = g
+
     @torch.no_grad()
     def step(self, closure=None):
-        g = self.param_groups[0]
         st = torch.cuda.current_stream().cuda_stream
         f = self.flat
+        self._sync_grads()
+        self.sync_hyper()
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
         coef = None
         if self.clip_norm is not None:
             _lib.call("mcgm_grad_clip_coef", f.grad.data_ptr(), f.numel, float(self.clip_norm),
                       self.clip_out.data_ptr(), self.clip_ws.data_ptr(), st)
             _lib.launch_count += 1
             coef = self.clip_out.data_ptr()
-        _lib.call("mcgm_adam_step", f.param.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
-                  self.exp_avg_sq.data_ptr(), f.numel, self.step_dev.data_ptr(), float(g['lr']),
-                  float(g['betas'][0]), float(g['betas'][1]), float(g['eps']), float(g['weight_decay']),
-                  self.grad_scale, coef, st)
+        _lib.call("mcgm_adam_step_dev", f.param.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), f.numel, self.step_dev.data_ptr(), self.hyper_dev.data_ptr(), coef, st)
         _lib.launch_count += 1
         # the update wrote through raw pointers: tell autograd (and the packed-weight caches keyed on
         # ``Parameter._version``) that the parameters changed

@@ -49,12 +49,15 @@ class GradAllReduce:
     BatchNorm statistics stay per-rank, as with the reference's DataParallel replicas.
     """
 
-    def __init__(self, module, bucket_bytes=8 << 20, group=None, overlap=True):
+    def __init__(self, module, bucket_bytes=8 << 20, group=None, overlap=True, average=True):
         """overlap=True: hook-driven bucketed all-reduce during backward (eager mode).
         overlap=False: one all-reduce of the whole flat buffer in ``finish()`` — the form that is
-        captured inside a CUDA graph (the payload is 4-17 MB, i.e. tens of microseconds on NVLink)."""
+        captured inside a CUDA graph (the payload is 4-17 MB, i.e. tens of microseconds on NVLink).
+        average=False: ``finish()`` leaves the SUM in the buffer; the 1/world factor then rides on the
+        optimiser update (``FusedAdam.grad_scale``) instead of costing a pass over the gradients."""
         self.group = group
         self.overlap = overlap
+        self.average = average
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         from .optim import flat_buffers
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -103,7 +106,8 @@ class GradAllReduce:
             return
         if not self.overlap:
             dist.all_reduce(self.flat, group=self.group)
-            self.flat.div_(self.world)
+            if self.average:
+                self.flat.div_(self.world)
             return
         # parameters that received no gradient this step (unused) still need their bucket reduced
         for b, (s, e, n) in enumerate(self.buckets):
@@ -112,7 +116,8 @@ class GradAllReduce:
         for h in self.handles:
             h.wait()
         self.handles = []
-        self.flat.div_(self.world)
+        if self.average:
+            self.flat.div_(self.world)
 
 
 def hinge_d(d_real, d_fake):
@@ -215,7 +220,9 @@ class GraphedTrainStep:
     stay ahead of the B200.  The step has static shapes and never synchronises with the host, so
     it is captured after a few eager warm-up iterations (which also build every lazily created
     workspace, packed codebook and TMA descriptor) and replayed with new data copied into static
-    input buffers.  Optimisers must be built with ``capturable=True``.
+    input buffers.  Optimisers must be built with ``capturable=True``.  The warm-up iterations run on an
+    all-zero batch; parameters, buffers and optimiser state are snapshotted before and restored after them
+    (``optim.StateGuard``), so the caller's model starts real training exactly where it was.
     """
 
     def __init__(self, model, optimizer, batch_size, warmup=3, reducers=None, inject_noise=False):
@@ -229,6 +236,8 @@ class GraphedTrainStep:
         n_z = GAN_HYPER['iter']['discriminator'] + GAN_HYPER['iter']['generator']
         self.z = ([torch.zeros(batch_size, model.latent_size, device=dev) for _ in range(n_z)]
                   if inject_noise else None)
+        from .optim import StateGuard
+        guard = StateGuard(model, optimizer.values())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -242,6 +251,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
         self.native_launches = _lib.launch_count - c0      # libmcgm kernels inside one replay
+        guard.restore()
 
     def __call__(self, input):
         """input: {'img','label'} on the host (pinned) or the device; returns device loss tensors
@@ -251,19 +261,26 @@ class GraphedTrainStep:
         if self.z is not None:
             for dst, src in zip(self.z, input['z']):
                 dst.copy_(src, non_blocking=True)
+        for o in self.optimizer.values():
+            if hasattr(o, 'sync_hyper'):
+                o.sync_hyper()              # the captured Adam reads lr & co from a staged device buffer
         self.graph.replay()
         return self.out
 
 
 class GraphedDDPTrainStep:
-    """Data-parallel variant: the forward+backward of a D update and of a G update are captured
-    as two CUDA graphs (no collective inside a graph); after each replay the flat gradient buffer
-    is all-reduced over NCCL/NVLink and Adam steps eagerly.  Per iteration the host issues
-    6 graph launches + 6 all-reduces + 6 optimiser steps instead of ~6000 kernel launches.
-    Weight packing of G is forced inside the graphs (its cache check happens at capture time)."""
+    """Data-parallel variant with the collectives BETWEEN graph segments: the forward+backward of a D update
+    and of a G update are captured as two CUDA graphs; after each replay the flat gradient buffer is
+    all-reduced over NCCL/NVLink (sum; the 1/world factor rides on the Adam kernel) and Adam steps eagerly.
+    Per iteration the host issues 6 graph launches + 6 all-reduces + 6 optimiser steps instead of ~6000 kernel
+    launches.  Weight packing of G is forced inside the graphs (its cache check happens at capture time).
+    ``GraphedDDPIngraphTrainStep`` (collectives captured too) is the default; this form is the fallback."""
 
-    def __init__(self, model, optimizer, reducers, batch_size, warmup=2):
+    launch_form = "CUDA graph per D/G forward+backward, NCCL all-reduce + Adam between graphs (1/world folded into Adam)"
+
+    def __init__(self, model, optimizer, reducers, batch_size, warmup=2, inject_noise=False):
         from .models import mcgan as _m
+        from .optim import StateGuard
         dev = next(model.parameters()).device
         shape = model.generator.data_shape
         self.img = torch.zeros(batch_size, *shape, device=dev)
@@ -271,20 +288,28 @@ class GraphedDDPTrainStep:
         self.model, self.optimizer, self.reducers = model, optimizer, reducers
         self.n_d, self.n_g = GAN_HYPER['iter']['discriminator'], GAN_HYPER['iter']['generator']
         latent = model.latent_size
+        # one latent buffer per segment graph; with inject_noise the caller's z_k is copied in before replay k
+        self.z_d = torch.zeros(batch_size, latent, device=dev)
+        self.z_g = torch.zeros(batch_size, latent, device=dev)
+        self.inject = inject_noise
 
         def d_part():
             reducers['discriminator'].zero_grad()
             reducers['generator'].zero_grad()
-            return d_forward_backward(model, self.img, self.label, torch.randn(batch_size, latent, device=dev))
+            z = self.z_d if inject_noise else torch.randn(batch_size, latent, device=dev)
+            return d_forward_backward(model, self.img, self.label, z)
 
         def g_part():
             reducers['discriminator'].zero_grad()
             reducers['generator'].zero_grad()
-            return g_forward_backward(model, self.label, torch.randn(batch_size, latent, device=dev))
+            z = self.z_g if inject_noise else torch.randn(batch_size, latent, device=dev)
+            return g_forward_backward(model, self.label, z)
 
         for r in reducers.values():
             if r.overlap:
                 raise ValueError('Not valid reducer: graph mode needs GradAllReduce(overlap=False)')
+        _fold_world_into_adam(optimizer, reducers)
+        guard = StateGuard(model, optimizer.values())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -307,19 +332,124 @@ class GraphedDDPTrainStep:
             c2 = _lib.launch_count
         finally:
             _m._packs_force = False
-        self.native_launches = (c1 - c0) * self.n_d + (c2 - c1) * self.n_g
+        self.native_launches = (c1 - c0 + 2) * self.n_d + (c2 - c1 + 2) * self.n_g      # + the eager Adam launches
         self.out = {'loss_D': self.d_loss, 'loss_G': self.g_loss, 'loss': None}
+        guard.restore()
 
     def __call__(self, input):
         self.img.copy_(input['img'], non_blocking=True)
         self.label.copy_(input['label'], non_blocking=True)
+        zs = iter(input['z']) if self.inject else None
         for _ in range(self.n_d):
+            if zs is not None:
+                self.z_d.copy_(next(zs), non_blocking=True)
             self.graph_d.replay()
             self.reducers['discriminator'].finish()
             self.optimizer['discriminator'].step()
         for _ in range(self.n_g):
+            if zs is not None:
+                self.z_g.copy_(next(zs), non_blocking=True)
             self.graph_g.replay()
             self.reducers['generator'].finish()
             self.optimizer['generator'].step()
         self.out['loss'] = (self.d_loss - self.g_loss).abs()
         return self.out
+
+
+def _fold_world_into_adam(optimizer, reducers):
+    """Sum-reduce + (1/world inside the Adam kernel) instead of sum-reduce + a division pass."""
+    for k, r in reducers.items():
+        o = optimizer[k]
+        if not hasattr(o, 'grad_scale'):
+            raise ValueError('Not valid optimizer: the data-parallel graph steps need optim.FusedAdam')
+        if r.average:
+            r.average = False
+            o.grad_scale = o.grad_scale / r.world
+
+
+class GraphedDDPIngraphTrainStep:
+    """Data-parallel iteration as ONE CUDA graph per rank: forwards, backwards, the NCCL all-reduce of each
+    update's flat gradient buffer and the Adam updates are all captured (NCCL collectives are capturable; the
+    ranks replay the same graph in lock step).  The host issues one ``cudaGraphLaunch`` per iteration at any
+    world size — no launch gaps around the collectives, no eager optimiser launches, 1/world folded into Adam.
+    What stays exposed: the all-reduce itself (4.2 MB x 5 + 17.1 MB per iteration; the spectral-normed weight
+    gradients are produced by the batched launch at the END of D's backward, so nothing of D's backward is left
+    to hide it behind) and Adam, which depends on it."""
+
+    launch_form = "one CUDA graph per iteration, NCCL all-reduce + Adam captured inside (1/world folded into Adam)"
+
+    def __init__(self, model, optimizer, reducers, batch_size, warmup=2, inject_noise=False):
+        from .optim import StateGuard
+        for r in reducers.values():
+            if r.overlap:
+                raise ValueError('Not valid reducer: graph mode needs GradAllReduce(overlap=False)')
+        _fold_world_into_adam(optimizer, reducers)
+        dev = next(model.parameters()).device
+        shape = model.generator.data_shape
+        self.img = torch.zeros(batch_size, *shape, device=dev)
+        self.label = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.model, self.optimizer, self.reducers = model, optimizer, reducers
+        n_z = GAN_HYPER['iter']['discriminator'] + GAN_HYPER['iter']['generator']
+        self.z = ([torch.zeros(batch_size, model.latent_size, device=dev) for _ in range(n_z)]
+                  if inject_noise else None)
+        batch = {'img': self.img, 'label': self.label}
+        guard = StateGuard(model, optimizer.values())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                     # also brings up the NCCL communicator before the capture
+                train_step(model, optimizer, batch, z=self.z, reducers=reducers)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        from . import _lib
+        c0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+            self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
+        self.native_launches = _lib.launch_count - c0
+        guard.restore()
+
+    def __call__(self, input):
+        self.img.copy_(input['img'], non_blocking=True)
+        self.label.copy_(input['label'], non_blocking=True)
+        if self.z is not None:
+            for dst, src in zip(self.z, input['z']):
+                dst.copy_(src, non_blocking=True)
+        for o in self.optimizer.values():
+            o.sync_hyper()
+        self.graph.replay()
+        return self.out
+
+
+def make_ddp_step(model, optimizer, reducers, batch_size, mode='auto', inject_noise=False):
+    """The data-parallel graph step: 'ingraph' (collectives captured), 'segmented' (collectives between graph
+    segments), or 'auto' = ingraph, falling back to segmented if this torch / NCCL build refuses the capture
+    (every rank takes the same decision: the outcome is agreed through an all-reduce)."""
+    import sys
+    if mode == 'segmented':
+        return GraphedDDPTrainStep(model, optimizer, reducers, batch_size, inject_noise=inject_noise)
+    err = None
+    step = None
+    try:
+        step = GraphedDDPIngraphTrainStep(model, optimizer, reducers, batch_size, inject_noise=inject_noise)
+    except Exception as e:                           # noqa: BLE001 - capture failures surface as several types
+        if mode == 'ingraph':
+            raise
+        err = e
+    if dist.is_initialized() and mode == 'auto':
+        dev = next(model.parameters()).device
+        try:
+            torch.cuda.synchronize()
+        except Exception:                            # noqa: BLE001
+            pass
+        flag = torch.tensor([0 if step is not None else 1], device=dev)
+        dist.all_reduce(flag)
+        if int(flag) > 0:
+            step = None
+    if step is not None:
+        return step
+    print(f'[train_gan] in-graph NCCL capture unavailable ({type(err).__name__ if err else "peer rank"}: {err}); '
+          f'using segmented graphs', file=sys.stderr, flush=True)
+    return GraphedDDPTrainStep(model, optimizer, reducers, batch_size, inject_noise=inject_noise)

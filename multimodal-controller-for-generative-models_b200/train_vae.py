@@ -35,8 +35,9 @@ class GraphedTrainStep:
     A Glow step is ~48 flow steps x ~40 launches forward and as many backward, a VAE step a few hundred
     launches of 5-50 us kernels: issued eagerly both are bound by the host, not the B200.  The step has
     static shapes and — with ``optim.FusedAdam`` (device-side step counter and clip coefficient) — never
-    synchronises with the host, so it is captured after a few eager warm-up steps (which also run Glow's
-    data-dependent ActNorm initialisation, build every workspace, packed codebook and TMA descriptor) and
+    synchronises with the host, so it is captured after a few eager warm-up steps (which build every workspace,
+    packed codebook and TMA descriptor; the model / optimiser state they touch is rolled back afterwards, so
+    Glow's data-dependent ActNorm initialisation must already have happened: ``train_glow.init_actnorm``) and
     replayed with new data copied into static input buffers.  ``noise``: optional static buffer for the
     injected reparameterisation (VAE) / dequantisation (Glow) noise of parity runs; otherwise the noise is
     drawn inside the graph (torch's graph-safe Philox stream).  No autograd graph of an earlier eager step on
@@ -52,6 +53,13 @@ class GraphedTrainStep:
         self.noise = inject_noise.detach().clone() if inject_noise is not None else None
         self.model, self.optimizer = model, optimizer
         batch = {"img": self.img, "label": self.label}
+        from .optim import StateGuard
+        for m in model.modules():
+            if hasattr(m, "needs_init") and m.needs_init():
+                raise ValueError("Not valid model state: run the data-dependent ActNorm initialisation first "
+                                 "(train_glow.init_actnorm, src/train_glow.py:60-67) — the warm-up steps of the "
+                                 "capture are rolled back and must not be the ones that initialise it")
+        guard = StateGuard(model, [optimizer])
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -65,6 +73,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.out = train_step(model, optimizer, batch, self.noise)
         self.native_launches = _lib.launch_count - c0
+        guard.restore()
 
     def __call__(self, input, noise=None):
         """input: {'img','label'} on the host (pinned) or the device; returns the output dict of device
@@ -73,5 +82,6 @@ class GraphedTrainStep:
         self.label.copy_(input["label"], non_blocking=True)
         if self.noise is not None and noise is not None:
             self.noise.copy_(noise, non_blocking=True)
+        self.optimizer.sync_hyper()          # lr schedulers: the captured Adam reads lr from a staged device buffer
         self.graph.replay()
         return self.out

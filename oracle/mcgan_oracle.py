@@ -18,7 +18,7 @@ The arithmetic of the reference lives in PyTorch itself (unpinned; README.md:8 c
 requirements.txt that is not shipped), so the oracle calls the same torch CPU ops.  Parity
 pinning: the reference has no tests or golden vectors; this oracle is
 pinned against the reference imported from /root/reference in this container
-(tests/test_oracle_vs_reference.py, run when that tree exists) and against the fixtures in
+(tests/test_oracle_golden.py) through the fixtures in
 tests/golden/ that oracle/make_golden.py generated FROM THE REFERENCE.
 """
 import torch

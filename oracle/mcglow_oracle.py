@@ -131,3 +131,61 @@ def train_step(sd, opt, img, label, num_mode, noise):
 
 def make_adam(sd, lr=3e-4):
     return Adam(trainable(sd), lr, (0.9, 0.999))
+
+
+# ----------------------------------------------------------------------------- sampling path (reverse)
+def coupling_reverse(out, ind, sd, pre):
+    """AffineCoupling.reverse (src/models/mcglow.py:166-175): in_b = out_b / sigmoid(log_s + 2) - t."""
+    out_a, out_b = out.chunk(2, 1)
+    h = F.conv2d(out_a, sd[pre + 'net.0.module.weight'], sd[pre + 'net.0.module.bias'], padding=1)
+    h = F.relu(actnorm(h, sd, pre + 'net.1.module.', False, False))
+    h = mc_mask(h, ind, sd[pre + 'net.3.codebook'])
+    h = F.conv2d(h, sd[pre + 'net.4.module.weight'], sd[pre + 'net.4.module.bias'])
+    h = F.relu(actnorm(h, sd, pre + 'net.5.module.', False, False))
+    h = mc_mask(h, ind, sd[pre + 'net.7.codebook'])
+    log_s, t = zero_conv(h, sd, pre + 'net.8.module.').chunk(2, 1)
+    in_b = out_b / torch.sigmoid(log_s + 2) - t
+    return torch.cat([out_a, in_b], 1)
+
+
+def flow_reverse(out, ind, sd, pre):
+    """Flow.reverse (src/models/mcglow.py:195-201): coupling^-1, invconv^-1 (conv with W^-1, :114-116),
+    actnorm^-1 (output / scale - loc, :54-55)."""
+    x = coupling_reverse(out, ind, sd, pre + 'coupling.')
+    w = invconv_weight(sd, pre + 'invconv.')
+    x = F.conv2d(x, w.squeeze().inverse().unsqueeze(2).unsqueeze(3))
+    return x / sd[pre + 'actnorm.scale'] - sd[pre + 'actnorm.loc']
+
+
+def block_reverse(output, ind, sd, pre, split, eps, reconstruct):
+    """Block.reverse (src/models/mcglow.py:241-265)."""
+    x = output
+    if reconstruct:
+        x = torch.cat([output, eps], 1) if split else eps
+    elif split:
+        mean, log_sd = zero_conv(x, sd, pre + 'prior.').chunk(2, 1)
+        x = torch.cat([output, mean + torch.exp(log_sd) * eps], 1)
+    else:
+        mean, log_sd = zero_conv(torch.zeros_like(x), sd, pre + 'prior.').chunk(2, 1)
+        x = mean + torch.exp(log_sd) * eps
+    k = 0
+    while (pre + f'flows.{k}.actnorm.loc') in sd:
+        k += 1
+    for i in range(k - 1, -1, -1):
+        x = flow_reverse(x, ind, sd, pre + f'flows.{i}.')
+    b, c, h, w = x.shape
+    return x.view(b, c // 4, 2, 2, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b, c // 4, h * 2, w * 2)
+
+
+def reverse(z, label, sd, num_mode, reconstruct):
+    """MCGlow.reverse (src/models/mcglow.py:314-325); ``generate`` is reverse(z ~ N(0, T), reconstruct=False)."""
+    ind = one_hot(label, num_mode)
+    n_blocks = 0
+    while f'blocks.{n_blocks}.prior.scale' in sd:
+        n_blocks += 1
+    x = None
+    for i in range(n_blocks):
+        b = n_blocks - 1 - i
+        x = block_reverse(z[-1] if i == 0 else x, ind, sd, f'blocks.{b}.', split=b < n_blocks - 1,
+                          eps=z[-(i + 1)], reconstruct=reconstruct)
+    return torch.clamp(x, -.5, .5) * 2

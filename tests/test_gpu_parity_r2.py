@@ -1,0 +1,271 @@
+"""-m gpu: parity at the configurations and on the paths that round 1 benchmarked but never checked
+(VERDICT r01 "next round" item 1): BASELINE configs[1] at its real batch (512), configs[4] at full size
+(K=16, hidden 512), element-wise parameter deltas of the fp32 pipeline, the eval-mode sampling paths, the
+optimiser's checkpoint round trip and the input feeder."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN, build_model, d_strides, load_arrays, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg_model(model_name, data_name, classes, device="cuda", **over):
+    from mcgm_b200 import cfg, models, process_control
+    cfg.update(device=device, data_name=data_name, model_name=model_name, control={"controller_rate": "0.5"})
+    process_control()
+    cfg["classes_size"] = classes
+    for k, v in over.items():
+        sec, key = k.split("__")
+        cfg[sec][key] = v
+    torch.manual_seed(0)
+    np.random.seed(0)
+    return getattr(models, model_name)()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def test_config2_batch512_full_iteration_vs_bf16_storage_oracle():
+    """BASELINE.json configs[1] — the benchmarked workload: full widths, batch 512, one reference iteration
+    (5 D + 1 G, Adam) with injected noise, GPU (bf16 storage) against the ORACLE run with simulated bf16 storage
+    on the host cores.  Stated tolerances: losses 3e-2 absolute; BN running statistics 3e-2 relative; parameter
+    update norms within 15 % (Adam's first steps are sign-like)."""
+    from mcgm_b200 import train_gan
+    from oracle import bf16_storage_sim as S
+    from oracle import mcgan_oracle as O
+    case = {"data_name": "CIFAR10", "classes": 10, "seed": 0}
+    B = 512
+    model = build_model(case, device="cuda")
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to("cuda")
+    model.train(True)
+    g = torch.Generator().manual_seed(21)
+    img = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
+    label = torch.randint(0, 10, (B,), generator=g)
+    zs = [torch.randn(B, 128, generator=g) for _ in range(6)]
+    opt = train_gan.make_optimizers(model)
+    out = train_gan.train_step(model, opt, {"img": img.cuda(), "label": label.cuda()}, z=[z.cuda() for z in zs])
+    torch.cuda.synchronize()
+    sd_sim = O.make_trainable(sd0)
+    torch.set_num_threads(os.cpu_count())
+    with S._Patched():
+        d_sim, g_sim = O.train_iteration(sd_sim, O.make_adams(sd_sim), img, label, zs, 10, [2, 1, 1])
+    print("batch-512 iteration: gpu", float(out["loss_D"]), float(out["loss_G"]), "| bf16-storage oracle", float(d_sim), float(g_sim))
+    assert abs(float(out["loss_D"]) - float(d_sim)) < 3e-2
+    assert abs(float(out["loss_G"]) - float(g_sim)) < 3e-2
+    sd1 = model.state_dict()
+    bad = []
+    for k, v0 in sd0.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_err(sd1[k].float().cpu(), sd_sim[k]) < 3e-2, k
+        if not (v0.is_floating_point() and sd_sim[k].requires_grad):
+            continue
+        ref = float((sd_sim[k].detach() - v0).norm())
+        got = float((sd1[k].float().cpu() - v0).norm())
+        if ref > 1e-4 and abs(got - ref) > 0.15 * ref + 2.5e-4:
+            bad.append((k, got, ref))
+    assert not bad, bad[:5]
+
+
+def test_config5_full_size_glow_forward_backward_vs_oracle():
+    """BASELINE.json configs[4] at FULL size (K=16, L=3, hidden 512, 22.2 M parameters), batch 16: the
+    data-dependent init pass, the loss and every parameter gradient against the oracle on the host cores.
+    Tolerances as for the K=2 fixture: loss 2e-2, worst gradient 1.2e-1, median 3e-2."""
+    from mcgm_b200 import train_glow
+    from oracle import mcglow_oracle as G
+    model = _cfg_model("mcglow", "CIFAR10", 10)
+    assert len(model.blocks[0].flows) == 16
+    sd = G.make_trainable(model.state_dict())
+    model = model.to("cuda")
+    model.train(True)
+    g = torch.Generator().manual_seed(22)
+    B = 16
+    img = torch.rand(B, 3, 32, 32, generator=g) * 2 - 1
+    label = torch.randint(0, 10, (B,), generator=g)
+    noise = torch.rand(B, 3, 32, 32, generator=g)
+    inp = {"img": img.cuda(), "label": label.cuda()}
+    init = train_glow.init_actnorm(model, inp, noise=noise.cuda())
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref_init = G.forward(img, label, sd, 10, noise)
+    print("full glow init loss", float(init["loss"]), float(ref_init["loss"]))
+    assert abs(float(init["loss"]) - float(ref_init["loss"])) < 2e-2
+    out = model(inp, noise.cuda())
+    out["loss"].backward()
+    ref = G.forward(img, label, sd, 10, noise)
+    ref["loss"].backward()
+    print("full glow loss", float(out["loss"].detach()), float(ref["loss"].detach()))
+    assert abs(float(out["loss"].detach()) - float(ref["loss"].detach())) < 2e-2
+    for i, z in enumerate(out["z"]):
+        assert rel_err(z.detach().float().cpu(), ref["z"][i].detach()) < 3e-2
+    errs = sorted(((rel_err(p.grad.float().cpu(), sd[k].grad), k) for k, p in model.named_parameters()
+                   if sd[k].grad is not None and float(sd[k].grad.norm()) > 1e-6), reverse=True)
+    print("full glow worst gradient errors:", errs[:4], "median", errs[len(errs) // 2])
+    assert errs[0][0] < 1.2e-1, errs[:4]
+    assert errs[len(errs) // 2][0] < 3e-2
+
+
+@pytest.mark.parametrize("name", ["tiny_cifar", "tiny_omni"])
+def test_fp32_pipeline_elementwise_parameter_deltas(golden, name):
+    """north_star: "one full G+D step's losses and parameter deltas match within [1e-3 in fp32/tf32]".
+    Element-wise: delta = theta_after - theta_before of one 5D+1G iteration, fp32 pipeline vs the fp32 oracle.
+    Adam's first updates are lr * g / (|g| + eps)-like, so an element whose gradient is at the fp32 noise floor
+    can flip sign (both in the reference run at another thread count and here); the check is therefore
+      (1) >= 99.5 % of the elements of every parameter within 1e-3 * |delta_ref| + 1e-3 * lr, and
+      (2) relative Frobenius error of every parameter's delta <= 2e-2,
+    with the conv biases that feed a BatchNorm (analytically zero gradient: pure noise in the reference too)
+    masked out explicitly."""
+    from mcgm_b200 import cfg, ops, train_gan
+    from oracle import mcgan_oracle as O
+    LR = 2e-4
+    try:
+        cfg["compute_dtype"] = "fp32"
+        case, arr = golden["cases"][name], load_arrays(name)
+        model = build_model(case, device="cuda")
+        sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        model = model.to("cuda")
+        model.train(True)
+        opt = train_gan.make_optimizers(model)
+        train_gan.train_step(model, opt, {"img": arr["img"].cuda(), "label": arr["label"].cuda()}, z=[t.cuda() for t in arr["zs"]])
+        sd1 = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        sd_ref = O.make_trainable(sd0)
+        O.train_iteration(sd_ref, O.make_adams(sd_ref), arr["img"], arr["label"], list(arr["zs"]), case["classes"], d_strides(case))
+        report = []
+        for k, v0 in sd0.items():
+            if not (v0.is_floating_point() and sd_ref[k].requires_grad):
+                continue
+            if case["grad_norms"].get(k, 1.0) < 1e-5:          # bias in front of a BatchNorm: analytically zero gradient
+                continue
+            d_ref, d_got = sd_ref[k].detach() - v0, sd1[k] - v0
+            ok = ((d_got - d_ref).abs() <= 1e-3 * d_ref.abs() + 1e-3 * LR).float().mean().item()
+            report.append((ok, rel_err(d_got, d_ref), k))
+        report.sort()
+        print("fp32 deltas: lowest in-tolerance fractions", report[:3])
+        print("fp32 deltas: largest Frobenius errors", sorted(report, key=lambda r: -r[1])[:3])
+        assert report[0][0] >= 0.995, report[:3]
+        assert max(r[1] for r in report) <= 2e-2, sorted(report, key=lambda r: -r[1])[:3]
+    finally:
+        cfg["compute_dtype"] = "bf16"
+        ops.ACT_DTYPE = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def test_eval_mode_generate_matches_reference_fixtures():
+    """§8 f2, the sampling path (src/train_gan.py:197-220): eval-mode ``generate`` (BatchNorm on running
+    statistics, no power iteration in D) of MCGAN and MCVAE after train-mode forwards, against outputs of the
+    unmodified reference (tests/golden/eval_generate.npz).  bf16 storage: 3e-2 relative."""
+    arr = load_arrays("eval_generate")
+    m = _cfg_model("mcgan", "CIFAR10", 10, gan__generator_hidden_size=[64] * 4, gan__discriminator_hidden_size=[64] * 4).to("cuda")
+    label, zs = arr["gan/label"].cuda(), arr["gan/zs"].cuda()
+    m.train(True)
+    with torch.no_grad():
+        m.generate(label, zs[0])
+        m.generate(label, zs[1])
+    m.train(False)
+    with torch.no_grad():
+        out = m.generate(label, zs[2])
+        d = m.discriminate(arr["gan/generated"].cuda(), label)
+    assert rel_err(out.float().cpu(), arr["gan/generated"]) < 3e-2
+    assert rel_err(d.float().cpu(), arr["gan/d_eval"]) < 3e-2
+    u0 = m.discriminator.blocks[0].conv[0].module.weight_u.clone()
+    with torch.no_grad():
+        m.discriminate(arr["gan/generated"].cuda(), label)
+    assert torch.equal(u0, m.discriminator.blocks[0].conv[0].module.weight_u), "eval-mode D must not run the power iteration"
+
+    v = _cfg_model("mcvae", "COIL100", 100).to("cuda")
+    v.train(True)
+    with torch.no_grad():
+        v({"img": arr["vae/img"].cuda(), "label": arr["vae/label"].cuda()}, arr["vae/eps"].cuda())
+    v.train(False)
+    with torch.no_grad():
+        gen = v.generate(arr["vae/label"].cuda(), arr["vae/z"].cuda())
+        ev = v({"img": arr["vae/img"].cuda(), "label": arr["vae/label"].cuda()})
+    with open(os.path.join(GOLDEN, "r2_golden.json")) as f:
+        r2 = json.load(f)
+    assert rel_err(gen.float().cpu(), arr["vae/generated"]) < 3e-2
+    assert rel_err(ev["img"].float().cpu(), arr["vae/eval_recon"]) < 3e-2
+    assert abs(float(ev["loss"]) - r2["vae_eval_loss"]) < 2e-2
+
+
+def test_glow_generate_and_reconstruct_match_reference_fixtures():
+    """§8 f2: MCGlow ``generate`` (reverse from z ~ N(0, 0.7), priors sampled through ZeroConv2d) and
+    ``reverse(reconstruct=True)`` on the flow kernels against the unmodified reference."""
+    from test_oracle_r2 import fill_glow_zero_layers
+    from mcgm_b200 import train_glow
+    arr = load_arrays("eval_generate")
+    m = _cfg_model("mcglow", "CIFAR10", 10, glow__K=2, glow__hidden_size=128).to("cuda")
+    inp = {"img": arr["glow/img"].cuda(), "label": arr["glow/label"].cuda()}
+    train_glow.init_actnorm(m, inp, noise=arr["glow/noise"].cuda())
+    fill_glow_zero_layers(list(m.named_parameters()))
+    m.train(False)
+    with torch.no_grad():
+        gen = m.generate(inp["label"], [arr[f"glow/z{i}"].cuda() for i in range(3)])
+        fz = m(inp, arr["glow/noise"].cuda())["z"]
+        rec = m.reverse({"z": fz, "label": inp["label"], "reconstruct": True})["img"]
+    print("glow generate err", rel_err(gen.float().cpu(), arr["glow/generated"]), "reconstruct err", rel_err(rec.float().cpu(), arr["glow/reconstructed"]))
+    assert rel_err(gen.float().cpu(), arr["glow/generated"]) < 3e-2
+    assert rel_err(rec.float().cpu(), arr["glow/reconstructed"]) < 3e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def test_fused_adam_state_dict_round_trips_with_torch_adam():
+    """the reference checkpoints ``optimizer.state_dict()`` and resumes from it (src/train_vae.py:86).
+    A torch.optim.Adam state loads into FusedAdam (and back) and both continue identically."""
+    from mcgm_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    net_a = torch.nn.Sequential(torch.nn.Linear(33, 40), torch.nn.Tanh(), torch.nn.Linear(40, 7)).cuda()
+    net_b = copy.deepcopy(net_a)
+    x = torch.randn(16, 33, device="cuda")
+
+    def step(net, opt, use_model_zero=False):
+        (net.zero_grad() if use_model_zero else opt.zero_grad())      # model.zero_grad() sets grads to None
+        net(x).square().mean().backward()
+        opt.step()
+
+    ta = torch.optim.Adam(net_a.parameters(), lr=3e-3, betas=(0.8, 0.99))
+    for _ in range(3):
+        step(net_a, ta)
+    net_b.load_state_dict(net_a.state_dict())
+    fb = FusedAdam(net_b.parameters(), lr=1.0)                         # wrong hyper-parameters on purpose
+    fb.load_state_dict(ta.state_dict())
+    assert fb.param_groups[0]["lr"] == 3e-3 and int(fb.step_dev) == 3
+    for _ in range(2):
+        step(net_a, ta)
+        step(net_b, fb, use_model_zero=True)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert rel_err(pb.detach().cpu(), pa.detach().cpu()) < 2e-5
+    # and back: FusedAdam.state_dict() -> torch.optim.Adam
+    net_c = copy.deepcopy(net_b)
+    tc = torch.optim.Adam(net_c.parameters(), lr=1.0)
+    tc.load_state_dict(fb.state_dict())
+    step(net_b, fb)
+    step(net_c, tc)
+    for pb, pc in zip(net_b.parameters(), net_c.parameters()):
+        assert rel_err(pc.detach().cpu(), pb.detach().cpu()) < 2e-5
+
+
+def test_device_feeder_and_meter():
+    """§8 f4: batches produced by a host loader arrive bit-identical on the device, in order, through the pinned
+    staging ring; DeviceMeter's means equal the reference Logger.append running means."""
+    from mcgm_b200 import data
+    ds = data.SyntheticImages(64, [3, 32, 32], 10, seed=3)
+    # list-of-samples loader with the reference's collate_fn (dict of lists) and a pre-collated loader
+    loader = torch.utils.data.DataLoader(ds, batch_size=16, shuffle=False, collate_fn=data.input_collate)
+    got = [{k: v.clone() for k, v in b.items()} for b in data.DeviceFeeder(loader, "cuda", depth=2)]
+    assert len(got) == 4
+    for i, b in enumerate(got):
+        ref = data.collate(data.input_collate([ds[j] for j in range(16 * i, 16 * i + 16)]))
+        assert torch.equal(b["img"].cpu(), ref["img"]) and torch.equal(b["label"].cpu(), ref["label"])
+        assert torch.equal(b["img"].cpu(), ds.batch(torch.arange(16 * i, 16 * i + 16))["img"])
+    meter = data.DeviceMeter("cuda", flush_every=2)
+    vals = [(0.5, 1.5, 16), (0.25, 2.5, 16), (1.0, 0.5, 8)]
+    for a, b, n in vals:
+        meter.append({"loss_D": torch.tensor(a, device="cuda"), "loss_G": torch.tensor(b, device="cuda")}, "train", n)
+    mean = meter.mean
+    tot = sum(n for _, _, n in vals)
+    assert abs(mean["train/loss_D"] - sum(a * n for a, _, n in vals) / tot) < 1e-9
+    assert abs(mean["train/loss_G"] - sum(b * n for _, b, n in vals) / tot) < 1e-9

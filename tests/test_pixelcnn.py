@@ -1,0 +1,119 @@
+"""-m gpu: the MC-gated PixelCNN (src/models/mcpixelcnn.py) on the B200 kernels — the gated
+activation kernel pair and the explicit-tap convs against plain torch, the model against the oracle and the
+fixture generated from the unmodified reference.  bf16 storage; tolerances as for the other families."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import GOLDEN, load_arrays, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def test_explicit_tap_conv_matches_cropped_conv2d():
+    """vertical (k/2+1) x k and horizontal 1 x (k/2+1) stacks: forward, data gradient, weight and bias gradient
+    against F.conv2d + crop on bf16-representable inputs (fp32 accumulate on both sides)."""
+    from mcgm_b200 import ops
+    torch.manual_seed(0)
+    N, H, C, K = 6, 8, 64, 128
+    for (R, S, pad) in ((4, 7, (3, 3)), (2, 3, (1, 1)), (1, 4, (0, 3)), (1, 2, (0, 1))):
+        x = _bf(torch.randn(N, C, H, H)).cuda().requires_grad_(True)
+        w = _bf(torch.randn(K, C, R, S) * 0.05).cuda().requires_grad_(True)
+        b = torch.randn(K).cuda().requires_grad_(True)
+        ref = F.conv2d(x, w, b, padding=pad)[:, :, :H, :H]
+        g = _bf(torch.randn_like(ref))
+        ref.backward(g)
+        xn = x.detach().permute(0, 2, 3, 1).contiguous().bfloat16().requires_grad_(True)
+        w2 = w.detach().clone().requires_grad_(True)
+        b2 = b.detach().clone().requires_grad_(True)
+        out = ops.ConvTapsFn.apply(xn, w2, b2, pad, None)
+        out.backward(g.permute(0, 2, 3, 1).contiguous().bfloat16())
+        assert rel_err(out.float().permute(0, 3, 1, 2).cpu(), ref.detach().cpu()) < 6e-3, (R, S)
+        assert rel_err(xn.grad.float().permute(0, 3, 1, 2).cpu(), x.grad.cpu()) < 6e-3, (R, S)
+        assert rel_err(w2.grad.cpu(), w.grad.cpu()) < 2e-4, (R, S)
+        assert rel_err(b2.grad.cpu(), b.grad.cpu()) < 2e-4, (R, S)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_gated_activation_kernels_match_torch(training):
+    from mcgm_b200 import MultimodalController, ops
+    torch.manual_seed(1)
+    N, H, C, M = 10, 8, 64, 10
+    mc = MultimodalController(C, M, 0.5).cuda()
+    labels = torch.randint(0, M, (N,)).cuda()
+    h = _bf(torch.randn(N, 2 * C, H, H)).cuda().requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).cuda()
+    bn.weight.data.normal_(1.0, 0.2); bn.bias.data.normal_(0, 0.2)
+    bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    bn2 = torch.nn.BatchNorm2d(C).cuda()
+    bn2.load_state_dict(bn.state_dict())
+    bn.train(training); bn2.train(training)
+    xh, yh = h.chunk(2, dim=1)
+    ref = F.relu(bn(xh)) * torch.sigmoid(yh) * mc.codebook[labels].view(N, C, 1, 1)
+    g = _bf(torch.randn_like(ref))
+    ref.backward(g)
+    hn = h.detach().permute(0, 2, 3, 1).contiguous().bfloat16().requires_grad_(True)
+    out = ops.SGateFn.apply(hn, bn2.weight, bn2.bias, ops.as_labels(labels), mc.packed_bits(), bn2.running_mean, bn2.running_var,
+                            bn2.momentum, bn2.eps, training)
+    out.backward(g.permute(0, 2, 3, 1).contiguous().bfloat16())
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu(), ref.detach().cpu()) < 6e-3
+    assert rel_err(hn.grad.float().permute(0, 3, 1, 2).cpu(), h.grad.cpu()) < 8e-3
+    assert rel_err(bn2.weight.grad.cpu(), bn.weight.grad.cpu()) < 1e-3
+    assert rel_err(bn2.bias.grad.cpu(), bn.bias.grad.cpu()) < 1e-3
+    if training:
+        assert rel_err(bn2.running_mean.cpu(), bn.running_mean.cpu()) < 1e-5
+        assert rel_err(bn2.running_var.cpu(), bn.running_var.cpu()) < 1e-5
+
+
+def test_pixelcnn_model_vs_oracle_and_reference_fixture():
+    from mcgm_b200 import cfg, models, process_control
+    from oracle import mcpixelcnn_oracle as P
+    with open(os.path.join(GOLDEN, "r2_golden.json")) as f:
+        case = json.load(f)["pixelcnn_small"]
+    arr = load_arrays("pixelcnn_small")
+    cfg.update(device="cuda", data_name="CIFAR10", model_name="mcpixelcnn", control={"controller_rate": "0.5"})
+    process_control()
+    cfg["classes_size"] = 10
+    cfg["pixelcnn"]["num_layer"], cfg["pixelcnn"]["hidden_size"] = case["num_layer"], case["hidden_size"]
+    torch.manual_seed(0)
+    model = models.mcpixelcnn()
+    sd = P.make_trainable(model.state_dict())
+    model = model.to("cuda")
+    model.train(True)
+    inp = {"img": arr["img"].cuda(), "label": arr["label"].cuda()}
+    out = model(inp)
+    out["loss"].backward()
+    ref = P.forward(arr["img"], arr["label"], sd, 10)
+    ref["loss"].backward()
+    print("pixelcnn loss", float(out["loss"].detach()), float(ref["loss"].detach()), case["loss_fwd"])
+    assert abs(float(out["loss"].detach()) - case["loss_fwd"]) < 2e-2
+    assert rel_err(out["logits"].detach().float().cpu()[:4], arr["logits"]) < 3e-2
+    errs = sorted(((rel_err(p.grad.float().cpu(), sd[k].grad), k) for k, p in model.named_parameters()
+                   if sd[k].grad is not None and float(sd[k].grad.norm()) > 1e-6), reverse=True)
+    print("pixelcnn worst gradient errors:", errs[:4], "median", errs[len(errs) // 2])
+    assert errs[0][0] < 1.2e-1, errs[:4]
+    assert errs[len(errs) // 2][0] < 3e-2
+    # mask 'A' is applied in place on the stored weights, as make_causal does
+    assert float(model.layers[0].vert_stack.weight[:, :, -1].abs().max()) == 0.0
+    assert float(model.layers[0].horiz_stack.weight[:, :, :, -1].abs().max()) == 0.0
+    # eval mode (running statistics)
+    model.train(False)
+    with torch.no_grad():
+        ev = model(inp)
+    assert abs(float(ev["loss"]) - case["loss_eval"]) < 2e-2
+    assert rel_err(ev["logits"].float().cpu()[:4], arr["logits_eval"]) < 3e-2
+    # causality: the logits at (i, j) do not depend on the code at (i, j) or later positions
+    code2 = arr["img"].clone()
+    code2[:, 4, 4:] = (code2[:, 4, 4:] + 7) % 512
+    code2[:, 5:, :] = (code2[:, 5:, :] + 3) % 512
+    with torch.no_grad():
+        ev2 = model({"img": code2.cuda(), "label": arr["label"].cuda()})
+    a, b = ev["logits"].float().cpu(), ev2["logits"].float().cpu()
+    assert torch.equal(a[:, :, :4, :], b[:, :, :4, :]) and torch.equal(a[:, :, 4, :5], b[:, :, 4, :5])

@@ -36,12 +36,13 @@ prof, ops.PROFILE = ops.PROFILE, None
 total = e0.elapsed_time(e1)
 rows = {}
 for tag, recs in prof.items():
-    for a, b, work, desc in recs:
+    for a, b, work, desc, _ref in recs:
         r = rows.setdefault((tag, desc), [0, 0.0, 0.0])
         r[0] += 1; r[1] += a.elapsed_time(b); r[2] += work
 acc = sum(r[1] for r in rows.values())
 print(f"eager iteration {total:.2f} ms, bracketed native calls {acc:.2f} ms")
 print(f"{'tag':6s} {'shape':58s} {'n':>4s} {'ms':>8s} {'%':>6s} {'us/call':>8s} {'rate':>10s}")
 for (tag, desc), (n, ms, work) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
-    rate = work / (ms * 1e-3) / (1e9 if tag == "gate" else 1e12)
-    print(f"{tag:6s} {desc:58s} {n:4d} {ms:8.3f} {100 * ms / acc:6.2f} {ms / n * 1e3:8.1f} {rate:8.1f} {'GB/s' if tag == 'gate' else 'TF/s'}")
+    hbm = tag in ("gate", "thin")
+    rate = work / (ms * 1e-3) / (1e9 if hbm else 1e12)
+    print(f"{tag:6s} {desc:58s} {n:4d} {ms:8.3f} {100 * ms / acc:6.2f} {ms / n * 1e3:8.1f} {rate:8.1f} {'GB/s' if hbm else 'TF/s'}")
