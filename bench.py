@@ -403,20 +403,20 @@ def run_native(args, C):
         for _ in range(n_steps):
             yield dataset.batch(torch.randint(0, len(dataset), (B,), generator=idx_gen))
 
+    feeder = data.DeviceFeeder(None, dev, depth=2)
+
     def run_e2e(n_steps):
-        feeder = data.DeviceFeeder(loader(n_steps), dev, depth=2)
         out = None
-        for batch in feeder:
+        for batch in feeder.iterate(loader(n_steps)):
             out = W.step(batch)
             host_loss.copy_(W.losses(out), non_blocking=True)
-        return feeder
 
-    run_e2e(2)
+    run_e2e(3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    feeder = run_e2e(args.steps)
+    run_e2e(args.steps)
     torch.cuda.synchronize()
     wall = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

@@ -128,6 +128,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # developer A/B knobs of the kernels (tools/, bring-up): MCGM_DEBUG_SET="key=value,key=value" -> mcgm_debug_set
+    for kv in filter(None, os.environ.get("MCGM_DEBUG_SET", "").split(",")):
+        k, v = kv.split("=")
+        if lib.mcgm_debug_set(int(k), int(v)) != 0:
+            raise RuntimeError(f"mcgm_debug_set({k}, {v}) failed")
     return lib
 
 

@@ -19,6 +19,9 @@ cfg = {
     "init_seed": 0,
     # B200 build: storage type of activations inside the fused blocks ('bf16'; fp32 accumulate)
     "compute_dtype": "bf16",
+    # B200 build: BatchNorm batch statistics accumulated by the producing conv's (staged) epilogue instead of a pass
+    # over the tensor (MCGM_BN_STATS_IN_CONV=0 switches back to the separate statistics kernels)
+    "bn_stats_in_conv": __import__("os").environ.get("MCGM_BN_STATS_IN_CONV", "1") == "1",
 }
 
 # data_name -> (data_shape, generate_per_mode)                      src/utils.py:107-127

@@ -137,6 +137,9 @@ struct DescKnobs {
   uint32_t mt2 = 1, mt2_256 = 0;             // forward conv: two M tiles per CTA (BN <= 128 / BN = 256)
   uint32_t nt2 = 1;                          // wgrad: two filter taps per CTA (Cin tile 128)
   uint32_t wg_splits = 0;                    // wgrad: force the split-K factor (0 = automatic)
+  // staged forward epilogue: bit 2 = fetch the residual / ReLU-sign tile by TMA load (else through registers)
+  uint32_t tma_epi = 7;
+  uint32_t cluster = 2;                      // forward conv: CTAs per cluster sharing one weight slab by TMA multicast (1, 2, 4)
 };
 static DescKnobs g_knobs;
 
@@ -164,6 +167,7 @@ struct ConvFwdParams {
   signed char tap_dh[4 * kMaxTaps], tap_dw[4 * kMaxTaps];   // [phase][tap]
   int TW, TH, TN, tiles_w, tiles_h;
   int n_tiles, m_super, total_tiles;
+  int m_super_c, total_ctiles;               // the same counted in CLUSTER tiles (CL consecutive CTA tiles, one per CTA of a cluster)
   int kpt, num_kb;
   uint64_t desc_templ;
   uint32_t idesc;
@@ -175,17 +179,25 @@ struct ConvFwdParams {
   int words;
   int flags;
   int quad;                                  // 4 consecutive tile pixels never straddle a tile row (TW % 4 == 0)
-  float* stats;                              // STATS kernels: [4 * gridDim][2][Cout] per-warp-row sum / sum of squares
+  int tma_epi;                               // epilogue stages bf16 tiles in shared memory and writes them with TMA stores
+  int side_tma;                              // ... and fetches the residual / ReLU-sign tile with a TMA load into the same buffer
+  float* stats;                              // tma_epi only: [4 * gridDim][2][Cout] per-warp sum / sum of squares of the stored values
   void* out;
 };
 
 // MT = number of 128-pixel M tiles one CTA accumulates against the SAME weight slab: the B
 // bytes fetched from L2 per MMA halve with MT = 2 (the kernel is L2->SM bound, not tensor bound).
-template <int BN, int MT>
+// TMAEPI: the epilogue owns kEpiGroups 16 KB staging tiles (128 pixels x 64 channels bf16, 128B-swizzled = one TMA box)
+// carved out of the operand ring: warps write their accumulator rows there (conflict-free thanks to the swizzle) and ONE
+// thread per group stores the tile with cp.async.bulk.tensor — no per-thread global stores, no register transposes.
+static constexpr int kSlabBytes = kTileM * 64 * 2;   // 16 KB
+template <int BN, int MT, bool TMAEPI = false>
 struct FwdCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kEpiGroups = BN >= 128 ? 2 : 1;
+  static constexpr int kStagingBytes = TMAEPI ? kEpiGroups * kSlabBytes : 0;
+  static constexpr int kStages = ((196608 - kStagingBytes) / kStageBytes) > 8 ? 8 : ((196608 - kStagingBytes) / kStageBytes);
   static constexpr int kAccStages = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int kTmemRaw = kAccStages * MT * BN;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
@@ -193,7 +205,8 @@ struct FwdCfg {
   // gets is not).  The total must stay under the 196 KB shared-memory carve-out (200704 B incl. 1 KB the
   // system reserves): one step more and L1 drops from 60 KB to 28 KB, which costs the epilogue's row-strided
   // loads and stores 10-40 % (measured on the 1x1 / thin / residual convs).
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kMaxBiasBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kMaxBiasBytes;
+  static_assert(kStages >= 2, "forward conv needs at least two pipeline stages");
   static_assert(kSmemBytes + 1024 <= 200704, "forward conv must fit the 196 KB carve-out");
 };
 
@@ -223,22 +236,6 @@ __device__ __forceinline__ void quad_transpose(uint4 (&u)[4], const int lane) {
   }
 }
 
-// Column sums of a 32 x 32 tile held one ROW per lane: after five exchange-and-add steps lane l holds the
-// sum over the 32 rows of column l (31 shuffles instead of 32 x 5 for per-column butterflies).
-__device__ __forceinline__ float warp_column_sums(float (&s)[32], const int lane) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const bool hi = lane & m;
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-      const float send = hi ? s[i] : s[i + m];
-      const float keep = hi ? s[i + m] : s[i];
-      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-    }
-  }
-  return s[0];
-}
-
 // One chunk (CW <= 32 consecutive output channels of one pixel) of the fused epilogue.  Executed by ALL
 // lanes of the warp (quad shuffles inside); `row_ok` only predicates the global accesses of this row.
 //   acc    fp32 bit patterns from TMEM
@@ -249,14 +246,11 @@ __device__ __forceinline__ float warp_column_sums(float (&s)[32], const int lane
 //          read in place; the fp32 parity pipeline (TF32) reads everything in place.
 //   QUAD   bf16 rows move as quad-transposed 64-byte runs (needs CW == 32 and quads that do not straddle a
 //          tile row: p.quad)
-//   STATS  also return this chunk's per-column sum and sum of squares over the warp's 32 rows (lane l:
-//          column col0 + l) of the values AS STORED (bf16-rounded) — the batch statistics of the BatchNorm that
-//          consumes this tensor (src/models/mcgan.py:15,20,56), so that gate needs no statistics pass of its own
-template <int CW, bool GENERIC_STORE, bool QUAD, bool STATS, typename OutT, bool TF32>
+template <int CW, bool GENERIC_STORE, bool QUAD, typename OutT, bool TF32>
 __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int flags, uint32_t (&acc)[32],
                                                const int pix, const int rpix, const int col0, const bool row_ok,
                                                const float* sbias, const uint32_t mbits, uint4 (&sd)[4],
-                                               const int lane, float& col_sum, float& col_sq) {
+                                               const int lane) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(acc[i]);
@@ -352,18 +346,6 @@ __device__ __forceinline__ void epilogue_chunk(const ConvFwdParams& p, const int
       }
       o[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if constexpr (STATS) {
-      float t[32];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) unpack16<__nv_bfloat16>(o[i], t + 8 * i);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) t[i] = row_ok ? t[i] : 0.0f;
-      float t2[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) t2[i] = t[i] * t[i];
-      col_sum = warp_column_sums(t, lane);
-      col_sq = warp_column_sums(t2, lane);
-    }
     quad_transpose(o, lane);
     const uint32_t okb = __ballot_sync(0xffffffffu, row_ok);
     const int base = lane & ~3;
@@ -423,52 +405,145 @@ __device__ __forceinline__ void side_load(const __nv_bfloat16* base, const int p
   }
 }
 
-template <int BN, int MT, typename OutT, bool TF32, bool STATS = false>
+// One 32-column chunk of the fused epilogue for the shared-memory staged path: values in, packed bf16 out.
+//   acc    fp32 bit patterns from TMEM (row = this lane's pixel)
+//   sd     the residual row (RES / RES_UP2) or the ReLU-sign row (POSMASK) of these 32 columns, one row per lane
+__device__ __forceinline__ void epilogue_chunk_pack(const int flags, const uint32_t (&acc)[32], const float* sbias,
+                                                    const uint32_t mbits, const uint4 (&sd)[4], const bool row_ok,
+                                                    uint4 (&o)[4]) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  if (flags & MCGM_EPI_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);      // warp-uniform address: broadcast
+      v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+    }
+  }
+  if (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      float r[8];
+      unpack16<__nv_bfloat16>(sd[i / 8], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i + j] += r[j];
+    }
+  }
+  if (flags & MCGM_EPI_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (flags & MCGM_EPI_MASK) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((mbits >> i) & 1u) ? v[i] : 0.0f;
+  }
+  if (flags & MCGM_EPI_POSMASK) {                          // never together with a residual on this path (host)
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      float r[8];
+      unpack16<__nv_bfloat16>(sd[i / 8], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i + j] = (r[j] > 0.0f) ? v[i + j] : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+      w[j] = row_ok ? *reinterpret_cast<uint32_t*>(&h) : 0u;     // rows outside the tensor: zeros (never stored; keep the statistics clean)
+    }
+    o[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds4(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// CL > 1: thread-block clusters of CL CTAs work on CL consecutive M tiles against the SAME weight slab.  Each CTA fetches
+// 1/CL of every weight k-block and MULTICASTS it to all CTAs of the cluster, so one L2 read feeds CL SMs: the kernel is
+// bound by the L2 -> SM operand feed (48 KB per 512 tensor-core cycles and SM), and the weights are 2/3 of those bytes
+// for the 256-wide layers.  A pipeline stage is free when EVERY CTA of the cluster has consumed it (the peers' multicasts
+// land in it), so every MMA warp signals the stage's empty barrier in all CTAs (tcgen05.commit ... multicast::cluster).
+template <int BN, int MT, typename OutT, bool TF32, int CL = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_side,
                 const ConvFwdParams p) {
-  using Cfg = FwdCfg<BN, MT>;
+  constexpr bool kTmaEpi = (sizeof(OutT) == 2) && !TF32 && BN >= 64;    // bf16 tiles of >= 64 channels: staged + TMA-stored
+  using Cfg = FwdCfg<BN, MT, kTmaEpi>;
   constexpr int kElems = TF32 ? 32 : 64;                 // operand elements per 128-byte k-block row
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();                       // 128B-swizzled TMA tiles need a 1024-byte aligned base
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr (4 B)
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], tmem ptr (4 B + pad), side[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto side_bar = [&](int g) { return bar_base + 8u * (2 * Cfg::kStages + 5 + g); };
   // bias of all n_tiles * BN (zero-padded) output channels, after the 256 B barrier block
   float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256);
   for (int i = threadIdx.x; i < p.n_tiles * BN; i += kConvThreads)
     sbias[i] = ((p.flags & MCGM_EPI_BIAS) && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;         // this CTA's rank inside its cluster
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;         // cluster index / number of clusters
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kConvThreads - 64); }
+    if (kTmaEpi && p.tma_epi) {
+      tma_prefetch_desc(&tmap_out);
+      if (p.side_tma) tma_prefetch_desc(&tmap_side);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kConvThreads - 64); mbar_init(side_bar(s), 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                // the peers' barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // a CTA tile = MT consecutive 128-pixel M tiles x one BN-wide slab of output channels
+  // a CTA tile = MT consecutive 128-pixel M tiles x one BN-wide slab of output channels; a cluster tile = CL of them that
+  // differ in the M index only.  CTA tile of cluster tile tc: (nt, ms = msc * CL + crank, ph); ms past the last tile is a
+  // dummy (every coordinate out of range: zero-filled loads, clipped stores) that keeps the cluster in lock step.
   const int tiles_per_img_block = p.tiles_w * p.tiles_h;
+  auto tile_of = [&](int tc, int& nt, int& ms, int& ph) {
+    nt = tc % p.n_tiles;
+    ms = ((tc / p.n_tiles) % p.m_super_c) * CL + crank;
+    ph = tc / (p.n_tiles * p.m_super_c);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
+      for (int tc = cid; tc < p.total_ctiles; tc += ncl) {
+        int nt, ms, ph;
+        tile_of(tc, nt, ms, ph);
         const int mt0 = ms * MT;
         const int wrow0 = ph * p.Cout + nt * BN;             // weight rows of this phase / channel slab
         int w0[MT], h0[MT], n0[MT];
@@ -488,7 +563,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
           for (int j = 0; j < MT; ++j)
             tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kElems, w0[j] + dw, h0[j] + dh, n0[j]);
-          tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kElems, wrow0);
+          if constexpr (CL == 1) {
+            tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kElems, wrow0);
+          } else {                                           // my 1/CL of the weight rows, to every CTA of the cluster
+            tma_load_2d_mc(sa + MT * kABytes + crank * (Cfg::kBBytes / CL), &tmap_w, full_bar(stage),
+                           tap * p.Cin + cb * kElems, wrow0 + crank * (BN / CL), kClusterMask);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           if (++cb == p.kpt) { cb = 0; ++tap; }
         }
@@ -498,7 +578,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (lane == 0) {
       // ===== MMA issuer =====
       int stage = 0, phase = 0, it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int tc = cid; tc < p.total_ctiles; tc += ncl, ++it) {
         const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
@@ -515,7 +595,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_any(TF32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
+          if constexpr (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), kClusterMask);      // the stage is free for the peers' multicasts too
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(as));
@@ -523,36 +604,191 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else {
     // ===== epilogue: 8 warps.  A warp may only touch TMEM lanes [32*(warp%4), +32); the two warps of a
-    // quadrant split the accumulator columns.  The epilogue is latency-, not issue-bound (ncu: one or two
-    // warps per scheduler, every global load exposed), so nothing it needs is fetched after the
-    // accumulator is ready: the bias sits in shared memory (staged once per CTA), the labels of the
-    // tile's samples plus the first codebook word and residual / ReLU-sign row are requested BEFORE the
-    // wait on the MMA, and inside the tile the TMEM load, codebook word and side row of chunk q+1 are in
-    // flight while chunk q is processed.  Two chunk bodies (even / odd buffers) in a rolled loop keep the
-    // code inside the instruction cache.  bf16 rows travel quad-transposed (see quad_transpose).
+    // quadrant split the accumulator columns.
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int tw = m % p.TW, th = (m / p.TW) % p.TH, tn = m / (p.TW * p.TH);
-    constexpr int CW = BN < 32 ? BN : 32;                    // columns per TMEM load
+    const int flags = p.flags;
+    const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
+
+    // ---------------------------------------------------------------------------------------------------------
+    // (A) bf16 tiles of >= 64 channels: shared-memory staged, TMA-stored.
+    // The accumulator of a CTA tile is cut into SLABS of 128 pixels x 64 channels = 16 KB = one TMA box with the
+    // 128B swizzle.  The warps of a GROUP (BN >= 128: the four warps of one column half; BN = 64: all eight) fill a
+    // slab: every thread converts its pixel row (fused bias / residual / ReLU / MC mask / ReLU-sign mask) and writes
+    // it as 16-byte units at unit ^ (row & 7) — the swizzle makes the 32 rows of a warp hit all banks exactly once.
+    // One thread then issues cp.async.bulk.tensor (global <- shared): no per-thread global stores, no register
+    // transposes, out-of-tensor rows clipped by the TMA unit.  The residual (or ReLU-sign source) slab is fetched BY
+    // TMA INTO THE SAME BUFFER first (side_tma) and each thread reads back exactly the units it overwrites.
+    // Optional batch statistics of the stored values (the BatchNorm that consumes this tensor): every warp sums the
+    // 32 rows it has just written, two columns per lane, conflict-free 4-byte reads — no shuffles.
+    // ---------------------------------------------------------------------------------------------------------
+    auto tile_loop_tma = [&](auto quad_tag) {
+      constexpr bool QUAD = decltype(quad_tag)::value;       // register-path side rows travel quad-transposed
+      constexpr int G = Cfg::kEpiGroups;
+      constexpr int GT = 256 / G;                            // threads per group
+      constexpr int CPS = BN >= 128 ? 2 : 1;                 // 32-column chunks of one warp inside a slab
+      constexpr int SPG = BN >= 128 ? (BN / 2) / 64 : 1;     // slabs per group and M tile
+      const int grp = BN >= 128 ? half : 0;
+      const bool leader = (quad == 0) && (BN >= 128 || half == 0) && lane == 0;
+      const uint32_t buf = staging_base + grp * kSlabBytes;
+      const uint32_t sbar = side_bar(grp);
+      const uint32_t row_addr = buf + m * 128;
+      const int sw = m & 7;
+      const int cw0 = BN >= 128 ? 0 : half * 32;             // this warp's first column inside the slab
+      const bool side_tma = p.side_tma;
+      const bool side_reg = !side_tma && (res_on || (flags & MCGM_EPI_POSMASK));
+      const __nv_bfloat16* side = res_on ? p.res : p.aux;
+      const bool stats_on = p.stats != nullptr;
+      float st_sum[SPG][2], st_sq[SPG][2];
+#pragma unroll
+      for (int k = 0; k < SPG; ++k) { st_sum[k][0] = st_sum[k][1] = st_sq[k][0] = st_sq[k][1] = 0.0f; }
+      uint32_t side_phase = 0;
+      int it = 0;
+      for (int tc = cid; tc < p.total_ctiles; tc += ncl, ++it) {
+        const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
+        int nt, ms, ph;
+        tile_of(tc, nt, ms, ph);
+        const int mt0 = ms * MT;
+        int pix[MT], rpix[MT], lab[MT], cw[MT], ch[MT], cn[MT];
+        bool valid[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int mt = mt0 + j;
+          const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+          cn[j] = (mt / tiles_per_img_block) * p.TN;
+          cw[j] = w0 * p.OS + (ph & 1);                        // TMA coordinates of the output box of this M tile
+          ch[j] = h0 * p.OS + (ph >> 1);
+          const int wg = w0 + tw, hg = h0 + th, n = cn[j] + tn;
+          valid[j] = (n < p.N) && (hg < p.Hg) && (wg < p.Wg);
+          const int h = hg * p.OS + (ph >> 1), w = wg * p.OS + (ph & 1);
+          pix[j] = (n * p.Ho + h) * p.Wo + w;
+          rpix[j] = (flags & MCGM_EPI_RES_UP2) ? (n * (p.Ho >> 1) + (h >> 1)) * (p.Wo >> 1) + (w >> 1) : pix[j];
+          lab[j] = ((flags & MCGM_EPI_MASK) && valid[j]) ? __ldg(p.labels + n) : 0;
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN);
+        bool waited = false;
+#pragma unroll
+        for (int s = 0; s < MT * SPG; ++s) {
+          const int j = s / SPG, sl = s % SPG;
+          const int c_tile = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0);       // slab's first column inside the CTA tile
+          const int c_slab = nt * BN + c_tile;                                  // ... and inside the tensor
+          const bool ok = (MT == 2 && j) ? valid[MT - 1] : valid[0];
+          // everything that does not depend on the accumulator: side rows through registers, mask words
+          uint4 sd[CPS][4];
+          uint32_t mwd[CPS];
+#pragma unroll
+          for (int k = 0; k < CPS; ++k) {
+            const int col = c_slab + cw0 + 32 * k;
+            if (side_reg)
+              side_load<32, QUAD>(side, res_on ? ((MT == 2 && j) ? rpix[MT - 1] : rpix[0]) : ((MT == 2 && j) ? pix[MT - 1] : pix[0]),
+                                  p.Cout, col, ok, sd[k], lane);
+            mwd[k] = 0u;
+            if ((flags & MCGM_EPI_MASK) && ok)
+              mwd[k] = __ldg(p.bits + (size_t)((MT == 2 && j) ? lab[MT - 1] : lab[0]) * p.words + (col >> 5));
+          }
+          // the staging buffer is free once the previous store has been read out of it; then the side slab may land in it
+          if (leader) {
+            tma_store_wait_read();
+            if (side_tma) {
+              mbar_arrive_expect_tx(sbar, kSlabBytes);
+              tma_load_4d(buf, &tmap_side, sbar, c_slab, (MT == 2 && j) ? cw[MT - 1] : cw[0], (MT == 2 && j) ? ch[MT - 1] : ch[0],
+                          (MT == 2 && j) ? cn[MT - 1] : cn[0]);
+            }
+          }
+          if (!waited) {                                       // accumulator of this CTA tile ready?
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t acc[CPS][32];
+#pragma unroll
+          for (int k = 0; k < CPS; ++k) tmem_ld32(t_row + j * BN + c_tile + cw0 + 32 * k, acc[k]);
+          if (side_tma) mbar_wait(sbar, side_phase);
+          else named_bar_sync(1 + grp, GT);
+          side_phase ^= 1u;
+          tmem_ld_wait();
+          if (s == MT * SPG - 1) {                             // accumulator drained: the MMA warp may refill it
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+          }
+#pragma unroll
+          for (int k = 0; k < CPS; ++k) {
+            const int u0 = (cw0 + 32 * k) >> 3;                // first 16-byte unit of this chunk inside the 128-byte row
+            if (side_tma) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) sd[k][u] = lds16(row_addr + (((u0 + u) ^ sw) << 4));
+            } else if (QUAD && side_reg) {
+              quad_transpose(sd[k], lane);                     // back to one row per lane
+            }
+            uint4 o[4];
+            epilogue_chunk_pack(flags, acc[k], sbias + c_slab + cw0 + 32 * k, mwd[k], sd[k], ok, o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sts16(row_addr + (((u0 + u) ^ sw) << 4), o[u]);
+          }
+          if (stats_on) {                                      // column sums of the 32 rows this warp has just written
+            __syncwarp();
+            const int col = cw0 + 2 * lane;                    // column pair inside the slab
+            if (col < cw0 + 32 * CPS) {
+              const uint32_t base = buf + (uint32_t)(quad * 32) * 128 + ((col & 7) << 1);
+              const int unit = col >> 3;
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t wv = lds4(base + r * 128 + ((unit ^ (r & 7)) << 4));
+                const float a = __uint_as_float(wv << 16), b = __uint_as_float(wv & 0xffff0000u);
+                s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+              }
+              st_sum[sl][0] += s0; st_sum[sl][1] += s1; st_sq[sl][0] += q0; st_sq[sl][1] += q1;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, GT);
+          if (leader) {
+            tma_store_4d(&tmap_out, buf, c_slab, (MT == 2 && j) ? cw[MT - 1] : cw[0], (MT == 2 && j) ? ch[MT - 1] : ch[0],
+                         (MT == 2 && j) ? cn[MT - 1] : cn[0]);
+            tma_store_commit();
+          }
+        }
+      }
+      if (leader) tma_store_wait_all();
+      if (stats_on) {
+        const int col = cw0 + 2 * lane;
+        if (col < cw0 + 32 * CPS) {
+          float* sp = p.stats + (size_t)(blockIdx.x * 4 + quad) * 2 * p.Cout;
+#pragma unroll
+          for (int sl = 0; sl < SPG; ++sl) {
+            const int c = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0) + col;      // n_tiles == 1 (host)
+            sp[c] = st_sum[sl][0]; sp[c + 1] = st_sum[sl][1];
+            sp[p.Cout + c] = st_sq[sl][0]; sp[p.Cout + c + 1] = st_sq[sl][1];
+          }
+        }
+      }
+    };
+
+    // ---------------------------------------------------------------------------------------------------------
+    // (B) every other output (fp32, TF32 pipeline, narrow tiles): per-thread stores.  The epilogue is latency-, not
+    // issue-bound, so nothing it needs is fetched after the accumulator is ready: the bias sits in shared memory, the
+    // labels of the tile's samples plus the first codebook word and residual / ReLU-sign row are requested BEFORE the
+    // wait on the MMA, and inside the tile the TMEM load, codebook word and side row of chunk q+1 are in flight while
+    // chunk q is processed.  Two chunk bodies (even / odd buffers) in a rolled loop keep the code inside the
+    // instruction cache.  bf16 rows travel quad-transposed (see quad_transpose).
+    // ---------------------------------------------------------------------------------------------------------
+    [[maybe_unused]] constexpr int CW = BN < 32 ? BN : 32;   // columns per TMEM load
     constexpr int HALF = (BN / 2 >= CW) ? BN / 2 : BN;       // columns per warp (narrow tiles: warp half 0 only)
     constexpr int NCH = HALF / CW;
     constexpr int Q = MT * NCH;                              // chunks per CTA tile and warp: 1, 2 or 4
     static_assert(Q == 1 || Q % 2 == 0, "chunk pipeline handles one chunk or pairs");
     constexpr bool kQuadOk = CW == 32 && !TF32;
     const bool works = half * HALF < BN;
-    const int flags = p.flags;
-    const bool res_on = flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2);
     const __nv_bfloat16* side = TF32 ? nullptr : (res_on ? p.res : ((flags & MCGM_EPI_POSMASK) ? p.aux : nullptr));
     auto tile_loop = [&](auto quad_tag) {
       constexpr bool QUAD = decltype(quad_tag)::value;
-      static_assert(!STATS || (CW == 32 && sizeof(OutT) == 2 && !TF32), "STATS: bf16 output, 32-column chunks");
-      float st_sum[NCH], st_sq[NCH];                           // STATS: per-lane column accumulators (n_tiles == 1)
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) st_sum[k] = st_sq[k] = 0.0f;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int tc = cid; tc < p.total_ctiles; tc += ncl, ++it) {
         const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
-        const int nt = t % p.n_tiles, ms = (t / p.n_tiles) % p.m_super, ph = t / (p.n_tiles * p.m_super);
+        int nt, ms, ph;
+        tile_of(tc, nt, ms, ph);
         const int mt0 = ms * MT;
         const int cl0 = nt * BN + half * HALF;                 // first output channel of this warp
         int pix[MT], rpix[MT], lab[MT];                        // pixel indices fit 31 bits (checked on the host)
@@ -588,20 +824,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         };
         auto run = [&](int q, uint32_t (&a)[32], uint4 (&sd)[4], uint32_t mwd) {
           const int j = q / NCH, col = cl0 + (q % NCH) * CW;
-          if (col < p.Cout) {                                  // warp-uniform
-            float cs = 0.0f, cq = 0.0f;
-            epilogue_chunk<CW, BN == 16, QUAD, STATS && QUAD, OutT, TF32>(
+          if (col < p.Cout)                                    // warp-uniform
+            epilogue_chunk<CW, BN == 16, QUAD, OutT, TF32>(
                 p, flags, a, (MT == 2 && j) ? pix[MT - 1] : pix[0], (MT == 2 && j) ? rpix[MT - 1] : rpix[0], col,
-                (MT == 2 && j) ? valid[MT - 1] : valid[0], sbias + col, mwd, sd, lane, cs, cq);
-            if constexpr (STATS) {
-              const int ci = q % NCH;
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) {
-                st_sum[k] += (k == ci) ? cs : 0.0f;
-                st_sq[k] += (k == ci) ? cq : 0.0f;
-              }
-            }
-          }
+                (MT == 2 && j) ? valid[MT - 1] : valid[0], sbias + col, mwd, sd, lane);
         };
         uint32_t acc[2][32];
         uint4 sd[2][4];
@@ -633,19 +859,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
       }
-      if constexpr (STATS) {
-        if (works) {
-          float* sp = p.stats + (size_t)(blockIdx.x * 4 + quad) * 2 * p.Cout + half * HALF + lane;
-#pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            sp[k * CW] = st_sum[k];
-            sp[p.Cout + k * CW] = st_sq[k];
-          }
-        }
-      }
     };
-    if constexpr (STATS) {
-      tile_loop(std::true_type{});                             // host guarantees p.quad
+    if constexpr (kTmaEpi) {
+      if (p.quad) tile_loop_tma(std::true_type{});
+      else tile_loop_tma(std::false_type{});
     } else if constexpr (kQuadOk) {
       if (p.quad) tile_loop(std::true_type{});
       else tile_loop(std::false_type{});
@@ -655,7 +872,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                // no CTA leaves while a peer may still signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -954,29 +1172,64 @@ static bool pick_pixel_box(int H, int W, int npix, int* bw, int* bh, int* bn) {
   return true;
 }
 
-template <int BN, int MT, typename OutT, bool TF32 = false, bool STATS = false>
-static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, ConvFwdParams p, cudaStream_t st) {
-  using Cfg = FwdCfg<BN, MT>;
-  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32, STATS>;
+struct FwdMaps {
+  CUtensorMap x, w, out, side;          // out / side: only read by kernels launched with p.tma_epi / p.side_tma
+};
+
+template <int BN, int MT, typename OutT, bool TF32 = false, int CL = 1>
+static int launch_fwd(const FwdMaps& maps, ConvFwdParams p, cudaStream_t st) {
+  constexpr bool kTmaEpi = (sizeof(OutT) == 2) && !TF32 && BN >= 64;
+  using Cfg = FwdCfg<BN, MT, kTmaEpi>;
+  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32, CL>;
+  if (!kTmaEpi) p.tma_epi = p.side_tma = 0;
+  static int max_clusters = 0;         // co-resident clusters of this kernel on this device (CL > 1)
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (CL > 1) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(CL * 148); q.blockDim = dim3(kConvThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute a{};
+      a.id = cudaLaunchAttributeClusterDimension;
+      a.val.clusterDim.x = CL; a.val.clusterDim.y = 1; a.val.clusterDim.z = 1;
+      q.attrs = &a; q.numAttrs = 1;
+      MCGM_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+      if (max_clusters < 1) return fail(MCGM_E_CUDA, "no cluster of %d CTAs fits this device", CL);
+    }
     configured = true;
   }
   int sms = sm_count();
   if (sms <= 0) return fail(MCGM_E_CUDA, "cannot query SM count");
   p.m_super = (p.m_super + MT - 1) / MT;           // in: M tiles per phase; out: CTA tiles per phase
   p.total_tiles = p.m_super * p.n_tiles * p.PH;
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(mx, mw, p);
-  MCGM_LAUNCH_CHECK();
+  p.m_super_c = (p.m_super + CL - 1) / CL;
+  p.total_ctiles = p.m_super_c * p.n_tiles * p.PH;
+  if (CL == 1) {
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps.x, maps.w, maps.out, maps.side, p);
+    MCGM_LAUNCH_CHECK();
+    return 0;
+  }
+  const int nclusters = p.total_ctiles < max_clusters ? p.total_ctiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * CL); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  MCGM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.x, maps.w, maps.out, maps.side, p));
   return 0;
 }
 
 template <int BN, int MT>
-static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const ConvFwdParams& p, bool f32, cudaStream_t st) {
-  if (p.tf32) return launch_fwd<BN, MT, float, true>(mx, mw, p, st);      // fp32 parity pipeline
-  return f32 ? launch_fwd<BN, MT, float>(mx, mw, p, st) : launch_fwd<BN, MT, __nv_bfloat16>(mx, mw, p, st);
+static int launch_fwd_t(const FwdMaps& maps, const ConvFwdParams& p, bool f32, cudaStream_t st, int cl = 1) {
+  if (p.tf32) return launch_fwd<BN, MT, float, true>(maps, p, st);      // fp32 parity pipeline
+  if (f32) return launch_fwd<BN, MT, float>(maps, p, st);
+  if constexpr ((BN == 256 && MT == 1) || (BN == 128 && MT == 2)) {     // the shapes that carry the flops: cluster variants
+    if (cl == 2) return launch_fwd<BN, MT, __nv_bfloat16, false, 2>(maps, p, st);
+    if (cl == 4) return launch_fwd<BN, MT, __nv_bfloat16, false, 4>(maps, p, st);
+  }
+  return launch_fwd<BN, MT, __nv_bfloat16>(maps, p, st);
 }
 
 template <int BN, int NT>
@@ -1062,6 +1315,8 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 7: g_knobs.mt2_256 = (uint32_t)value; break;
     case 8: g_knobs.nt2 = (uint32_t)value; break;
     case 9: g_knobs.wg_splits = (uint32_t)value; break;
+    case 10: g_knobs.tma_epi = (uint32_t)value; break;
+    case 11: g_knobs.cluster = (uint32_t)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
   }
   return 0;
@@ -1171,40 +1426,63 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   p.bias = bias; p.res = (const __nv_bfloat16*)res; p.aux = (const __nv_bfloat16*)aux;
   p.labels = labels; p.bits = bits; p.words = (Cout + 31) / 32; p.flags = flags; p.out = out;
 
-  CUtensorMap mx, mw;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f32 = out_dtype == MCGM_F32;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  // two M tiles per CTA (halves the weight bytes per MMA) whenever single tiles would need > 1 wave
+  const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles * p.PH > sms);
+  // clusters with multicast weights for the layers that carry the flops, when every SM gets several tiles anyway
+  int cl = 1;
+  if (!f32 && !tf32 && ((BN == 256 && !(pair && g_knobs.mt2_256)) || (BN == 128 && pair)) &&
+      (g_knobs.cluster == 2 || g_knobs.cluster == 4) && (long)m_tiles * p.n_tiles * p.PH >= 4L * sms)
+    cl = (int)g_knobs.cluster;
+  FwdMaps maps{};
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint32_t box[4] = {(uint32_t)kblk, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
-    if (int e = make_tmap(&mx, x, 4, dims, box, p.IS, tf32)) return e;
+    if (int e = make_tmap(&maps.x, x, 4, dims, box, p.IS, tf32)) return e;
   }
   {
     const uint64_t dims[2] = {(uint64_t)p.T * Cin, (uint64_t)p.PH * Cout};
-    const uint32_t box[2] = {(uint32_t)kblk, (uint32_t)BN};
-    if (int e = make_tmap(&mw, w, 2, dims, box, 1, tf32)) return e;
+    const uint32_t box[2] = {(uint32_t)kblk, (uint32_t)(BN / cl)};      // a cluster CTA fetches BN / cl weight rows
+    if (int e = make_tmap(&maps.w, w, 2, dims, box, 1, tf32)) return e;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool f32 = out_dtype == MCGM_F32;
-  // two M tiles per CTA (halves the weight bytes per MMA) whenever single tiles would need > 1 wave
-  int sms = sm_count();
-  if (sms <= 0) sms = 148;
-  const bool pair = g_knobs.mt2 && (m_tiles * p.n_tiles * p.PH > sms);
+  // Staged epilogue (bf16 tiles of >= 64 channels): the output tile of an M tile is the box (64 ch, TW*OS, TH*OS, TN) at
+  // (c, w0*OS + pw, h0*OS + ph, n0) of the NHWC tensor, traversal stride OS — the store-side twin of the operand loads.
+  // The residual / ReLU-sign tensor has the output's geometry, so (same resolution only) its tile is loaded by the same box.
+  const bool both_sides = (flags & (MCGM_EPI_RES | MCGM_EPI_RES_UP2)) && (flags & MCGM_EPI_POSMASK);
+  const bool tma_ok = !f32 && !tf32 && BN >= 64;
+  if (tma_ok && both_sides)
+    return fail(MCGM_E_UNSUPPORTED, "conv_fwd: a residual together with POSMASK is only available with an fp32 output");
+  if (tma_ok) {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)N};
+    const uint32_t box[4] = {64u, (uint32_t)(p.TW * p.OS), (uint32_t)(p.TH * p.OS), (uint32_t)p.TN};
+    if (int e = make_tmap(&maps.out, out, 4, dims, box, p.OS, 0)) return e;
+    p.tma_epi = 1;
+    const void* side = (flags & MCGM_EPI_RES) ? res : ((flags & MCGM_EPI_POSMASK) ? aux : nullptr);
+    if (side != nullptr && p.OS == 1 && (g_knobs.tma_epi & 4u)) {
+      if (int e = make_tmap(&maps.side, side, 4, dims, box, 1, 0)) return e;
+      p.side_tma = 1;
+    }
+  }
   p.m_super = m_tiles;           // launch_fwd turns this into ceil(m_tiles / MT)
   if (stats != nullptr) {
-    // batch statistics of the output for the BatchNorm that consumes it, accumulated by the epilogue
-    if (!(BN == 256 && p.n_tiles == 1 && !tf32 && !f32 && p.quad) || (flags & (MCGM_EPI_RELU | MCGM_EPI_MASK | MCGM_EPI_POSMASK | MCGM_EPI_TANH)))
-      return fail(MCGM_E_UNSUPPORTED, "conv_fwd_bnstats: needs Cout = 256, bf16 operands and output, a linear epilogue and tile rows of >= 4 pixels");
+    // batch statistics of the STORED output for the BatchNorm that consumes it, accumulated by the staged epilogue
+    if (!(p.tma_epi && p.n_tiles == 1))
+      return fail(MCGM_E_UNSUPPORTED, "conv_fwd_bnstats: needs a bf16 output with Cout in {64, 128, 256} (one channel tile, staged epilogue)");
     MCGM_CHECK_ARG(stat_slots_host, "conv_fwd_bnstats: stat_slots_host is NULL");
-    const long total = (long)m_tiles * p.n_tiles * p.PH;
-    *stat_slots_host = 4 * (int)(total < sms ? total : sms);
+    // four slots (one per epilogue warp row) for every CTA the device can hold; CTAs that are not launched leave zeros
+    *stat_slots_host = 4 * sms;
+    MCGM_CUDA(cudaMemsetAsync(stats, 0, (size_t)4 * sms * 2 * Cout * sizeof(float), st));
     p.stats = stats;
-    return launch_fwd<256, 1, __nv_bfloat16, false, true>(mx, mw, p, st);
   }
   switch (BN) {
-    case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(mx, mw, p, f32, st) : launch_fwd_t<256, 1>(mx, mw, p, f32, st);
-    case 128: return pair ? launch_fwd_t<128, 2>(mx, mw, p, f32, st) : launch_fwd_t<128, 1>(mx, mw, p, f32, st);
-    case 64: return pair ? launch_fwd_t<64, 2>(mx, mw, p, f32, st) : launch_fwd_t<64, 1>(mx, mw, p, f32, st);
-    case 32: return launch_fwd_t<32, 1>(mx, mw, p, f32, st);
-    default: return launch_fwd_t<16, 1>(mx, mw, p, f32, st);
+    case 256: return (pair && g_knobs.mt2_256) ? launch_fwd_t<256, 2>(maps, p, f32, st) : launch_fwd_t<256, 1>(maps, p, f32, st, cl);
+    case 128: return pair ? launch_fwd_t<128, 2>(maps, p, f32, st, cl) : launch_fwd_t<128, 1>(maps, p, f32, st);
+    case 64: return pair ? launch_fwd_t<64, 2>(maps, p, f32, st) : launch_fwd_t<64, 1>(maps, p, f32, st);
+    case 32: return launch_fwd_t<32, 1>(maps, p, f32, st);
+    default: return launch_fwd_t<16, 1>(maps, p, f32, st);
   }
 }
 

@@ -59,6 +59,43 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// ---- thread-block clusters -------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of every CTA of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tile load delivered to the SAME shared-memory offset (and signalled on the mbarrier at the same offset) in every
+// CTA of the cluster whose bit is set in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// shared -> global tile store (bulk async-group completion): issued by ONE thread after every writer of the tile
+// has executed fence.proxy.async and the writers have been synchronised
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed stores of this thread have finished READING shared memory (the buffer may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have fully completed (global writes visible)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA / tcgen05)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // whole warp; writes the allocated base address to *smem_dst
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -99,6 +136,12 @@ __device__ __forceinline__ void umma_any(bool tf32, uint32_t tmem_d, uint64_t ad
 // mbarrier arrives once all previously issued tcgen05 ops of this thread retire
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ... and arrives on the mbarrier at the same offset in every CTA of the cluster selected by `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i gets lane (base_lane + i)

@@ -130,6 +130,12 @@ class DeviceFeeder:
         except BaseException as e:          # surface loader errors in the consumer
             q.put(e)
 
+    def iterate(self, loader):
+        """Iterate another loader through the same staging ring (pinned and device buffers are kept: no
+        cudaHostAlloc / cudaMalloc — both synchronise the device — after the first pass)."""
+        self.loader = loader
+        return iter(self)
+
     def __iter__(self):
         q, free = queue.Queue(maxsize=self.depth), queue.Queue()
         for s in range(self.depth):

@@ -113,14 +113,15 @@ def _sync_act_dtype():
 
 
 _pack_cache = {}
-_packs_force = False      # set while capturing re-playable graph segments: the cache check is capture-time only
+# ops.PACKS_FORCE is set while re-playable graph SEGMENTS are captured: the cache check below happens at capture time
+# only, so a segment must re-pack inside the graph (the parameters change between replays of different segments)
 
 
 def _packs(weight):
     """bf16 (KRSC, flipped CRSK) copies of a parameter, cached until the parameter changes."""
     key = id(weight)
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1] is weight and not _packs_force:
+    if hit is not None and hit[0] == weight._version and hit[1] is weight and not ops.PACKS_FORCE:
         return hit[2]
     packs = ops.pack_weight(weight.detach())
     _pack_cache[key] = (weight._version, weight, packs)
@@ -128,13 +129,14 @@ def _packs(weight):
 
 
 _up2_cache = {}
+ops.PACK_CACHES += [_pack_cache, _up2_cache]
 
 
 def _up2_packs(weight):
     """Phase / adjoint weights of an upsample-fused 3x3 conv, cached like ``_packs``."""
     key = id(weight)
     hit = _up2_cache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1] is weight and not _packs_force:
+    if hit is not None and hit[0] == weight._version and hit[1] is weight and not ops.PACKS_FORCE:
         return hit[2]
     packs = ops.up2_conv_packs(weight.detach())
     _up2_cache[key] = (weight._version, weight, packs)
@@ -196,10 +198,11 @@ class GenResBlock(nn.Module):
         if self.stride != 2:
             raise ValueError('Not valid stride (the fused generator block upsamples by 2)')
         t = self.training
-        # epilogue statistics are OFF by default: with the thread-per-row TMEM layout the column reduction costs
-        # the 256-wide convs more (+2.6 ms / iteration) than the statistics passes it removes (-1.7 ms) — measured,
-        # DESIGN.md §7.  cfg['bn_stats_in_conv'] = True switches them on (parity-tested either way).
-        ws = t and bool(cfg.get('bn_stats_in_conv', False))
+        # epilogue statistics (default ON): the staged epilogue sums the tile it has just written to shared memory —
+        # two columns per lane, no shuffles — so the statistics pass over the tensor disappears (-1.07 ms / iteration
+        # measured; round 1's shuffle-based column sums cost more than they saved).  cfg['bn_stats_in_conv'] = False
+        # switches back to the separate statistics kernels (parity-tested either way).
+        ws = t and bool(cfg.get('bn_stats_in_conv', True))
         a, s = _bn_gate(x, self.conv[0].module, self.mc_1, ctx, t, want_raw=True, pre_stats=x_stats)   # LOW resolution
         sc = _conv(s, self.shortcut[2].module, ctx)                      # 1x1 commutes with the upsample
         c1m = self.conv[4].module                                        # Up(2) -> Conv3x3 as a 4-phase 2x2 conv

@@ -166,8 +166,8 @@ def take_stats():
 
 
 def stats_supported(x, Cout, res=None):
-    """The epilogue-statistics conv variant exists for bf16 tensors with 256 output channels and rows >= 4 px."""
-    return x.dtype == torch.bfloat16 and Cout == 256 and x.shape[2] >= 4
+    """Epilogue statistics ride on the staged (TMA-store) epilogue: bf16 tensors whose Cout is one channel tile."""
+    return x.dtype == torch.bfloat16 and Cout in (64, 128, 256)
 
 
 def bn_finalize(stats, C, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
@@ -912,6 +912,15 @@ def _pad_cols(m, cols):
     return torch.cat([m, m.new_zeros(m.shape[0], cols - m.shape[1])], 1)
 
 
+PACKS_FORCE = False             # see models/mcgan.py:_packs (graph-segment capture)
+PACK_CACHES = []                # packed-weight caches of the model files (cleared before a CUDA-graph capture)
+
+
+def clear_pack_caches():
+    """Forget every cached packed weight: the next use re-packs.  Called right before a CUDA graph is captured so that
+    the packing kernels are part of the graph no matter what ran before the capture."""
+    for c in PACK_CACHES:
+        c.clear()
 ACT_DTYPE = torch.bfloat16      # storage type of activations; torch.float32 selects the fp32 parity pipeline
 _TK = 32          # patch columns of the direct thin-conv kernels (csrc/thin_mma.cu)
 _KU = 64          # im2col width of the thin tensor (R*S*Ct <= 36 taps*channels, padded to one 64-wide K block)

@@ -144,7 +144,12 @@ class FusedAdam(torch.optim.Optimizer):
         """Same structure as ``torch.optim.Adam.state_dict()`` (the reference checkpoints it as
         'optimizer_dict' and resumes from it, src/train_vae.py:86 / resume()): loads into torch's Adam and back."""
         self._bind_state(int(self.step_dev.item()))
-        return super().state_dict()
+        sd = super().state_dict()
+        # a snapshot, not live views: torch's load_state_dict keeps the tensors it is handed when dtype / device already
+        # match, so handing out views would alias this optimiser's moments into whoever loads the dict
+        sd['state'] = {k: {kk: (vv.detach().clone() if torch.is_tensor(vv) else vv) for kk, vv in st.items()}
+                       for k, st in sd['state'].items()}
+        return sd
 
     def load_state_dict(self, state_dict):
         """Accepts a ``torch.optim.Adam`` (or FusedAdam) state_dict: moments are copied into the flat buffers,

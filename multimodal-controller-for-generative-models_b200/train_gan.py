@@ -212,6 +212,14 @@ def train_step(model, optimizer, input, z=None, reducers=None):
     return {'loss': total, 'loss_D': d_loss, 'loss_G': g_loss}
 
 
+def _bump_versions(optimizers):
+    """A replayed graph updates the parameters without Python noticing: bump their version counters so that the
+    packed-weight caches (keyed on ``Parameter._version``) re-pack on the next EAGER use (evaluation, sampling)."""
+    for o in optimizers:
+        if hasattr(o, 'flat'):
+            torch.autograd.graph.increment_version(o.flat.params)
+
+
 class GraphedTrainStep:
     """The whole training iteration (5 D + 1 G updates: forwards, backwards, Adam, noise draws)
     captured ONCE into a CUDA graph and replayed per batch.
@@ -247,6 +255,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         from . import _lib
         c0 = _lib.launch_count
+        from . import ops as _ops
+        _ops.clear_pack_caches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
@@ -265,6 +275,7 @@ class GraphedTrainStep:
             if hasattr(o, 'sync_hyper'):
                 o.sync_hyper()              # the captured Adam reads lr & co from a staged device buffer
         self.graph.replay()
+        _bump_versions(self.optimizer.values())
         return self.out
 
 
@@ -279,7 +290,7 @@ class GraphedDDPTrainStep:
     launch_form = "CUDA graph per D/G forward+backward, NCCL all-reduce + Adam between graphs (1/world folded into Adam)"
 
     def __init__(self, model, optimizer, reducers, batch_size, warmup=2, inject_noise=False):
-        from .models import mcgan as _m
+        from . import ops
         from .optim import StateGuard
         dev = next(model.parameters()).device
         shape = model.generator.data_shape
@@ -319,7 +330,10 @@ class GraphedDDPTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
-        _m._packs_force = True
+        # (round 1 set this flag on ``models.mcgan`` — which is the FACTORY FUNCTION re-exported by models/__init__, not
+        # the module: the D segment then replayed with the generator weights packed at capture time.  Found by
+        # tests/test_gpu_ddp.py; the flag now lives in ops.)
+        ops.PACKS_FORCE = True
         try:
             c0 = _lib.launch_count
             self.graph_d = torch.cuda.CUDAGraph()
@@ -331,7 +345,7 @@ class GraphedDDPTrainStep:
                 self.g_loss = g_part()
             c2 = _lib.launch_count
         finally:
-            _m._packs_force = False
+            ops.PACKS_FORCE = False
         self.native_launches = (c1 - c0 + 2) * self.n_d + (c2 - c1 + 2) * self.n_g      # + the eager Adam launches
         self.out = {'loss_D': self.d_loss, 'loss_G': self.g_loss, 'loss': None}
         guard.restore()
@@ -405,6 +419,8 @@ class GraphedDDPIngraphTrainStep:
             dist.barrier()
         from . import _lib
         c0 = _lib.launch_count
+        from . import ops as _ops
+        _ops.clear_pack_caches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
@@ -420,6 +436,7 @@ class GraphedDDPIngraphTrainStep:
         for o in self.optimizer.values():
             o.sync_hyper()
         self.graph.replay()
+        _bump_versions(self.optimizer.values())
         return self.out
 
 

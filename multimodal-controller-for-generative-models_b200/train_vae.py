@@ -69,6 +69,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         from . import _lib
         c0 = _lib.launch_count
+        from . import ops as _ops
+        _ops.clear_pack_caches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = train_step(model, optimizer, batch, self.noise)
@@ -84,4 +86,5 @@ class GraphedTrainStep:
             self.noise.copy_(noise, non_blocking=True)
         self.optimizer.sync_hyper()          # lr schedulers: the captured Adam reads lr from a staged device buffer
         self.graph.replay()
+        torch.autograd.graph.increment_version(self.optimizer.flat.params)     # packed-weight caches: re-pack on eager use
         return self.out

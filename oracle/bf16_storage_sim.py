@@ -23,14 +23,15 @@ class _Round(torch.autograd.Function):
 
 
 class _Patched:
-    """Context manager that makes the oracles (MCGAN and MCVAE) round like the bf16 pipeline:
+    """Context manager that makes the oracles (MCGAN, MCVAE, PixelCNN) round like the bf16 pipeline:
     conv weights, conv inputs coming from an fp32 image (<= 4 channels: the im2col buffer is bf16),
     conv / conv-transpose outputs with more than 4 channels (RGB outputs stay fp32), and every
     4-D masked activation."""
 
     def __enter__(self):
+        from . import mcpixelcnn_oracle as P
         from . import mcvae_oracle as V
-        self.V = V
+        self.V, self.P = V, P
         self.conv2d, self.convt, self.mask_o, self.mask_v = F.conv2d, F.conv_transpose2d, O.mc_mask, V.mc_mask
 
         def conv2d(x, w, b=None, stride=1, padding=0):
@@ -47,13 +48,13 @@ class _Patched:
         ns.conv2d = staticmethod(conv2d)
         ns.conv_transpose2d = staticmethod(conv_transpose2d)
         mask = lambda x, i, c: _Round.apply(self.mask_o(x, i, c)) if x.dim() > 2 else self.mask_o(x, i, c)  # noqa: E731
-        O.F = V.F = ns
-        O.mc_mask = V.mc_mask = mask
+        O.F = V.F = P.F = ns
+        O.mc_mask = V.mc_mask = P.mc_mask = mask
         return self
 
     def __exit__(self, *a):
-        O.F = self.V.F = F
-        O.mc_mask, self.V.mc_mask = self.mask_o, self.mask_v
+        O.F = self.V.F = self.P.F = F
+        O.mc_mask, self.V.mc_mask, self.P.mc_mask = self.mask_o, self.mask_v, self.mask_o
 
 
 def gradients(sd, z, label, num_mode, strides, simulate):

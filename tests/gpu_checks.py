@@ -459,6 +459,68 @@ def check_conv_variants():
     return rows
 
 
+def check_conv_cluster():
+    """Thread-block clusters with multicast weights (mcgm_debug_set key 11): large-M forward convs — the shapes whose
+    launch takes the cluster path — must be BIT-IDENTICAL with clusters of 1, 2 and 4 CTAs (the arithmetic is the
+    same, only the operand delivery differs), including odd tile counts (a dummy tile for the last cluster), every
+    fused epilogue and the epilogue statistics; the cluster-of-2 result is also held against torch's fp32 conv."""
+    from mcgm_b200._lib import CONV_PHASE2, CONV_S1, EPI_BIAS
+    rows = []
+    M = 10
+    cases = [("s1", 80, 32, 64, 256, 3, 0), ("s1", 75, 32, 64, 256, 3, EPI_RES), ("s1", 77, 32, 128, 256, 1, EPI_RES_UP2),
+             ("s1", 160, 32, 64, 128, 3, EPI_RES), ("s1", 151, 32, 64, 128, 3, EPI_POSMASK), ("s1", 160, 32, 128, 128, 3, EPI_RELU | EPI_MASK),
+             ("ph", 150, 16, 64, 256, 0, 0), ("ph", 321, 8, 128, 128, 0, 0)]
+    for (kind, N, H, Cin, Cout, R, fl) in cases:
+        g = torch.Generator().manual_seed(100 + N)
+        x = torch.randn(N, H, H, Cin, generator=g).to(DEV).to(torch.bfloat16)
+        bias = torch.randn(Cout, generator=g).to(DEV)
+        Ho = H if kind == "s1" else 2 * H
+        res = aux = labels = packed = None
+        if fl & EPI_RES:
+            res = torch.randn(N, Ho, Ho, Cout, generator=g).to(DEV).to(torch.bfloat16)
+        if fl & EPI_RES_UP2:
+            res = torch.randn(N, Ho // 2, Ho // 2, Cout, generator=g).to(DEV).to(torch.bfloat16)
+        if fl & EPI_POSMASK:
+            aux = torch.randn(N, Ho, Ho, Cout, generator=g).to(DEV).to(torch.bfloat16)
+        if fl & EPI_MASK:
+            packed = ops.PackedCodebook(_codebook(M, Cout, 3).to(DEV))
+            labels = torch.randint(0, M, (N,), generator=g).to(DEV).to(torch.int32)
+        if kind == "s1":
+            w = (torch.randn(Cout, R, R, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            run = lambda: ops.conv_fwd(x, w, torch.bfloat16, bias, res, aux, labels, packed, fl)       # noqa: E731
+            run_st = (lambda: ops.conv_fwd_bnstats(CONV_S1, x, w, bias, res, fl)) if not (fl & (EPI_POSMASK | EPI_MASK)) else None
+        else:
+            w = (torch.randn(4, Cout, 2, 2, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            run = lambda: ops.conv_fwd_ex(CONV_PHASE2, x, w, torch.bfloat16, bias)                     # noqa: E731
+            run_st = lambda: ops.conv_fwd_bnstats(CONV_PHASE2, x, w, bias)                             # noqa: E731
+        outs, stats = {}, {}
+        for cl in (1, 2, 4):
+            _lib.call("mcgm_debug_set", 11, cl)
+            try:
+                outs[cl] = run()
+                if run_st is not None:
+                    o2, st = run_st()
+                    stats[cl] = ops.bn_finalize(st, Cout)
+                    rows.append((f"cluster{cl} {kind} N={N} {Cin}->{Cout} f{fl:#x}: bnstats output identical", float((o2.float() != outs[cl].float()).sum()), EXACT))
+            finally:
+                _lib.call("mcgm_debug_set", 11, 2)
+        tag = f"{kind} N={N} H={H} {Cin}->{Cout} k{R} f{fl:#x}"
+        for cl in (2, 4):
+            rows.append((f"cluster{cl} == cluster1 {tag}", float((outs[cl].float() != outs[1].float()).sum()), EXACT))
+            if stats:
+                rows.append((f"cluster{cl} stats mean {tag}", rel(stats[cl][0], stats[1][0]), F32_TOL))
+                rows.append((f"cluster{cl} stats rstd {tag}", rel(stats[cl][1], stats[1][1]), F32_TOL))
+        if kind == "s1" and not (fl & (EPI_POSMASK | EPI_MASK | EPI_RES_UP2)):
+            ref = F.conv2d(nchw(x.float()), w.float().permute(0, 3, 1, 2), bias, padding=(R - 1) // 2)
+            if res is not None:
+                ref = ref + nchw(res.float())
+            rows.append((f"cluster2 vs torch fp32 conv {tag}", rel(nchw(outs[2].float()), ref), BF16_OUT))
+        if stats:
+            mref, rref = ops.bn_stats(outs[2])
+            rows.append((f"cluster2 stats vs statistics pass {tag}", max(rel(stats[2][0], mref), rel(stats[2][1], rref)), F32_TOL))
+    return rows
+
+
 ALL_KERNEL_CHECKS = [check_codebook_and_mask, check_gate, check_pool, check_conv_fwd, check_conv_epilogues,
                      check_conv_wgrad, check_thin, check_conv_variants, check_sn, check_conv_ex, check_conv_tf32]
 
@@ -569,28 +631,30 @@ def check_conv_bnstats():
     (the bf16-rounded stores), different summation order."""
     from mcgm_b200._lib import CONV_PHASE2, CONV_S1, EPI_BIAS
     rows = []
-    for (kind, N, H, Cin, res_up) in [(CONV_S1, 4, 16, 256, True), (CONV_S1, 5, 8, 256, False), (CONV_S1, 3, 32, 128, True),
-                                      (CONV_PHASE2, 4, 8, 256, False), (CONV_PHASE2, 5, 4, 256, False)]:
+    for (kind, N, H, Cin, res_up, Co) in [(CONV_S1, 4, 16, 256, True, 256), (CONV_S1, 5, 8, 256, False, 256), (CONV_S1, 3, 32, 128, True, 256),
+                                          (CONV_PHASE2, 4, 8, 256, False, 256), (CONV_PHASE2, 5, 4, 256, False, 256),
+                                          (CONV_S1, 37, 16, 128, False, 128), (CONV_S1, 150, 8, 64, True, 64), (CONV_PHASE2, 80, 8, 128, False, 128),
+                                          (CONV_S1, 300, 8, 128, False, 128), (CONV_S1, 3, 4, 64, False, 64)]:
         g = torch.Generator().manual_seed(31 + H + N)
         x = torch.randn(N, H, H, Cin, generator=g).to(DEV).to(torch.bfloat16)
-        bias = torch.randn(256, generator=g).to(DEV)
+        bias = torch.randn(Co, generator=g).to(DEV)
         if kind == CONV_S1:
-            w = (torch.randn(256, 3, 3, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
-            res = torch.randn(N, H // 2, H // 2, 256, generator=g).to(DEV).to(torch.bfloat16) if res_up else None
+            w = (torch.randn(Co, 3, 3, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            res = torch.randn(N, H // 2, H // 2, Co, generator=g).to(DEV).to(torch.bfloat16) if res_up else None
             fl = EPI_RES_UP2 if res_up else 0
             ref = ops.conv_fwd(x, w, torch.bfloat16, bias, res, None, None, None, fl)
             out, st = ops.conv_fwd_bnstats(kind, x, w, bias, res, fl)
         else:
-            w = (torch.randn(4, 256, 2, 2, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+            w = (torch.randn(4, Co, 2, 2, Cin, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
             ref = ops.conv_fwd_ex(kind, x, w, torch.bfloat16, bias)
             out, st = ops.conv_fwd_bnstats(kind, x, w, bias)
-        tag = f"conv+bnstats kind={kind} N={N} H={H} Cin={Cin}"
+        tag = f"conv+bnstats kind={kind} N={N} H={H} Cin={Cin} Cout={Co}"
         rows.append((tag + " output identical", float((out.float() != ref.float()).sum()), EXACT))
-        rm0, rv0 = torch.zeros(256, device=DEV), torch.ones(256, device=DEV)
+        rm0, rv0 = torch.zeros(Co, device=DEV), torch.ones(Co, device=DEV)
         rm1, rv1 = rm0.clone(), rv0.clone()
-        mean, rstd = ops.bn_finalize(st, 256, rm0, rv0, 0.1, 1e-5)
+        mean, rstd = ops.bn_finalize(st, Co, rm0, rv0, 0.1, 1e-5)
         mref, rref = ops.bn_stats(ref, rm1, rv1, 0.1, 1e-5)
-        rows.append((tag + " count", float(abs(st.count - ref.numel() // 256)), EXACT))
+        rows.append((tag + " count", float(abs(st.count - ref.numel() // Co)), EXACT))
         rows.append((tag + " mean", rel(mean, mref), F32_TOL))
         rows.append((tag + " rstd", rel(rstd, rref), F32_TOL))
         rows.append((tag + " running_mean", rel(rm0, rm1), F32_TOL))

@@ -15,7 +15,7 @@ def _run(fn):
 @pytest.mark.parametrize("name", ["check_codebook_and_mask", "check_gate", "check_pool", "check_conv_fwd",
                                   "check_conv_epilogues", "check_conv_wgrad", "check_thin", "check_conv_variants", "check_sn", "check_conv_ex", "check_conv_tf32",
                                   "check_optim", "check_flow", "check_conv_bnstats",
-                                  "check_batched_paths"])
+                                  "check_batched_paths", "check_conv_cluster"])
 def test_kernel_family(name):
     assert torch.cuda.is_available()
     import gpu_checks

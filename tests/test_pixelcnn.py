@@ -84,6 +84,7 @@ def test_pixelcnn_model_vs_oracle_and_reference_fixture():
     cfg["pixelcnn"]["num_layer"], cfg["pixelcnn"]["hidden_size"] = case["num_layer"], case["hidden_size"]
     torch.manual_seed(0)
     model = models.mcpixelcnn()
+    build_sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     sd = P.make_trainable(model.state_dict())
     model = model.to("cuda")
     model.train(True)
@@ -95,11 +96,26 @@ def test_pixelcnn_model_vs_oracle_and_reference_fixture():
     print("pixelcnn loss", float(out["loss"].detach()), float(ref["loss"].detach()), case["loss_fwd"])
     assert abs(float(out["loss"].detach()) - case["loss_fwd"]) < 2e-2
     assert rel_err(out["logits"].detach().float().cpu()[:4], arr["logits"]) < 3e-2
-    errs = sorted(((rel_err(p.grad.float().cpu(), sd[k].grad), k) for k, p in model.named_parameters()
-                   if sd[k].grad is not None and float(sd[k].grad.norm()) > 1e-6), reverse=True)
-    print("pixelcnn worst gradient errors:", errs[:4], "median", errs[len(errs) // 2])
+    # Gradients.  Batch 16 on 8x8 maps: every BatchNorm sees 1024 values per channel and its backward cancels most of the
+    # incoming gradient, so bf16 STORAGE alone moves the fp32 oracle's gradients by several per cent (as for the VAE at
+    # batch 16).  The floor is derived, not guessed: the oracle itself is re-run with a bf16 round trip at every tensor
+    # the kernels store (oracle/bf16_storage_sim.py); the GPU must not be worse than that simulation by more than a
+    # small factor, and must stay under the family-wide 1.2e-1 worst-case bound.
+    from oracle import bf16_storage_sim as S
+    sd_sim = P.make_trainable({k: v.cpu() for k, v in build_sd0.items()})
+    with S._Patched():
+        sim = P.forward(arr["img"], arr["label"], sd_sim, 10)
+        sim["loss"].backward()
+    keys = [k for k, p in model.named_parameters() if sd[k].grad is not None and float(sd[k].grad.norm()) > 1e-6]
+    got = {k: p.grad.float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    assert all(k in got for k in keys)            # every parameter the reference gives a gradient gets one here
+    errs = sorted(((rel_err(got[k], sd[k].grad), k) for k in keys), reverse=True)
+    floor = sorted(((rel_err(sd_sim[k].grad, sd[k].grad), k) for k in keys), reverse=True)
+    print("pixelcnn gradient errors vs fp32 oracle: worst", errs[:3], "median", errs[len(errs) // 2])
+    print("bf16-storage oracle vs fp32 oracle:      worst", floor[:3], "median", floor[len(floor) // 2])
     assert errs[0][0] < 1.2e-1, errs[:4]
-    assert errs[len(errs) // 2][0] < 3e-2
+    assert errs[0][0] < 1.5 * floor[0][0] + 2e-2
+    assert errs[len(errs) // 2][0] < 1.5 * floor[len(floor) // 2][0] + 1e-2
     # mask 'A' is applied in place on the stored weights, as make_causal does
     assert float(model.layers[0].vert_stack.weight[:, :, -1].abs().max()) == 0.0
     assert float(model.layers[0].horiz_stack.weight[:, :, :, -1].abs().max()) == 0.0

@@ -12,10 +12,8 @@ from mcgm_b200 import ops  # noqa: E402
 from mcgm_b200._lib import GATE_BN, GATE_MASK, GATE_RELU, GATE_UP2  # noqa: E402
 
 from mcgm_b200 import _lib  # noqa: E402
-for kv in filter(None, os.environ.get("MCGM_DEBUG_SET", "").split(",")):
-    k, v = kv.split("=")
-    _lib.call("mcgm_debug_set", int(k), int(v))
-    print("debug_set", k, v)
+_lib.load()                  # applies MCGM_DEBUG_SET
+print("debug_set", os.environ.get("MCGM_DEBUG_SET", ""))
 dev = "cuda"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
