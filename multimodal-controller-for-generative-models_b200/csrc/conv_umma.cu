@@ -139,7 +139,11 @@ struct DescKnobs {
   uint32_t wg_splits = 0;                    // wgrad: force the split-K factor (0 = automatic)
   // staged forward epilogue: bit 2 = fetch the residual / ReLU-sign tile by TMA load (else through registers)
   uint32_t tma_epi = 7;
-  uint32_t cluster = 2;                      // forward conv: CTAs per cluster sharing one weight slab by TMA multicast (1, 2, 4)
+  // forward conv: CTAs per cluster sharing one weight slab by TMA multicast (1 = off, 2, 4).  Bit-identical results
+  // (tests/gpu_checks.py:check_conv_cluster) but measured 0-2 % SLOWER (2) / 10 % slower (4): the kernel is bound by
+  // shared-memory bandwidth (TMA writes + both MMA operands read from smem = 192 B/clk against 128), not by the L2 feed
+  // that multicast relieves — DESIGN.md §7.  Kept as a tested knob, off by default.
+  uint32_t cluster = 1;
 };
 static DescKnobs g_knobs;
 
@@ -191,13 +195,20 @@ struct ConvFwdParams {
 // carved out of the operand ring: warps write their accumulator rows there (conflict-free thanks to the swizzle) and ONE
 // thread per group stores the tile with cp.async.bulk.tensor — no per-thread global stores, no register transposes.
 static constexpr int kSlabBytes = kTileM * 64 * 2;   // 16 KB
+// Shared memory of the staged forward kernel: operand ring + staging tiles.  224 KB (the whole 227 KB a CTA may own, L1
+// down to its minimum): the staged epilogue no longer lives on L1 (TMA stores / loads instead of row-strided global
+// accesses), so the fourth pipeline stage is worth more than the cache — measured 3-7 % on every 3x3 shape against 192 KB.
+#ifndef MCGM_FWD_RING_BYTES
+#define MCGM_FWD_RING_BYTES 229376
+#endif
 template <int BN, int MT, bool TMAEPI = false>
 struct FwdCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
   static constexpr int kEpiGroups = BN >= 128 ? 2 : 1;
   static constexpr int kStagingBytes = TMAEPI ? kEpiGroups * kSlabBytes : 0;
-  static constexpr int kStages = ((196608 - kStagingBytes) / kStageBytes) > 8 ? 8 : ((196608 - kStagingBytes) / kStageBytes);
+  static constexpr int kRing = TMAEPI ? MCGM_FWD_RING_BYTES : 196608;
+  static constexpr int kStages = ((kRing - kStagingBytes) / kStageBytes) > 8 ? 8 : ((kRing - kStagingBytes) / kStageBytes);
   static constexpr int kAccStages = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int kTmemRaw = kAccStages * MT * BN;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
@@ -207,7 +218,8 @@ struct FwdCfg {
   // loads and stores 10-40 % (measured on the 1x1 / thin / residual convs).
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kMaxBiasBytes;
   static_assert(kStages >= 2, "forward conv needs at least two pipeline stages");
-  static_assert(kSmemBytes + 1024 <= 200704, "forward conv must fit the 196 KB carve-out");
+  static_assert(kSmemBytes <= (TMAEPI ? MCGM_FWD_RING_BYTES : 196608) + 3072, "forward conv: shared-memory budget");
+  static_assert(kSmemBytes <= 232448, "forward conv exceeds the 227 KB a CTA may own");
 };
 
 // 4x4 transpose of 16-byte units across the 4 lanes of a quad.  Before: lane l holds units 0..3 (64
@@ -861,6 +873,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     };
     if constexpr (kTmaEpi) {
+#ifdef MCGM_KEEP_OLD_EPI          // A/B build only: also compile the per-thread-store epilogue into the staged instantiations
+      if (!p.tma_epi) {
+        if (p.quad) tile_loop(std::true_type{});
+        else tile_loop(std::false_type{});
+      } else
+#endif
       if (p.quad) tile_loop_tma(std::true_type{});
       else tile_loop_tma(std::false_type{});
     } else if constexpr (kQuadOk) {

@@ -503,7 +503,7 @@ def check_conv_cluster():
                     stats[cl] = ops.bn_finalize(st, Cout)
                     rows.append((f"cluster{cl} {kind} N={N} {Cin}->{Cout} f{fl:#x}: bnstats output identical", float((o2.float() != outs[cl].float()).sum()), EXACT))
             finally:
-                _lib.call("mcgm_debug_set", 11, 2)
+                _lib.call("mcgm_debug_set", 11, 1)
         tag = f"{kind} N={N} H={H} {Cin}->{Cout} k{R} f{fl:#x}"
         for cl in (2, 4):
             rows.append((f"cluster{cl} == cluster1 {tag}", float((outs[cl].float() != outs[1].float()).sum()), EXACT))
