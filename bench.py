@@ -526,7 +526,8 @@ def run_native(args, C):
             line["roofline"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        from mcgm_b200 import train_gan
+        train_gan.shutdown_process_group(W.graphed)
 
 
 if __name__ == "__main__":

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "reduce.cuh"
+#include "tmap.cuh"
 #include "umma.cuh"
 
 namespace mcgm {
@@ -54,9 +55,9 @@ struct MapKey {
   const void* ptr;
   uint64_t d[4];
   uint32_t b[4];
-  int rank, estride, f32;
+  int rank, estride, f32, swizzle;
   bool operator==(const MapKey& o) const {
-    if (ptr != o.ptr || rank != o.rank || estride != o.estride || f32 != o.f32) return false;
+    if (ptr != o.ptr || rank != o.rank || estride != o.estride || f32 != o.f32 || swizzle != o.swizzle) return false;
     for (int i = 0; i < 4; ++i)
       if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
     return true;
@@ -64,7 +65,7 @@ struct MapKey {
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride + 64 * k.f32) * 0x9e3779b97f4a7c15ull;
+    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride + 64 * k.f32 + 128 * k.swizzle) * 0x9e3779b97f4a7c15ull;
     for (int i = 0; i < 4; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
     return h;
   }
@@ -73,8 +74,8 @@ struct MapKeyHash {
 // bf16 tensor, dims innermost-first, dense strides, 128B swizzle, zero OOB fill.  `estride` is the
 // TMA traversal stride of the two spatial dims of a 4-D NHWC map (1, or 2 for stride-2 gathers): a
 // box of b elements then lands b/estride elements in shared memory.
-static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box,
-                     int estride = 1, int f32 = 0) {
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, int estride, int f32,
+              int swizzle) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{};
@@ -82,6 +83,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
   key.rank = rank;
   key.estride = estride;
   key.f32 = f32;
+  key.swizzle = swizzle;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   {
     std::lock_guard<std::mutex> lock(mu);
@@ -113,7 +115,7 @@ static int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
     if (i < rank - 1) gstride[i] = stride;
   }
   CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride,
-                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu)",
@@ -137,6 +139,7 @@ struct DescKnobs {
   uint32_t mt2 = 1, mt2_256 = 0;             // forward conv: two M tiles per CTA (BN <= 128 / BN = 256)
   uint32_t nt2 = 1;                          // wgrad: two filter taps per CTA (Cin tile 128)
   uint32_t wg_splits = 0;                    // wgrad: force the split-K factor (0 = automatic)
+  uint32_t wg_pair = 1;                      // wgrad, NT = 2: one N = 2*BN MMA per k step for both taps (0: one MMA per tap)
   // staged forward epilogue: bit 2 = fetch the residual / ReLU-sign tile by TMA load (else through registers)
   uint32_t tma_epi = 7;
   // forward conv: CTAs per cluster sharing one weight slab by TMA multicast (1 = off, 2, 4).  Bit-identical results
@@ -185,7 +188,7 @@ struct ConvFwdParams {
   int quad;                                  // 4 consecutive tile pixels never straddle a tile row (TW % 4 == 0)
   int tma_epi;                               // epilogue stages bf16 tiles in shared memory and writes them with TMA stores
   int side_tma;                              // ... and fetches the residual / ReLU-sign tile with a TMA load into the same buffer
-  float* stats;                              // tma_epi only: [4 * gridDim][2][Cout] per-warp sum / sum of squares of the stored values
+  float* stats;                              // tma_epi only: [gridDim][2][Cout] per-CTA sum / sum of squares of the stored values
   void* out;
 };
 
@@ -765,14 +768,31 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
       if (leader) tma_store_wait_all();
       if (stats_on) {
+        // one statistics slot per CTA: the four warp rows are summed through the (now idle) staging buffers in a fixed
+        // order — the finalize kernel reads 4x fewer partials
+        float* sm = reinterpret_cast<float*>(smem_raw + (staging_base - smem_base));       // [4 quads][2][BN] floats <= 8 KB
+        named_bar_sync(3, 256);                                // every group's last store has left the staging buffers
         const int col = cw0 + 2 * lane;
-        if (col < cw0 + 32 * CPS) {
-          float* sp = p.stats + (size_t)(blockIdx.x * 4 + quad) * 2 * p.Cout;
+        const bool mine = col < cw0 + 32 * CPS;
+        if (mine) {
 #pragma unroll
           for (int sl = 0; sl < SPG; ++sl) {
             const int c = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0) + col;      // n_tiles == 1 (host)
-            sp[c] = st_sum[sl][0]; sp[c + 1] = st_sum[sl][1];
-            sp[p.Cout + c] = st_sq[sl][0]; sp[p.Cout + c + 1] = st_sq[sl][1];
+            sm[(quad * 2 + 0) * BN + c] = st_sum[sl][0]; sm[(quad * 2 + 0) * BN + c + 1] = st_sum[sl][1];
+            sm[(quad * 2 + 1) * BN + c] = st_sq[sl][0];  sm[(quad * 2 + 1) * BN + c + 1] = st_sq[sl][1];
+          }
+        }
+        named_bar_sync(3, 256);
+        if (mine && quad == 0) {
+          float* sp = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+#pragma unroll
+          for (int sl = 0; sl < SPG; ++sl) {
+            const int c = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0) + col;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              sp[c + e] = (sm[0 * BN + c + e] + sm[2 * BN + c + e]) + (sm[4 * BN + c + e] + sm[6 * BN + c + e]);
+              sp[p.Cout + c + e] = (sm[1 * BN + c + e] + sm[3 * BN + c + e]) + (sm[5 * BN + c + e] + sm[7 * BN + c + e]);
+            }
           }
         }
       }
@@ -916,6 +936,7 @@ struct WgradParams {
   int cout_tiles, cin_tiles, taps, tap_groups;
   uint64_t desc_templ;
   uint32_t idesc, idesc_bias;
+  uint32_t idesc_pair;                  // NT = 2: one N = 2*BN instruction covers both taps (their X tiles are adjacent in smem)
   float* partial;                       // [splits][Cout*R*S*Cin]
   float* bias_partial;                  // [splits][bias_slots][Cout] or nullptr
   int bias_taps[4], bias_slots;         // taps whose dY pixels tile dY exactly once (stride-2 dY: 4 parity classes)
@@ -1047,6 +1068,16 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint64_t adesc = smem_desc(p.desc_templ, sa);
         const uint32_t acc_on = kb > kb0;
+        if (NT == 2 && ntaps == 2 && p.idesc_pair != 0u) {
+          // Both taps in ONE instruction: their X tiles sit back to back in the stage, i.e. 2*BN/64 MN-blocks at the
+          // uniform 8 KB stride the descriptor's LBO describes = a valid N = 2*BN operand.  dY (the A operand) is then
+          // read from shared memory once per k step instead of once per tap: the kernel is bound by shared-memory
+          // bandwidth (TMA writes + both MMA operands), and this removes a quarter of the operand reads.
+          const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc_pair, acc_on | (uint32_t)(k != 0));
+        } else
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           if (q < ntaps) {
@@ -1321,6 +1352,8 @@ static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout
 
 using namespace mcgm;
 
+namespace mcgm { extern int g_thin_umma_wgrad, g_thin_umma_fwd; }
+
 extern "C" int mcgm_debug_set(int key, uint64_t value) {
   switch (key) {
     case 0: g_knobs.k_lbo = (uint32_t)value; break;
@@ -1335,6 +1368,9 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 9: g_knobs.wg_splits = (uint32_t)value; break;
     case 10: g_knobs.tma_epi = (uint32_t)value; break;
     case 11: g_knobs.cluster = (uint32_t)value; break;
+    case 14: g_knobs.wg_pair = (uint32_t)value; break;
+    case 12: g_thin_umma_wgrad = (int)value; break;       // thin (RGB-side) convs: tcgen05 / TMA kernels (1) or mma.sync kernels (0)
+    case 13: g_thin_umma_fwd = (int)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
   }
   return 0;
@@ -1490,9 +1526,9 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
     if (!(p.tma_epi && p.n_tiles == 1))
       return fail(MCGM_E_UNSUPPORTED, "conv_fwd_bnstats: needs a bf16 output with Cout in {64, 128, 256} (one channel tile, staged epilogue)");
     MCGM_CHECK_ARG(stat_slots_host, "conv_fwd_bnstats: stat_slots_host is NULL");
-    // four slots (one per epilogue warp row) for every CTA the device can hold; CTAs that are not launched leave zeros
-    *stat_slots_host = 4 * sms;
-    MCGM_CUDA(cudaMemsetAsync(stats, 0, (size_t)4 * sms * 2 * Cout * sizeof(float), st));
+    // one slot for every CTA the device can hold; CTAs that are not launched leave zeros
+    *stat_slots_host = sms;
+    MCGM_CUDA(cudaMemsetAsync(stats, 0, (size_t)sms * 2 * Cout * sizeof(float), st));
     p.stats = stats;
   }
   switch (BN) {
@@ -1576,6 +1612,7 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
   p.desc_templ = make_smem_desc_hi_lbo(tf32 ? 4096 : g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1, tf32);
+  p.idesc_pair = (g_knobs.wg_pair && 2 * pl.BN <= 256) ? make_idesc_bf16(kTileM, 2 * pl.BN, 1, 1, tf32) : 0u;
   p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1, tf32);
   p.bias_slots = 1; p.bias_taps[0] = 0;
   if (kind == MCGM_CONV_PHASE2) {          // dY is read with stride 2: the four offsets in {0,1}^2 cover it once

@@ -359,6 +359,14 @@ static int thin_geom(ThinGeom* g, int N, int H, int W, int Ct, int R, int S, int
   return 0;
 }
 
+// thin_umma.cu: the same forward on tcgen05 + TMA (0 launched, 1 not applicable, < 0 error)
+int thin_conv_fwd_umma(const float* img, const void* w_bf16, const float* bias, const int32_t* labels, const uint32_t* bits,
+                       int relu, void* out_bf16, int N, int H, int W, int Ct, int R, int S, int Cout, cudaStream_t st);
+
+// ... and the weight gradient (-> number of CTA partials written, 0 = not applicable, < 0 error)
+int thin_conv_wgrad_umma(const float* img, const void* dy_bf16, float* partial, int max_partials, int N, int H, int W, int Ct,
+                         int R, int S, int Cout, cudaStream_t st);
+
 static constexpr int kThinFwdSmem = (kThinTileP * kThinKP + 128 * kThinKP + 8 * 16 * 136) * 2;
 static constexpr int kThinWgSmem = (kThinWP * kThinKP + kWgStages * kThinWP * 136) * 2;
 static constexpr int kThinWgBlocks = 444;            // 3 per SM (registers): latency is hidden by occupancy + the register prefetch
@@ -367,12 +375,20 @@ static constexpr int kThinWgBlocks = 444;            // 3 per SM (registers): la
 
 using namespace mcgm;
 
+namespace mcgm { int g_thin_umma_wgrad = 1, g_thin_umma_fwd = 1; }      // developer A/B knobs (mcgm_debug_set 12 / 13)
+
 extern "C" int mcgm_thin_conv_fwd(const float* img, const void* w_bf16, int w_row_stride, const float* bias,
                                   const int32_t* labels, const uint32_t* bits, int M, int relu, void* out_bf16, int N,
                                   int H, int W, int Ct, int R, int S, int Cout, void* stream) {
   MCGM_CHECK_ARG(img && w_bf16 && out_bf16 && N > 0 && H > 0 && W > 0, "thin_conv_fwd: bad arguments");
   MCGM_CHECK_ARG(w_row_stride >= kThinK && w_row_stride % 8 == 0, "thin_conv_fwd: weight rows must hold >= 32 bf16 columns, 16-byte aligned");
   MCGM_CHECK_ARG((labels == nullptr) == (bits == nullptr) && (!bits || (M > 0 && Cout % 32 == 0)), "thin_conv_fwd: MASK needs labels, bits and Cout %% 32 == 0");
+  // weights padded to 64 columns (128-byte rows = the UMMA operand layout): the tcgen05 / TMA kernel of thin_umma.cu;
+  // 32-column weights or shapes it does not cover: the mma.sync kernel below
+  if (w_row_stride == 64 && g_thin_umma_fwd) {
+    const int r = thin_conv_fwd_umma(img, w_bf16, bias, labels, bits, relu, out_bf16, N, H, W, Ct, R, S, Cout, (cudaStream_t)stream);
+    if (r <= 0) return r;
+  }
   ThinGeom g;
   if (int e = thin_geom(&g, N, H, W, Ct, R, S, Cout, kThinTileP)) return e;
   static bool configured = false;
@@ -409,11 +425,16 @@ extern "C" int mcgm_thin_conv_wgrad(const float* img, const void* dy_bf16, float
     configured = true;
   }
   const long P = (long)N * H * W, tiles = (P + kThinWP - 1) / kThinWP;
-  const int grid = (int)(tiles < kThinWgBlocks ? tiles : kThinWgBlocks);
   cudaStream_t st = (cudaStream_t)stream;
-  thin_conv_wgrad_kernel<<<grid, kThinThreads, kThinWgSmem, st>>>(img, (const __nv_bfloat16*)dy_bf16, (float*)workspace, g, P, tiles,
-                                                                 R * S * Ct);
-  MCGM_LAUNCH_CHECK();
+  // tcgen05 / TMA kernel (thin_umma.cu) where it applies; its CTA partials use the same [blocks][Cout][32] workspace
+  int grid = g_thin_umma_wgrad ? thin_conv_wgrad_umma(img, dy_bf16, (float*)workspace, kThinWgBlocks, N, H, W, Ct, R, S, Cout, st) : 0;
+  if (grid < 0) return grid;
+  if (grid == 0) {
+    grid = (int)(tiles < kThinWgBlocks ? tiles : kThinWgBlocks);
+    thin_conv_wgrad_kernel<<<grid, kThinThreads, kThinWgSmem, st>>>(img, (const __nv_bfloat16*)dy_bf16, (float*)workspace, g, P, tiles,
+                                                                   R * S * Ct);
+    MCGM_LAUNCH_CHECK();
+  }
   const size_t nout = (size_t)Cout * kThinK;
   thin_partial_reduce_kernel<<<(int)((nout + 31) / 32), 32 * kThinRedLanes, 0, st>>>((const float*)workspace, grid, nout, dwm);
   MCGM_LAUNCH_CHECK();

@@ -448,7 +448,7 @@ def sn_pack_all(states):
     for m in mods:
         K, C, R, S = m.weight_orig.shape
         if C <= 4:
-            rs = _TK if R * S * C <= _TK - 1 else _KU
+            rs = _KU                    # 64 columns = 128-byte rows: the UMMA operand layout of the thin forward kernel
             sizes.append(K * rs)
             metas.append((1, rs))
         else:
@@ -1099,12 +1099,12 @@ class WideFromThinFn(torch.autograd.Function):
         if (not f32 and stride == 1 and pad is None and R == S and R in (1, 3) and R * S * C <= _TK - 1 and K % 16 == 0
                 and 128 % thin.shape[2] == 0 and (thin.shape[1] * thin.shape[2]) % 128 == 0):
             # direct path (csrc/thin_mma.cu): the patch matrix never leaves shared memory
-            wm = wm_packed if (wm_packed is not None and wm_packed.shape[-1] == _TK) else \
-                pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _TK)
+            wm = wm_packed if (wm_packed is not None and wm_packed.shape[-1] == _KU) else \
+                pack_weight_padded(w.detach(), sn[0:1] if sn is not None else None, _KU)
             N, H, Wd, _ = thin.shape
             out = torch.empty(N, H, Wd, K, dtype=torch.bfloat16, device=thin.device)
             ev = _prof_begin()
-            _lib.call("mcgm_thin_conv_fwd", thin.data_ptr(), wm.data_ptr(), _TK, _ptr(bias), _ptr(labels),
+            _lib.call("mcgm_thin_conv_fwd", thin.data_ptr(), wm.data_ptr(), _KU, _ptr(bias), _ptr(labels),
                       _ptr(packed.bits if packed else None), packed.M if packed else 0, int(gate is not None),
                       out.data_ptr(), N, H, Wd, C, R, S, K, _stream())
             _prof_end(ev, "thin", thin.numel() * 4 + out.numel() * 2, f"thin_conv {N}x{H}x{Wd} {C}->{K} k{R} gate{int(gate is not None)}")

@@ -78,6 +78,7 @@ class GradAllReduce:
         if count:
             self.buckets.append([0, stop, count])
         self.pending = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
         self.handles = []
         self.enabled = True
         if self.world > 1 and overlap:
@@ -90,15 +91,23 @@ class GradAllReduce:
         for p, g in zip(self.params, self.views):
             p.grad = g
         self.pending = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
         self.handles = []
 
     def _hook(self, p):
         if not self.enabled:
             return
+        from . import ops
         b = self.bucket_of[id(p)]
         self.pending[b] += 1
-        if self.pending[b] == self.buckets[b][2]:
+        # A bucket goes out during backward only when every gradient in it has really been written.  With deferred
+        # end-of-backward work (ops.SN_DEFER: the D update's spectral-norm backwards and grouped weight gradients are
+        # added to .grad by ONE callback after the pass) the hook count says nothing — autograd fires the hook for those
+        # parameters too (with an undefined gradient) — so such a pass is reduced in finish().  Found by the 2-rank
+        # parity test: the eager overlapped form all-reduced D's bucket before the deferred gradients existed.
+        if self.pending[b] == self.buckets[b][2] and not ops.SN_DEFER:
             s, e, _ = self.buckets[b]
+            self.launched[b] = True
             self.handles.append(dist.all_reduce(self.flat[s:e], group=self.group, async_op=True))
 
     def finish(self):
@@ -109,9 +118,10 @@ class GradAllReduce:
             if self.average:
                 self.flat.div_(self.world)
             return
-        # parameters that received no gradient this step (unused) still need their bucket reduced
+        # buckets that did not go out during backward (unused parameters, deferred gradients)
         for b, (s, e, n) in enumerate(self.buckets):
-            if self.pending[b] != n:
+            if not self.launched[b]:
+                self.launched[b] = True
                 self.handles.append(dist.all_reduce(self.flat[s:e], group=self.group, async_op=True))
         for h in self.handles:
             h.wait()
@@ -350,6 +360,12 @@ class GraphedDDPTrainStep:
         self.out = {'loss_D': self.d_loss, 'loss_G': self.g_loss, 'loss': None}
         guard.restore()
 
+    def close(self):
+        """Release the captured graphs (call before ``dist.destroy_process_group()``)."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.graph_d = self.graph_g = None
+
     def __call__(self, input):
         self.img.copy_(input['img'], non_blocking=True)
         self.label.copy_(input['label'], non_blocking=True)
@@ -427,6 +443,13 @@ class GraphedDDPIngraphTrainStep:
         self.native_launches = _lib.launch_count - c0
         guard.restore()
 
+    def close(self):
+        """Release the captured graph.  It holds NCCL kernels: destroy it BEFORE ``dist.destroy_process_group()`` —
+        tearing the communicator down under a live graph that references it blocks (measured: both ranks hang in
+        ``destroy_process_group`` until killed)."""
+        torch.cuda.synchronize()
+        self.graph = None
+
     def __call__(self, input):
         self.img.copy_(input['img'], non_blocking=True)
         self.label.copy_(input['label'], non_blocking=True)
@@ -470,3 +493,31 @@ def make_ddp_step(model, optimizer, reducers, batch_size, mode='auto', inject_no
     print(f'[train_gan] in-graph NCCL capture unavailable ({type(err).__name__ if err else "peer rank"}: {err}); '
           f'using segmented graphs', file=sys.stderr, flush=True)
     return GraphedDDPTrainStep(model, optimizer, reducers, batch_size, inject_noise=inject_noise)
+
+
+def shutdown_process_group(*steps, grace_s=20.0):
+    """Orderly end of a data-parallel run: release the captured graphs (they reference the communicator), synchronise,
+    then destroy the process group.  A watchdog ends the process if the teardown itself blocks (a NCCL teardown that
+    waits forever would otherwise keep the launcher — and its GPUs — busy after all results have been written)."""
+    import gc
+    import os
+    import sys
+    import threading
+    for s in steps:
+        if s is not None and hasattr(s, 'close'):
+            s.close()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not dist.is_initialized():
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Timer(grace_s, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        t.cancel()

@@ -31,6 +31,7 @@ def main():
     graph = mode != "eager"
     opt = train_gan.make_optimizers(model, capturable=graph)
     red = {k: train_gan.GradAllReduce(getattr(model, k), overlap=not graph) for k in ("generator", "discriminator")}
+    step = None
     if graph:
         step = train_gan.make_ddp_step(model, opt, red, case["batch"], mode=mode, inject_noise=True)
         out = step(batch)
@@ -41,9 +42,27 @@ def main():
     torch.cuda.synchronize()
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     res = {"rank": rank, "loss_D": float(out["loss_D"]), "loss_G": float(out["loss_G"]), "form": form, "sd": sd}
+    if not graph:
+        # diagnostic: one more D backward; after finish() the flat gradient buffer must be bit-identical on all ranks
+        red["discriminator"].zero_grad(); red["generator"].zero_grad()
+        red["generator"].enabled = False
+        train_gan.d_forward_backward(model, batch["img"], batch["label"], batch["z"][0])
+        local = red["discriminator"].flat.clone()
+        red["discriminator"].finish()
+        red["generator"].enabled = True
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, red["discriminator"].flat)
+        diff = (both[0] - both[1]).abs()
+        exp = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(exp, local)
+        want = (exp[0] + exp[1]) / world
+        res["diag"] = {"ranks_max_diff": float(diff.max()), "n_diff": int((diff > 0).sum()), "numel": diff.numel(),
+                       "first_diff": int((diff > 0).nonzero()[0]) if bool((diff > 0).any()) else -1,
+                       "vs_expected_max": float((both[0] - want).abs().max()),
+                       "offsets": list(opt["discriminator"].flat.offsets)[:6], "buckets": red["discriminator"].buckets,
+                       "pending": list(red["discriminator"].pending)}
     torch.save(res, f"{out_path}.{rank}")
-    dist.barrier()
-    dist.destroy_process_group()
+    train_gan.shutdown_process_group(step)
 
 
 if __name__ == "__main__":

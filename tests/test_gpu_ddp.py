@@ -99,10 +99,10 @@ def test_two_rank_nccl_iteration_vs_oracle_shards(golden, mode):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                             "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
                             os.path.join(ROOT, "tests", "ddp_worker.py"), out, mode, name],
-                           capture_output=True, text=True, timeout=900, cwd=ROOT)
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-3000:]
         res = [torch.load(f"{out}.{k}") for k in range(world)]
-    print("launch form:", res[0]["form"])
+    print("launch form:", res[0]["form"], res[0].get("diag"))
     # every rank ends with identical parameters (BN running statistics are per-rank by design)
     for k, v in res[0]["sd"].items():
         if v.is_floating_point() and "running_" not in k:
@@ -129,9 +129,10 @@ def test_two_rank_nccl_iteration_vs_oracle_shards(golden, mode):
         assert abs(res[r_]["loss_D"] - lsim[r_][0]) < 3e-2 and abs(res[r_]["loss_G"] - lsim[r_][1]) < 3e-2
     # parameter updates against the fp32 oracle: update norms (Adam's first steps are sign-like) as in the N=1 test
     bad = []
+    from test_gpu_parity_r2 import _feeds_batchnorm
     for k, v0 in sd0.items():
-        if not v0.is_floating_point() or not sds32[0][k].requires_grad:
-            continue
+        if not v0.is_floating_point() or not sds32[0][k].requires_grad or _feeds_batchnorm(k):
+            continue           # (generator biases in front of a BatchNorm: analytically zero gradient, pure noise)
         ref = float((sds32[0][k].detach() - v0).norm())
         got = float((res[0]["sd"][k] - v0).norm())
         if ref > 1e-4 and abs(got - ref) > 0.15 * ref + 2.5e-4:

@@ -51,9 +51,23 @@ def launch_table(path, title):
     return "\n".join(out)
 
 
+def raw_rows(path):
+    """rows of the ncu raw page: from the report itself, or from the `<name>.raw.csv` exported on the GPU box
+    (gpurun brings back at most 64 MiB, the reports with imported source are larger)."""
+    if os.path.exists(path):
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        with open(path.replace(".ncu-rep", ".raw.csv")) as f:
+            raw = f.read()
+    return list(csv.reader(io.StringIO(raw)))
+
+
+def have(path):
+    return os.path.exists(path) or os.path.exists(path.replace(".ncu-rep", ".raw.csv"))
+
+
 def full_table(path, title):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rd = list(csv.reader(io.StringIO(raw)))
+    rd = raw_rows(path)
     if len(rd) < 3:
         return f"### {title}\n\n(no data)\n"
     hdr, units = rd[0], rd[1]
@@ -68,22 +82,26 @@ def full_table(path, title):
 
 os.makedirs(OUT, exist_ok=True)
 parts = [f"# ncu summaries — round {tag}", "",
-         "Workload: MCGAN CIFAR10-shaped, batch 512, bf16 (`tools/profile_step.py`), one B200.  Commands: `tools/ncu_pass.sh`.",
+         "Workload: MCGAN CIFAR10-shaped, batch 512, bf16 (`tools/profile_step.py`), one B200.  Commands: "
+         + ("`tools/ncu_pass.sh`." if tag == "r01" else "`tools/ncu_pass_r02.sh` (the reports are exported to CSV on the GPU box: `gpurun_out/prof_*.raw.csv`)."),
          ""]
 for name, title in (("launches_d.csv", "Launch list — one D update (D(real), G(z), D(G.detach()), backward, Adam)"),
                     ("launches_g.csv", "Launch list — one G update (G(z), D(G), backward, Adam)")):
     p = os.path.join(SRC, name)
     if os.path.exists(p):
         parts.append(launch_table(p, title))
-for name, title in (("prof_conv_fwd.ncu-rep", "`--set full`: conv_fwd_kernel, generator 256->256 3x3 @32x32 launches"),
-                    ("prof_conv_fwd_d.ncu-rep", "`--set full`: conv_fwd_kernel, discriminator 128->128 launches"),
+for name, title in (("prof_conv_fwd.ncu-rep", "`--set full`: conv_fwd_kernel<256, 1> (generator, 256-wide) launches"),
+                    ("prof_conv_fwd_big.ncu-rep", "`--set full`: conv_fwd_kernel<256, 1>, the 32x32 / 16x16 launches of a G update"),
+                    ("prof_conv_fwd_d.ncu-rep", "`--set full`: conv_fwd_kernel<128, 2> (discriminator, 128-wide) launches"),
                     ("prof_wgrad.ncu-rep", "`--set full`: conv_wgrad_kernel, generator launches"),
+                    ("prof_wgrad_d.ncu-rep", "`--set full`: conv_wgrad_kernel, discriminator launches"),
+                    ("prof_gate.ncu-rep", "`--set full`: gate_fwd_kernel / gate_bwd_reduce_kernel / gate_bwd_apply_kernel, G update"),
                     ("prof_gate_fwd.ncu-rep", "`--set full`: bn_partial_kernel / gate_fwd_kernel, generator launches"),
                     ("prof_gate_bwd.ncu-rep", "`--set full`: gate_bwd_reduce_kernel / gate_bwd_apply_kernel"),
-                    ("prof_thin.ncu-rep", "`--set full`: thin_conv_fwd_kernel (Conv2d(3,128,3,1,1) + ReLU + MC, no im2col buffer; microbench launches)"),
-                    ("prof_thin_wg.ncu-rep", "`--set full`: thin_conv_wgrad_kernel + its partial reduce (microbench launches)")):
+                    ("prof_thin.ncu-rep", "`--set full`: thin (RGB-side) conv kernels of a D update"),
+                    ("prof_thin_wg.ncu-rep", "`--set full`: thin_conv_wgrad kernels")):
     p = os.path.join(SRC, name)
-    if os.path.exists(p):
+    if have(p):
         parts.append(full_table(p, title))
 
 # per-launch DRAM traffic of the dominant shapes (bench.py attaches it to its roofline objects):
@@ -96,13 +114,30 @@ TRAFFIC = {"conv 512x32x32 256->256 k3 f0x5 bf16": ("prof_conv_fwd.ncu-rep", 1),
            "bn_stats P524288 C256": ("prof_gate_fwd.ncu-rep", 2),
            "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", 0)}
 import json
+if tag != "r01":
+    # round 2+: the launch of a shape is found by its duration window [lo, hi] us inside the report (the capture
+    # order depends on the step), not by a fixed index
+    TRAFFIC = {"conv+bnstats kind0 512x32x32 256->256 f0x5": ("prof_conv_fwd_big.ncu-rep", (380, 480)),
+               "conv+bnstats kind2 512x16x16 256->256 f0x1": ("prof_conv_fwd_big.ncu-rep", (190, 260)),
+               "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", (130, 175)),
+               "thin_conv 512x32x32 3->128 k3 gate1": ("prof_thin.ncu-rep", (44, 60)),
+               "gate_fwd 512x32x32x256 f0xb raw0": ("prof_gate.ncu-rep", (90, 110)),
+               "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", (480, 600)),
+               "wgrad 512x32x32 128->128 k3": ("prof_wgrad_d.ncu-rep", (150, 185))}
 traffic = {}
 for desc, (rep, idx) in TRAFFIC.items():
     pth = os.path.join(SRC, rep)
-    if not os.path.exists(pth):
+    if not have(pth):
         continue
-    raw = subprocess.run(["ncu", "-i", pth, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rd = list(csv.reader(io.StringIO(raw)))
+    rd = raw_rows(pth)
+    if isinstance(idx, tuple):
+        hdr, units = rd[0], rd[1]
+        di = hdr.index("gpu__time_duration.sum")
+        scale = {"us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "ns": 1e-3, "nsecond": 1e-3}.get(units[di].lower(), 1.0)
+        cand = [k for k, r in enumerate(rd[2:]) if idx[0] <= float(r[di].replace(",", "")) * scale <= idx[1]]
+        if not cand:
+            continue
+        idx = cand[0]
     if len(rd) < 3 + idx:
         continue
     hdr, units, row = rd[0], rd[1], rd[2 + idx]
