@@ -75,6 +75,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
   const uint32_t w_full = bar + 8u * 12;
   const uint32_t tmem_slot = bar + 8u * 13;
   float* sbias = reinterpret_cast<float*>(smem_raw + (bar - base) + 128);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(sbias + kTuMaxCout);       // per tile: AND-mask of every bf16 channel PAIR
   const float* swin = reinterpret_cast<const float*>(smem_raw + (w_base - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,16 +175,26 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
     }
   } else {
     // ===== epilogue: warps 6..9 own TMEM lane quadrants 2, 3, 0, 1 =====
+    // The epilogue is what this kernel's time is made of (ncu source view: its instructions, not a stall, carry the
+    // samples), so it is kept to ~3 instructions per output value: bias add, branch-free ReLU (max with 0 or -inf),
+    // pack, and ONE AND per channel pair for the MC mask — a 128-pixel tile lies inside one image, so the 0xFFFF /
+    // 0xFFFF0000 masks of all channel pairs are tile-uniform: built once per tile in shared memory, read by broadcast.
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
+    const int et = (warp - 6) * 32 + lane;                  // thread index inside the epilogue group
     const int sw = m & 7;
     const bool leader = (warp == 6 && lane == 0);
     const int slabs = p.Cout / 64;
+    const float lo = p.relu ? 0.0f : -INFINITY;
+    const bool masked = p.bits != nullptr;
     int it = 0, sidx = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
       const int b = it & 1, ph = (it >> 1) & 1;
-      const int n = t / p.tiles_per_img;
-      const int lab = p.bits ? __ldg(p.labels + n) : 0;
+      if (masked && et < p.Cout / 2) {                        // (the previous tile's readers are past their last barrier)
+        const int lab = __ldg(p.labels + t / p.tiles_per_img);
+        const uint32_t w = __ldg(p.bits + (size_t)lab * p.words + (et >> 4)) >> ((2 * et) & 31);
+        smask[et] = ((w & 1u) ? 0x0000ffffu : 0u) | ((w & 2u) ? 0xffff0000u : 0u);
+      }
       mbar_wait(t_full(b), ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + b * p.Cout;
@@ -191,14 +202,9 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
         uint32_t acc[2][32];
         tmem_ld32(t_row + s * 64, acc[0]);
         tmem_ld32(t_row + s * 64 + 32, acc[1]);
-        uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
-        if (p.bits) {
-          mw[0] = __ldg(p.bits + (size_t)lab * p.words + 2 * s);
-          mw[1] = __ldg(p.bits + (size_t)lab * p.words + 2 * s + 1);
-        }
         const uint32_t buf = s_base + (sidx & 1) * kTuSlabBytes;
         if (leader) tma_store_wait_read_1();               // the store that used this staging buffer (two slabs ago) is done
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 128);                              // ... and this tile's mask table is complete
         tmem_ld_wait();
         if (s == slabs - 1) {
           tc_fence_before();
@@ -206,20 +212,19 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          float bs[32];                                     // warp-uniform addresses: 8 broadcast 16-byte reads
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbias + s * 64 + 32 * k + i);
-            bs[i] = b4.x; bs[i + 1] = b4.y; bs[i + 2] = b4.z; bs[i + 3] = b4.w;
-          }
           uint32_t o[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x0 = __uint_as_float(acc[k][2 * i]) + bs[2 * i], x1 = __uint_as_float(acc[k][2 * i + 1]) + bs[2 * i + 1];
-            if (p.relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-            x0 = ((mw[k] >> (2 * i)) & 1u) ? x0 : 0.0f;
-            x1 = ((mw[k] >> (2 * i + 1)) & 1u) ? x1 : 0.0f;
-            o[i] = tu_pack(x0, x1);
+          for (int i = 0; i < 16; i += 2) {                  // 4 columns per step: one 16-byte bias read
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + s * 64 + 32 * k + 2 * i);
+            o[i] = tu_pack(fmaxf(__uint_as_float(acc[k][2 * i]) + b4.x, lo), fmaxf(__uint_as_float(acc[k][2 * i + 1]) + b4.y, lo));
+            o[i + 1] = tu_pack(fmaxf(__uint_as_float(acc[k][2 * i + 2]) + b4.z, lo), fmaxf(__uint_as_float(acc[k][2 * i + 3]) + b4.w, lo));
+          }
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const uint4 m4 = *reinterpret_cast<const uint4*>(smask + s * 32 + 16 * k + i);
+              o[i] &= m4.x; o[i + 1] &= m4.y; o[i + 2] &= m4.z; o[i + 3] &= m4.w;
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -244,7 +249,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
   }
 }
 
-static int tu_fwd_smem_bytes(int Cout) { return 2 * kTuABytes + Cout * 128 + 2 * kTuSlabBytes + 2 * kTuWinBytes + 128 + kTuMaxCout * 4; }
+static int tu_fwd_smem_bytes(int Cout) { return 2 * kTuABytes + Cout * 128 + 2 * kTuSlabBytes + 2 * kTuWinBytes + 128 + kTuMaxCout * 4 + kTuMaxCout * 2; }
 
 // -> 0 launched, 1 not applicable (the caller falls back to the mma.sync kernel), < 0 error
 int thin_conv_fwd_umma(const float* img, const void* w_bf16, const float* bias, const int32_t* labels, const uint32_t* bits,
