@@ -553,7 +553,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       int stage = 0, phase = 0;
       for (int tc = cid; tc < p.total_ctiles; tc += ncl) {
@@ -590,7 +590,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       int stage = 0, phase = 0, it = 0;
       for (int tc = cid; tc < p.total_ctiles; tc += ncl, ++it) {
@@ -645,7 +645,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       constexpr int CPS = BN >= 128 ? 2 : 1;                 // 32-column chunks of one warp inside a slab
       constexpr int SPG = BN >= 128 ? (BN / 2) / 64 : 1;     // slabs per group and M tile
       const int grp = BN >= 128 ? half : 0;
-      const bool leader = (quad == 0) && (BN >= 128 || half == 0) && lane == 0;
+      const bool leader_warp = (quad == 0) && (BN >= 128 || half == 0);   // its elected lane issues the TMA traffic of the group
       const uint32_t buf = staging_base + grp * kSlabBytes;
       const uint32_t sbar = side_bar(grp);
       const uint32_t row_addr = buf + m * 128;
@@ -703,7 +703,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               mwd[k] = __ldg(p.bits + (size_t)((MT == 2 && j) ? lab[MT - 1] : lab[0]) * p.words + (col >> 5));
           }
           // the staging buffer is free once the previous store has been read out of it; then the side slab may land in it
-          if (leader) {
+          if (leader_warp && elect_one()) {
             tma_store_wait_read();
             if (side_tma) {
               mbar_arrive_expect_tx(sbar, kSlabBytes);
@@ -759,14 +759,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
           fence_proxy_async_smem();
           named_bar_sync(1 + grp, GT);
-          if (leader) {
+          if (leader_warp && elect_one()) {
             tma_store_4d(&tmap_out, buf, c_slab, (MT == 2 && j) ? cw[MT - 1] : cw[0], (MT == 2 && j) ? ch[MT - 1] : ch[0],
                          (MT == 2 && j) ? cn[MT - 1] : cn[0]);
             tma_store_commit();
           }
         }
       }
-      if (leader) tma_store_wait_all();
+      if (leader_warp && elect_one()) tma_store_wait_all();
       if (stats_on) {
         // one statistics slot per CTA: the four warp rows are summed through the (now idle) staging buffers in a fixed
         // order — the finalize kernel reads 4x fewer partials
@@ -1026,7 +1026,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0, phase = 0;
       int dr[NT], ds[NT];                        // X-side tap offsets of this CTA's taps (registers: loops are unrolled)
 #pragma unroll
@@ -1060,7 +1060,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0, phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);

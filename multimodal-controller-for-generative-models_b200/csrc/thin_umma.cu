@@ -105,7 +105,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer: weights once, then one halo window per tile =====
       mbar_arrive_expect_tx(w_full, (uint32_t)p.Cout * 128u);
       tma_load_2d(b_base, &tmap_w, w_full, 0, 0);
@@ -119,7 +119,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       mbar_wait(w_full, 0);
       int it = 0;
@@ -183,7 +183,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
     const int m = quad * 32 + lane;
     const int et = (warp - 6) * 32 + lane;                  // thread index inside the epilogue group
     const int sw = m & 7;
-    const bool leader = (warp == 6 && lane == 0);
+    const bool leader_warp = (warp == 6);
     const int slabs = p.Cout / 64;
     const float lo = p.relu ? 0.0f : -INFINITY;
     const bool masked = p.bits != nullptr;
@@ -203,7 +203,7 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
         tmem_ld32(t_row + s * 64, acc[0]);
         tmem_ld32(t_row + s * 64 + 32, acc[1]);
         const uint32_t buf = s_base + (sidx & 1) * kTuSlabBytes;
-        if (leader) tma_store_wait_read_1();               // the store that used this staging buffer (two slabs ago) is done
+        if (leader_warp && elect_one()) tma_store_wait_read_1();               // the store that used this staging buffer (two slabs ago) is done
         named_bar_sync(1, 128);                              // ... and this tile's mask table is complete
         tmem_ld_wait();
         if (s == slabs - 1) {
@@ -232,13 +232,13 @@ thin_conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const __
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
-        if (leader) {
+        if (leader_warp && elect_one()) {
           tma_store_2d(&tmap_out, buf, s * 64, t * kTuTile);
           tma_store_commit();
         }
       }
     }
-    if (leader) tma_store_wait_all();
+    if (leader_warp && elect_one()) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -364,7 +364,7 @@ thin_conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
         const int b = it & 1, ph = (it >> 1) & 1;
@@ -381,7 +381,7 @@ thin_conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_img, const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
         const int b = it & 1, ph = (it >> 1) & 1;

@@ -13,6 +13,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- mbarrier ---------------------------------------------------------------
+// One lane of a converged warp (elect.sync).  Inside `if (elect_one())` the compiler knows a single thread is active, so the
+// operands of tcgen05.mma / cp.async.bulk.tensor move to uniform registers with one R2UR each; behind `lane == 0` it has to
+// emit an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per instruction, which made the MMA issue loop the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
