@@ -209,7 +209,18 @@ struct FwdCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
   static constexpr int kEpiGroups = BN >= 128 ? 2 : 1;
-  static constexpr int kStagingBytes = TMAEPI ? kEpiGroups * kSlabBytes : 0;
+  // Staging tiles per group.  The TMA store of a slab (and the side-slab load) queue behind the operand loads the producer
+  // keeps in flight, a few thousand cycles; with one tile per group every slab waits for the previous slab's store to
+  // drain before it may touch the buffer.  The 128-wide pair tile has only 2 x 64 MMA-cycles per k step to hide a slab
+  // behind, so it alternates between TWO tiles (one ring stage less); the 256-wide tile hides the wait as it is.
+#ifndef MCGM_FWD_STAGING_BUFS_128
+#define MCGM_FWD_STAGING_BUFS_128 1
+#endif
+#ifndef MCGM_FWD_STAGING_BUFS_256
+#define MCGM_FWD_STAGING_BUFS_256 1
+#endif
+  static constexpr int kStagingBufs = (BN == 128 && MT == 2) ? MCGM_FWD_STAGING_BUFS_128 : (BN == 256 ? MCGM_FWD_STAGING_BUFS_256 : 1);
+  static constexpr int kStagingBytes = TMAEPI ? kEpiGroups * kStagingBufs * kSlabBytes : 0;
   static constexpr int kRing = TMAEPI ? MCGM_FWD_RING_BYTES : 196608;
   static constexpr int kStages = ((kRing - kStagingBytes) / kStageBytes) > 8 ? 8 : ((kRing - kStagingBytes) / kStageBytes);
   static constexpr int kAccStages = (2 * MT * BN <= 512) ? 2 : 1;
@@ -646,9 +657,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       constexpr int SPG = BN >= 128 ? (BN / 2) / 64 : 1;     // slabs per group and M tile
       const int grp = BN >= 128 ? half : 0;
       const bool leader_warp = (quad == 0) && (BN >= 128 || half == 0);   // its elected lane issues the TMA traffic of the group
-      const uint32_t buf = staging_base + grp * kSlabBytes;
+      constexpr int NB = Cfg::kStagingBufs;                  // staging tiles per group, used alternately
+      static_assert(NB == 1 || (MT * SPG) % NB == 0, "the staging tile of a slab must be a compile-time choice");
+      const uint32_t buf0 = staging_base + grp * NB * kSlabBytes;
       const uint32_t sbar = side_bar(grp);
-      const uint32_t row_addr = buf + m * 128;
       const int sw = m & 7;
       const int cw0 = BN >= 128 ? 0 : half * 32;             // this warp's first column inside the slab
       const bool side_tma = p.side_tma;
@@ -689,6 +701,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const int c_tile = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0);       // slab's first column inside the CTA tile
           const int c_slab = nt * BN + c_tile;                                  // ... and inside the tensor
           const bool ok = (MT == 2 && j) ? valid[MT - 1] : valid[0];
+          const uint32_t buf = buf0 + (s % NB) * kSlabBytes;
+          const uint32_t row_addr = buf + m * 128;
           // everything that does not depend on the accumulator: side rows through registers, mask words
           uint4 sd[CPS][4];
           uint32_t mwd[CPS];
@@ -704,7 +718,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
           // the staging buffer is free once the previous store has been read out of it; then the side slab may land in it
           if (leader_warp && elect_one()) {
-            tma_store_wait_read();
+            if constexpr (NB == 2) tma_store_wait_read_1();    // the store before last used this tile
+            else tma_store_wait_read();
             if (side_tma) {
               mbar_arrive_expect_tx(sbar, kSlabBytes);
               tma_load_4d(buf, &tmap_side, sbar, c_slab, (MT == 2 && j) ? cw[MT - 1] : cw[0], (MT == 2 && j) ? ch[MT - 1] : ch[0],

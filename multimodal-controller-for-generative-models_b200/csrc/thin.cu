@@ -102,6 +102,51 @@ __global__ void thin_col2im_kernel(const float* __restrict__ Tm, int CT, float* 
 }
 
 
+// Tiled col2im: a CTA owns 256 consecutive pixels of the flattened (n, h, w) order.  The T rows those pixels gather from —
+// the tile plus W + 1 pixels on either side — are read ONCE, coalesced (16 bytes per thread), into shared memory with a
+// row pitch of CT + 1 floats, so the per-pixel tap reads (one row per thread, same column across the warp) hit 32
+// different banks.  The row-per-thread global reads of thin_col2im_kernel touch a 32-byte sector for every 4 bytes they
+// use per instruction: 70 us for the 67 MB of T at 512 x 32 x 32, against 10.4 us for one pass at HBM speed.
+static constexpr int kC2iTile = 256;
+__global__ void __launch_bounds__(kC2iTile)
+thin_col2im_tiled_kernel(const float* __restrict__ Tm, int CT, float* __restrict__ thin, long total, int H, int W, int Ct,
+                         int R, int S, const float* __restrict__ bias, int flags) {
+  extern __shared__ float srows[];
+  const int pad = (R - 1) / 2, halo = pad * (W + 1), pitch = CT + 1, rows = kC2iTile + 2 * halo, q4 = CT >> 2;
+  const long p0 = (long)blockIdx.x * kC2iTile;
+  for (int i = threadIdx.x; i < rows * q4; i += kC2iTile) {
+    const int r = i / q4, c = (i - r * q4) << 2;
+    const long pr = p0 - halo + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pr >= 0 && pr < total) v = __ldg(reinterpret_cast<const float4*>(Tm + pr * CT + c));
+    float* d = srows + r * pitch + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const long p = p0 + threadIdx.x;
+  if (p >= total) return;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  float acc[kMaxCt];
+#pragma unroll
+  for (int j = 0; j < kMaxCt; ++j) acc[j] = (j < Ct && (flags & MCGM_EPI_BIAS)) ? __ldg(bias + j) : 0.0f;
+  for (int r = 0; r < R; ++r) {
+    const int hh = h + r - pad;
+    if (hh < 0 || hh >= H) continue;
+    for (int s = 0; s < S; ++s) {
+      const int ww = w + s - pad;
+      if (ww < 0 || ww >= W) continue;
+      const float* tp = srows + ((int)threadIdx.x + halo + (r - pad) * W + (s - pad)) * pitch + (r * S + s) * Ct;
+#pragma unroll
+      for (int j = 0; j < kMaxCt; ++j)
+        if (j < Ct) acc[j] += tp[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxCt; ++j)
+    if (j < Ct) thin[p * Ct + j] = (flags & MCGM_EPI_TANH) ? tanhf(acc[j]) : acc[j];
+}
+
+
 }  // namespace mcgm
 
 using namespace mcgm;
@@ -136,6 +181,15 @@ extern "C" int mcgm_thin_col2im(const float* T, int CT, float* thin, int N, int 
   MCGM_CHECK_ARG(Ct >= 1 && Ct <= kMaxCt && R * S * Ct <= CT, "thin_col2im: Ct=%d R=%d S=%d do not fit CT=%d", Ct, R, S, CT);
   if (flags & MCGM_EPI_BIAS) MCGM_CHECK_ARG(bias, "thin_col2im: BIAS without bias");
   const long total = (long)N * H * W;
+  const int pad = (R - 1) / 2;
+  const size_t tiled_smem = (size_t)(kC2iTile + 2 * pad * (W + 1)) * (CT + 1) * sizeof(float);
+  if (R == S && (R & 1) && CT % 4 == 0 && tiled_smem <= 48 * 1024 && ((uintptr_t)T & 15) == 0) {
+    const long tiles = (total + kC2iTile - 1) / kC2iTile;
+    MCGM_CHECK_ARG(tiles < (1L << 31), "thin_col2im: tensor too large");
+    thin_col2im_tiled_kernel<<<(int)tiles, kC2iTile, tiled_smem, (cudaStream_t)stream>>>(T, CT, thin, total, H, W, Ct, R, S, bias, flags);
+    MCGM_LAUNCH_CHECK();
+    return 0;
+  }
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   thin_col2im_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(T, CT, thin, N, H, W, Ct, R, S, bias, flags);
