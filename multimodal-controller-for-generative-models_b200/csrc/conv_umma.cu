@@ -115,7 +115,8 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
     if (i < rank - 1) gstride[i] = stride;
   }
   CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride,
-                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu)",
@@ -147,6 +148,11 @@ struct DescKnobs {
   // shared-memory bandwidth (TMA writes + both MMA operands read from smem = 192 B/clk against 128), not by the L2 feed
   // that multicast relieves — DESIGN.md §7.  Kept as a tested knob, off by default.
   uint32_t cluster = 1;
+  // TIMING DIAGNOSTICS ONLY (results are garbage): bit 0 skip the MMAs, 1 skip the activation loads, 2 skip the weight
+  // loads, 3 skip the epilogue body.  tools/microbench.py uses them to time the pipeline's legs in isolation.
+  uint32_t fwd_dbg = 0;
+  // forward conv: CTA pairs (cta_group::2) for the 256-wide tiles / the 128-wide pair tiles (bit 0 / bit 1)
+  uint32_t pair_mma = 3;
 };
 static DescKnobs g_knobs;
 
@@ -188,6 +194,8 @@ struct ConvFwdParams {
   int quad;                                  // 4 consecutive tile pixels never straddle a tile row (TW % 4 == 0)
   int tma_epi;                               // epilogue stages bf16 tiles in shared memory and writes them with TMA stores
   int side_tma;                              // ... and fetches the residual / ReLU-sign tile with a TMA load into the same buffer
+  int dbg;                                   // timing diagnostics (DescKnobs::fwd_dbg), 0 in production
+  int pair_mma;                              // launched as CTA pairs (cta_group::2 MMAs, M = 256)
   float* stats;                              // tma_epi only: [gridDim][2][Cout] per-CTA sum / sum of squares of the stored values
   void* out;
 };
@@ -204,10 +212,25 @@ static constexpr int kSlabBytes = kTileM * 64 * 2;   // 16 KB
 #ifndef MCGM_FWD_RING_BYTES
 #define MCGM_FWD_RING_BYTES 229376
 #endif
-template <int BN, int MT, bool TMAEPI = false>
+// K extent of a pipeline stage (bf16 elements).  The operand ring is bound by bytes in flight over TMA latency (~1400
+// cycles L2 -> shared memory): a stage's bytes stay allocated from the load's issue until the LAST MMA that reads them
+// retires, so a 64-element stage (4 k-steps) holds its 48 KB for 512 tensor cycles longer than the data needs.  With
+// 32-element stages (64-byte rows, SWIZZLE_64B, twice as many stages) the same ring turns over faster.
+#ifndef MCGM_FWD_KB_128
+#define MCGM_FWD_KB_128 64
+#endif
+#ifndef MCGM_FWD_KB_256
+#define MCGM_FWD_KB_256 64
+#endif
+__host__ __device__ constexpr int fwd_kb(int BN, int MT, bool bf16_out, bool tf32, int CL) {
+  return (!bf16_out || tf32 || CL != 1) ? 64 : (BN == 128 && MT == 2) ? MCGM_FWD_KB_128 : (BN == 256 && MT == 1) ? MCGM_FWD_KB_256 : 64;
+}
+template <int BN, int MT, bool TMAEPI = false, int KB = 64, bool PAIR = false>
 struct FwdCfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kKB = KB;
+  static constexpr int kATile = kTileM * KB * 2;           // one M tile's k-block
+  static constexpr int kBBytes = BN * KB * 2 / (PAIR ? 2 : 1);   // a CTA pair splits the weight rows between its two CTAs
+  static constexpr int kStageBytes = MT * kATile + kBBytes;
   static constexpr int kEpiGroups = BN >= 128 ? 2 : 1;
   // Staging tiles per group.  The TMA store of a slab (and the side-slab load) queue behind the operand loads the producer
   // keeps in flight, a few thousand cycles; with one tile per group every slab waits for the previous slab's store to
@@ -219,7 +242,16 @@ struct FwdCfg {
 #ifndef MCGM_FWD_STAGING_BUFS_256
 #define MCGM_FWD_STAGING_BUFS_256 1
 #endif
-  static constexpr int kStagingBufs = (BN == 128 && MT == 2) ? MCGM_FWD_STAGING_BUFS_128 : (BN == 256 ? MCGM_FWD_STAGING_BUFS_256 : 1);
+  // CTA pairs hold half the weight rows per CTA: the 128-wide pair tile's second staging tile then costs no ring stage
+#ifndef MCGM_FWD_STAGING_BUFS_PAIR_128
+#define MCGM_FWD_STAGING_BUFS_PAIR_128 2
+#endif
+#ifndef MCGM_FWD_STAGING_BUFS_PAIR_256
+#define MCGM_FWD_STAGING_BUFS_PAIR_256 1
+#endif
+  static constexpr int kStagingBufs =
+      PAIR ? ((BN == 128 && MT == 2) ? MCGM_FWD_STAGING_BUFS_PAIR_128 : (BN == 256 ? MCGM_FWD_STAGING_BUFS_PAIR_256 : 1))
+           : ((BN == 128 && MT == 2) ? MCGM_FWD_STAGING_BUFS_128 : (BN == 256 ? MCGM_FWD_STAGING_BUFS_256 : 1));
   static constexpr int kStagingBytes = TMAEPI ? kEpiGroups * kStagingBufs * kSlabBytes : 0;
   static constexpr int kRing = TMAEPI ? MCGM_FWD_RING_BYTES : 196608;
   static constexpr int kStages = ((kRing - kStagingBytes) / kStageBytes) > 8 ? 8 : ((kRing - kStagingBytes) / kStageBytes);
@@ -504,14 +536,26 @@ __device__ __forceinline__ uint32_t lds4(uint32_t addr) {
 // bound by the L2 -> SM operand feed (48 KB per 512 tensor-core cycles and SM), and the weights are 2/3 of those bytes
 // for the 256-wide layers.  A pipeline stage is free when EVERY CTA of the cluster has consumed it (the peers' multicasts
 // land in it), so every MMA warp signals the stage's empty barrier in all CTAs (tcgen05.commit ... multicast::cluster).
-template <int BN, int MT, typename OutT, bool TF32, int CL = 1>
+//
+// PAIR (CL = 2): the two CTAs form a CTA PAIR and run cta_group::2 MMAs — M = 256: each CTA's M tile(s) against ONE weight
+// slab of which each CTA holds (and loads) half the rows.  Per SM and k-block that is 1/6 (128-wide pair tiles) to 1/3
+// (256-wide tiles) fewer bytes through TMA and shared memory than two independent CTAs, and the tensor core reads B
+// once for both.  The even CTA issues every MMA; stage / accumulator hand-offs cross the pair:
+//   full[s]   leader's barrier; armed by the leader's producer with BOTH CTAs' bytes, completed by both CTAs' loads
+//   empty[s]  each CTA's own; the leader's tcgen05.commit multicasts the arrival to both
+//   tfull[a]  each CTA's own; multicast commit
+//   tempty[a] leader's barrier; the epilogue threads of BOTH CTAs arrive on it
+template <int BN, int MT, typename OutT, bool TF32, int CL = 1, bool PAIR = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_side,
                 const ConvFwdParams p) {
   constexpr bool kTmaEpi = (sizeof(OutT) == 2) && !TF32 && BN >= 64;    // bf16 tiles of >= 64 channels: staged + TMA-stored
-  using Cfg = FwdCfg<BN, MT, kTmaEpi>;
-  constexpr int kElems = TF32 ? 32 : 64;                 // operand elements per 128-byte k-block row
+  static_assert(!PAIR || (CL == 2 && kTmaEpi), "CTA pairs: clusters of two, bf16 staged epilogue");
+  constexpr int KB = fwd_kb(BN, MT, sizeof(OutT) == 2, TF32, CL);
+  using Cfg = FwdCfg<BN, MT, kTmaEpi, KB, PAIR>;
+  constexpr int kElems = TF32 ? 32 : KB;                 // operand elements per k-block row (128 bytes; 64 with KB = 32)
+  constexpr int kABytes = Cfg::kATile;                   // shadows the 64-element constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();                       // 128B-swizzled TMA tiles need a 1024-byte aligned base
@@ -541,11 +585,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       tma_prefetch_desc(&tmap_out);
       if (p.side_tma) tma_prefetch_desc(&tmap_side);
     }
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kConvThreads - 64); mbar_init(side_bar(s), 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), PAIR ? 1 : CL); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), (kConvThreads - 64) * (PAIR ? 2 : 1));
+      mbar_init(side_bar(s), 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync_all();                // the peers' barriers are initialised before anyone signals them
   else __syncthreads();
@@ -584,8 +635,28 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int dh = p.tap_dh[ph * kMaxTaps + tap], dw = p.tap_dw[ph * kMaxTaps + tap];
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          if (CL == 1 && p.dbg) {                              // timing diagnostics: leave out one or both operands
+            mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 2) ? 0 : MT * kABytes) + ((p.dbg & 4) ? 0 : Cfg::kBBytes));
+            if (!(p.dbg & 2))
+              for (int j = 0; j < MT; ++j)
+                tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kElems, w0[j] + dw, h0[j] + dh, n0[j]);
+            if (!(p.dbg & 4)) tma_load_2d(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kElems, wrow0);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (++cb == p.kpt) { cb = 0; ++tap; }
+            continue;
+          }
+          if constexpr (PAIR) {
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+#pragma unroll
+            for (int j = 0; j < MT; ++j)
+              tma_load_4d_2sm(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kElems, w0[j] + dw, h0[j] + dh, n0[j]);
+            tma_load_2d_2sm(sa + MT * kABytes, &tmap_w, full_bar(stage), tap * p.Cin + cb * kElems, wrow0 + crank * (BN / 2));
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (++cb == p.kpt) { cb = 0; ++tap; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
           for (int j = 0; j < MT; ++j)
             tma_load_4d(sa + j * kABytes, &tmap_x, full_bar(stage), cb * kElems, w0[j] + dw, h0[j] + dh, n0[j]);
@@ -601,8 +672,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      // ===== MMA issuer =====
+    if ((!PAIR || crank == 0) && elect_one()) {
+      // ===== MMA issuer (CTA pairs: the leader CTA's, for both) =====
       int stage = 0, phase = 0, it = 0;
       for (int tc = cid; tc < p.total_ctiles; tc += ncl, ++it) {
         const int as = it % Cfg::kAccStages, aphase = (it / Cfg::kAccStages) & 1;
@@ -612,20 +683,30 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (CL == 1 && (p.dbg & 1)) {                        // timing diagnostics: consume the stage without computing
+            mbar_arrive(empty_bar(stage));
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t bdesc = smem_desc(p.desc_templ, sa + MT * kABytes);
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
             const uint64_t adesc = smem_desc(p.desc_templ, sa + j * kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_any(TF32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+            for (int k = 0; k < KB / 16; ++k) {
+              if constexpr (PAIR) umma_f16_2sm(d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+              else umma_any(TF32, d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+            }
           }
-          if constexpr (CL == 1) umma_commit(empty_bar(stage));
+          if constexpr (PAIR) umma_commit_2sm(empty_bar(stage));    // frees the stage in both CTAs
+          else if constexpr (CL == 1) umma_commit(empty_bar(stage));
           else umma_commit_mc(empty_bar(stage), kClusterMask);      // the stage is free for the peers' multicasts too
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(as));
+        if (CL == 1 && (p.dbg & 1)) mbar_arrive(tfull_bar(as));
+        else if constexpr (PAIR) umma_commit_2sm(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
       }
     }
   } else {
@@ -658,7 +739,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int grp = BN >= 128 ? half : 0;
       const bool leader_warp = (quad == 0) && (BN >= 128 || half == 0);   // its elected lane issues the TMA traffic of the group
       constexpr int NB = Cfg::kStagingBufs;                  // staging tiles per group, used alternately
-      static_assert(NB == 1 || (MT * SPG) % NB == 0, "the staging tile of a slab must be a compile-time choice");
       const uint32_t buf0 = staging_base + grp * NB * kSlabBytes;
       const uint32_t sbar = side_bar(grp);
       const int sw = m & 7;
@@ -695,9 +775,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * BN);
         bool waited = false;
+        if (p.dbg & 8) {                                       // timing diagnostics: release the accumulator untouched
+          mbar_wait(tfull_bar(as), aphase);
+          tc_fence_before();
+          if constexpr (PAIR) mbar_arrive_leader(tempty_bar(as));
+          else mbar_arrive(tempty_bar(as));
+          continue;
+        }
+        // rolled over the M tiles (the unrolled body of both tiles does not fit the instruction cache: a third of the
+        // epilogue's stall samples were instruction fetches), unrolled over the slabs of one tile
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
 #pragma unroll
-        for (int s = 0; s < MT * SPG; ++s) {
-          const int j = s / SPG, sl = s % SPG;
+        for (int sl = 0; sl < SPG; ++sl) {
+          const int s = j * SPG + sl;
           const int c_tile = (BN >= 128 ? half * (BN / 2) + sl * 64 : 0);       // slab's first column inside the CTA tile
           const int c_slab = nt * BN + c_tile;                                  // ... and inside the tensor
           const bool ok = (MT == 2 && j) ? valid[MT - 1] : valid[0];
@@ -740,7 +831,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           tmem_ld_wait();
           if (s == MT * SPG - 1) {                             // accumulator drained: the MMA warp may refill it
             tc_fence_before();
-            mbar_arrive(tempty_bar(as));
+            if constexpr (PAIR) mbar_arrive_leader(tempty_bar(as));      // the leader's MMA warp refills both CTAs' TMEM
+            else mbar_arrive(tempty_bar(as));
           }
 #pragma unroll
           for (int k = 0; k < CPS; ++k) {
@@ -779,6 +871,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                          (MT == 2 && j) ? cn[MT - 1] : cn[0]);
             tma_store_commit();
           }
+        }
         }
       }
       if (leader_warp && elect_one()) tma_store_wait_all();
@@ -929,7 +1022,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -1240,11 +1334,11 @@ struct FwdMaps {
   CUtensorMap x, w, out, side;          // out / side: only read by kernels launched with p.tma_epi / p.side_tma
 };
 
-template <int BN, int MT, typename OutT, bool TF32 = false, int CL = 1>
+template <int BN, int MT, typename OutT, bool TF32 = false, int CL = 1, bool PAIR = false>
 static int launch_fwd(const FwdMaps& maps, ConvFwdParams p, cudaStream_t st) {
   constexpr bool kTmaEpi = (sizeof(OutT) == 2) && !TF32 && BN >= 64;
-  using Cfg = FwdCfg<BN, MT, kTmaEpi>;
-  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32, CL>;
+  using Cfg = FwdCfg<BN, MT, kTmaEpi, fwd_kb(BN, MT, sizeof(OutT) == 2, TF32, CL), PAIR>;
+  auto kern = conv_fwd_kernel<BN, MT, OutT, TF32, CL, PAIR>;
   if (!kTmaEpi) p.tma_epi = p.side_tma = 0;
   static int max_clusters = 0;         // co-resident clusters of this kernel on this device (CL > 1)
   static bool configured = false;
@@ -1290,6 +1384,7 @@ static int launch_fwd_t(const FwdMaps& maps, const ConvFwdParams& p, bool f32, c
   if (p.tf32) return launch_fwd<BN, MT, float, true>(maps, p, st);      // fp32 parity pipeline
   if (f32) return launch_fwd<BN, MT, float>(maps, p, st);
   if constexpr ((BN == 256 && MT == 1) || (BN == 128 && MT == 2)) {     // the shapes that carry the flops: cluster variants
+    if (cl == 2 && p.pair_mma) return launch_fwd<BN, MT, __nv_bfloat16, false, 2, true>(maps, p, st);
     if (cl == 2) return launch_fwd<BN, MT, __nv_bfloat16, false, 2>(maps, p, st);
     if (cl == 4) return launch_fwd<BN, MT, __nv_bfloat16, false, 4>(maps, p, st);
   }
@@ -1384,6 +1479,8 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 10: g_knobs.tma_epi = (uint32_t)value; break;
     case 11: g_knobs.cluster = (uint32_t)value; break;
     case 14: g_knobs.wg_pair = (uint32_t)value; break;
+    case 15: g_knobs.fwd_dbg = (uint32_t)value; break;
+    case 16: g_knobs.pair_mma = (uint32_t)value; break;
     case 12: g_thin_umma_wgrad = (int)value; break;       // thin (RGB-side) convs: tcgen05 / TMA kernels (1) or mma.sync kernels (0)
     case 13: g_thin_umma_fwd = (int)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
@@ -1506,16 +1603,34 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
   if (!f32 && !tf32 && ((BN == 256 && !(pair && g_knobs.mt2_256)) || (BN == 128 && pair)) &&
       (g_knobs.cluster == 2 || g_knobs.cluster == 4) && (long)m_tiles * p.n_tiles * p.PH >= 4L * sms)
     cl = (int)g_knobs.cluster;
+  // CTA pairs for the tiles that carry the flops (ragged tile counts are padded with a dummy tile, see tile_of)
+  const bool mt2_sel = (BN == 256) ? (pair && g_knobs.mt2_256) : pair;
+  if (!f32 && !tf32 && cl == 1 && m_tiles >= 2 * (mt2_sel ? 2 : 1) &&
+      ((BN == 256 && !mt2_sel && (g_knobs.pair_mma & 1u)) || (BN == 128 && mt2_sel && (g_knobs.pair_mma & 2u)))) {
+    cl = 2;
+    p.pair_mma = 1;
+    p.idesc = make_idesc_bf16(2 * kTileM, BN, 0, 0, 0);
+  }
   FwdMaps maps{};
+  // the k-block of the instantiation launch_fwd_t will pick (fwd_kb): 64-byte rows travel with SWIZZLE_64B
+  const int mt_sel = (BN == 256) ? ((pair && g_knobs.mt2_256) ? 2 : 1) : (pair ? 2 : 1);
+  const int kb_sel = fwd_kb(BN, mt_sel, !f32, tf32, cl);
+  int op_swizzle = 2;
+  if (kb_sel == 32) {
+    op_swizzle = 1;
+    p.kblk = 32; p.kpt = Cin / 32; p.num_kb = p.T * p.kpt;
+    p.desc_templ = make_smem_desc_hi_lbo(g_knobs.k_lbo, 512, g_knobs.version, 4);    // SBO = 8 rows x 64 B, layout SWIZZLE_64B
+  }
+  const int kblk_sel = (kb_sel == 32) ? 32 : kblk;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint32_t box[4] = {(uint32_t)kblk, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
-    if (int e = make_tmap(&maps.x, x, 4, dims, box, p.IS, tf32)) return e;
+    const uint32_t box[4] = {(uint32_t)kblk_sel, (uint32_t)(p.TW * p.IS), (uint32_t)(p.TH * p.IS), (uint32_t)p.TN};
+    if (int e = make_tmap(&maps.x, x, 4, dims, box, p.IS, tf32, op_swizzle)) return e;
   }
   {
     const uint64_t dims[2] = {(uint64_t)p.T * Cin, (uint64_t)p.PH * Cout};
-    const uint32_t box[2] = {(uint32_t)kblk, (uint32_t)(BN / cl)};      // a cluster CTA fetches BN / cl weight rows
-    if (int e = make_tmap(&maps.w, w, 2, dims, box, 1, tf32)) return e;
+    const uint32_t box[2] = {(uint32_t)kblk_sel, (uint32_t)(BN / cl)};      // a cluster CTA fetches BN / cl weight rows
+    if (int e = make_tmap(&maps.w, w, 2, dims, box, 1, tf32, op_swizzle)) return e;
   }
   // Staged epilogue (bf16 tiles of >= 64 channels): the output tile of an M tile is the box (64 ch, TW*OS, TH*OS, TN) at
   // (c, w0*OS + pw, h0*OS + ph, n0) of the NHWC tensor, traversal stride OS — the store-side twin of the operand loads.
@@ -1535,6 +1650,7 @@ static int conv_fwd_impl(int kind, int in_dtype, const void* x, const void* w, v
       p.side_tma = 1;
     }
   }
+  p.dbg = (int)g_knobs.fwd_dbg;
   p.m_super = m_tiles;           // launch_fwd turns this into ceil(m_tiles / MT)
   if (stats != nullptr) {
     // batch statistics of the STORED output for the BatchNorm that consumes it, accumulated by the staged epilogue

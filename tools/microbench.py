@@ -115,3 +115,18 @@ if "gate" in which:
     packed = ops.PackedCodebook(cb)
     t = timeit(lambda: ops.gate_fwd(x, GATE_RELU | GATE_MASK, labels, packed, None, None, None, None, True))
     print(f"relu_gate 16x16 C128 +raw: {t * 1e6:7.1f} us {x.numel() * 2 * 3 / t / 1e9:7.0f} GB/s", flush=True)
+if "legs" in which:
+    # the forward conv's pipeline legs in isolation (debug knob 15; results are garbage, only the time matters)
+    from mcgm_b200._lib import EPI_BIAS, EPI_RES
+    LEGS = [(0, "all"), (8, "loads + MMA (no epilogue)"), (9, "loads only"), (9 | 4, "activation loads only"),
+            (9 | 2, "weight loads only"), (2 | 4 | 8, "MMA only"), (2 | 4, "MMA + epilogue"), (1 | 2 | 4, "epilogue only")]
+    for (H, C, fl) in [(32, 128, 0), (32, 128, 3), (32, 256, 0), (8, 128, 0)]:
+        x = torch.randn(N, H, H, C, device=dev).to(torch.bfloat16)
+        w = torch.randn(C, 3, 3, C, device=dev).to(torch.bfloat16)
+        bias = torch.randn(C, device=dev) if fl & EPI_BIAS else None
+        res = torch.randn(N, H, H, C, device=dev).to(torch.bfloat16) if fl & EPI_RES else None
+        for v, name in LEGS:
+            _lib.call("mcgm_debug_set", 15, v)
+            t = timeit(lambda: ops.conv_fwd(x, w, torch.bfloat16, bias, res, None, None, None, fl))
+            print(f"legs {H}x{H} {C}->{C} f{fl:#x} {name:28s}: {t * 1e6:8.1f} us", flush=True)
+        _lib.call("mcgm_debug_set", 15, 0)
