@@ -460,9 +460,10 @@ def check_conv_variants():
 
 
 def check_conv_cluster():
-    """Thread-block clusters with multicast weights (mcgm_debug_set key 11): large-M forward convs — the shapes whose
-    launch takes the cluster path — must be BIT-IDENTICAL with clusters of 1, 2 and 4 CTAs (the arithmetic is the
-    same, only the operand delivery differs), including odd tile counts (a dummy tile for the last cluster), every
+    """CTA pairs (cta_group::2 MMAs, mcgm_debug_set key 16 — the default for the 256-wide and the 128-wide pair tiles) and
+    thread-block clusters with multicast weights (key 11): large-M forward convs — the shapes whose launch takes those
+    paths — must be BIT-IDENTICAL with one CTA per tile, CTA pairs, and clusters of 2 and 4 CTAs (the arithmetic is the
+    same, only the operand delivery and the MMA's M extent differ), including odd tile counts (a dummy tile for the last cluster), every
     fused epilogue and the epilogue statistics; the cluster-of-2 result is also held against torch's fp32 conv."""
     from mcgm_b200._lib import CONV_PHASE2, CONV_S1, EPI_BIAS
     rows = []
@@ -494,8 +495,10 @@ def check_conv_cluster():
             run = lambda: ops.conv_fwd_ex(CONV_PHASE2, x, w, torch.bfloat16, bias)                     # noqa: E731
             run_st = lambda: ops.conv_fwd_bnstats(CONV_PHASE2, x, w, bias)                             # noqa: E731
         outs, stats = {}, {}
-        for cl in (1, 2, 4):
-            _lib.call("mcgm_debug_set", 11, cl)
+        # 1 = one CTA per tile (CTA pairs off), "pair" = cta_group::2 MMAs (key 16, the default), 2 / 4 = multicast clusters
+        for cl in (1, "pair", 2, 4):
+            _lib.call("mcgm_debug_set", 11, cl if isinstance(cl, int) else 1)
+            _lib.call("mcgm_debug_set", 16, 3 if cl == "pair" else 0)
             try:
                 outs[cl] = run()
                 if run_st is not None:
@@ -504,8 +507,9 @@ def check_conv_cluster():
                     rows.append((f"cluster{cl} {kind} N={N} {Cin}->{Cout} f{fl:#x}: bnstats output identical", float((o2.float() != outs[cl].float()).sum()), EXACT))
             finally:
                 _lib.call("mcgm_debug_set", 11, 1)
+                _lib.call("mcgm_debug_set", 16, 3)
         tag = f"{kind} N={N} H={H} {Cin}->{Cout} k{R} f{fl:#x}"
-        for cl in (2, 4):
+        for cl in ("pair", 2, 4):
             rows.append((f"cluster{cl} == cluster1 {tag}", float((outs[cl].float() != outs[1].float()).sum()), EXACT))
             if stats:
                 rows.append((f"cluster{cl} stats mean {tag}", rel(stats[cl][0], stats[1][0]), F32_TOL))

@@ -10,6 +10,7 @@ timeout 300 $P --mode g --warm 1 > gpurun_out/plain_g.log 2>&1 && \
 $NCU --profile-from-start off --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_g.csv $P --mode g --warm 1 > gpurun_out/ncu_g.log 2>&1
 F="--set full --import-source on --profile-from-start off"
 $NCU $F -k regex:"conv_fwd_kernel<.int.256" -c 4 -o gpurun_out/prof_conv_fwd -f $P --mode g --warm 1 > gpurun_out/ncu_f1.log 2>&1
+$NCU --set full --profile-from-start off -k regex:"conv_fwd_kernel<.int.256" -s 7 -c 3 -o gpurun_out/prof_conv_fwd_big -f $P --mode g --warm 1 > gpurun_out/ncu_f1b.log 2>&1
 $NCU $F -k regex:"conv_fwd_kernel<.int.128, .int.2" -c 3 -o gpurun_out/prof_conv_fwd_d -f $P --mode d --warm 1 > gpurun_out/ncu_f2.log 2>&1
 $NCU $F -k regex:"conv_wgrad_kernel" -c 4 -o gpurun_out/prof_wgrad -f $P --mode g --warm 1 > gpurun_out/ncu_f3.log 2>&1
 $NCU $F -k regex:"conv_wgrad_kernel" -c 3 -o gpurun_out/prof_wgrad_d -f $P --mode d --warm 1 > gpurun_out/ncu_f3b.log 2>&1

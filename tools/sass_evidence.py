@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "multimodal-controller-for-generative-models_b200", "libmcgm.so")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "HMMA", "LDSM", "LDGSTS", "SHFL",
+WATCH = ["UTCHMMA", "2CTA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "HMMA", "LDSM", "LDGSTS", "SHFL",
          "STG", "LDG", "LDL", "STL"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
@@ -25,6 +25,8 @@ for line in sass.splitlines():
     if m and cur is not None:
         cur[m.group(1)] += 1
         cur["_total"] += 1
+        if re.search(r"UTCHMMA\.2CTA", line):
+            cur["2CTA"] += 1
 
 rows = []
 for name, c in kernels.items():
@@ -34,11 +36,11 @@ for name, c in kernels.items():
 rows.sort(key=lambda r: r[0])
 out = [f"# SASS evidence — round {tag}", "",
        f"`cuobjdump -sass` of `libmcgm.so` (sm_100a), static instruction counts per kernel (`tools/sass_evidence.py`).",
-       "tcgen05.mma = `UTCHMMA` (bf16) / `UTCQMMA`-family, tcgen05.ld = `LDTM`, tcgen05.commit = `UTCBAR`, TMA loads = `UTMALDG`,",
+       "tcgen05.mma = `UTCHMMA` (bf16; `2CTA` = those issued as `UTCHMMA.2CTA`, cta_group::2 pairs) / `UTCQMMA`-family, tcgen05.ld = `LDTM`, tcgen05.commit = `UTCBAR`, TMA loads = `UTMALDG`,",
        "mbarrier = `SYNCS`, warp-level `mma.sync` = `HMMA`, `ldmatrix` = `LDSM`, `cp.async` = `LDGSTS`; `LDL`/`STL` = local-memory spills.", "",
        "| kernel | SASS instr | " + " | ".join(WATCH) + " |", "|---|---:|" + "---:|" * len(WATCH)]
 for d, c in rows:
-    if not any(c[w] for w in WATCH[:11]) and c["_total"] < 400:
+    if not any(c[w] for w in WATCH[:12]) and c["_total"] < 400:
         continue
     out.append(f"| `{d}` | {c['_total']} | " + " | ".join(str(c[w]) if c[w] else "" for w in WATCH) + " |")
 path = os.path.join(ROOT, "profiles", f"{tag}_sass_evidence.md")

@@ -117,9 +117,9 @@ import json
 if tag != "r01":
     # round 2+: the launch of a shape is found by its duration window [lo, hi] us inside the report (the capture
     # order depends on the step), not by a fixed index
-    TRAFFIC = {"conv+bnstats kind0 512x32x32 256->256 f0x5": ("prof_conv_fwd_big.ncu-rep", (380, 480)),
-               "conv+bnstats kind2 512x16x16 256->256 f0x1": ("prof_conv_fwd_big.ncu-rep", (190, 260)),
-               "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", (130, 175)),
+    TRAFFIC = {"conv+bnstats kind0 512x32x32 256->256 f0x5": ("prof_conv_fwd_big.ncu-rep", (330, 480)),
+               "conv+bnstats kind2 512x16x16 256->256 f0x1": ("prof_conv_fwd_big.ncu-rep", (180, 260)),
+               "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", (105, 175)),
                "thin_conv 512x32x32 3->128 k3 gate1": ("prof_thin.ncu-rep", (44, 60)),
                "gate_fwd 512x32x32x256 f0xb raw0": ("prof_gate.ncu-rep", (90, 110)),
                "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", (480, 600)),
