@@ -1070,8 +1070,15 @@ struct WgCfg {
   static constexpr int kTmemRaw = NT * BN + 16;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
   static constexpr int kOnesBytes = 8192;              // an all-ones [64 k][64 mn] bf16 operand tile
-  static constexpr int kStages = ((196608 - kOnesBytes) / kStageBytes) > 8 ? 8 : ((196608 - kOnesBytes) / kStageBytes);
+  // The whole 227 KB a CTA may own: the kernel never touches L1 (TMA operands, float4 partial stores), and the operand
+  // ring is bound by bytes in flight over TMA latency — the fourth 48 KB stage is what the 192 KB budget left out.
+#ifndef MCGM_WG_RING_BYTES
+#define MCGM_WG_RING_BYTES 229376
+#endif
+  static constexpr int kRing = MCGM_WG_RING_BYTES - kOnesBytes - 1280;
+  static constexpr int kStages = (kRing / kStageBytes) > 8 ? 8 : (kRing / kStageBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 256;
+  static_assert(kSmemBytes <= 232448, "wgrad exceeds the 227 KB a CTA may own");
 };
 
 template <int BN, int NT>
