@@ -53,12 +53,12 @@ static EncodeTiledFn get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  uint64_t d[4];
-  uint32_t b[4];
+  uint64_t d[5];
+  uint32_t b[5];
   int rank, estride, f32, swizzle;
   bool operator==(const MapKey& o) const {
     if (ptr != o.ptr || rank != o.rank || estride != o.estride || f32 != o.f32 || swizzle != o.swizzle) return false;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
       if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
     return true;
   }
@@ -66,7 +66,7 @@ struct MapKey {
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)(k.rank + 16 * k.estride + 64 * k.f32 + 128 * k.swizzle) * 0x9e3779b97f4a7c15ull;
-    for (int i = 0; i < 4; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
+    for (int i = 0; i < 5; ++i) h = h * 1099511628211ull ^ (k.d[i] * 31 + k.b[i]);
     return h;
   }
 };
@@ -130,6 +130,49 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
   return 0;
 }
 
+// 5-D view of a bf16 NHWC tensor for MN-major operand tiles: dims (64 channels, W, H, N, C/64) — the channel BLOCK is the
+// slowest box dimension, so ONE box of `blocks` channel blocks lands as `blocks` consecutive [pixels][64 ch] tiles with
+// the 128B swizzle, exactly the MN-block sequence a UMMA descriptor walks with its leading-dimension offset.  One TMA
+// operation per operand instead of one per 64 channels: the per-operation cost of cp.async.bulk.tensor is what bounded
+// the weight gradient's ring.
+int make_tmap_blocked(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int box_w, int box_h, int box_n,
+                      int blocks, int estride) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{};
+  key.ptr = ptr; key.rank = 5; key.estride = estride; key.f32 = 0; key.swizzle = 2;
+  const uint64_t dims[5] = {64u, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(C / 64)};
+  const uint32_t box[5] = {64u, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)box_n, (uint32_t)blocks};
+  for (int i = 0; i < 5; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+  key.d[0] = (uint64_t)C;                     // the channel count distinguishes views of one pointer
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < 5; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = (i == 1 || i == 2) ? (cuuint32_t)estride : 1u; }
+  gstride[0] = (cuuint64_t)C * 2;                       // w
+  gstride[1] = (cuuint64_t)W * C * 2;                   // h
+  gstride[2] = (cuuint64_t)H * W * C * 2;               // n
+  gstride[3] = 128;                                     // channel block
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5u, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MCGM_E_CUDA, "cuTensorMapEncodeTiled (blocked 5-D view) failed with CUresult %d (C %d W %d H %d N %d, box %d %d %d x %d blocks)",
+                (int)r, C, W, H, N, box_w, box_h, box_n, blocks);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // debug knobs (bring-up only): descriptor field overrides
 // ---------------------------------------------------------------------------
@@ -140,6 +183,9 @@ struct DescKnobs {
   uint32_t mt2 = 1, mt2_256 = 0;             // forward conv: two M tiles per CTA (BN <= 128 / BN = 256)
   uint32_t nt2 = 1;                          // wgrad: two filter taps per CTA (Cin tile 128)
   uint32_t wg_splits = 0;                    // wgrad: force the split-K factor (0 = automatic)
+  // wgrad: 5-D blocked tensor maps = one TMA operation per operand instead of one per 64 channels.  Parity green, time
+  // unchanged (404 vs 406 us, 130 vs 132 us): the ring is not bound by the operation count.  Off by default.
+  uint32_t wg_blocked = 0;
   uint32_t wg_pair = 1;                      // wgrad, NT = 2: one N = 2*BN MMA per k step for both taps (0: one MMA per tap)
   // staged forward epilogue: bit 2 = fetch the residual / ReLU-sign tile by TMA load (else through registers)
   uint32_t tma_epi = 7;
@@ -1045,6 +1091,7 @@ struct WgradParams {
   int cout_tiles, cin_tiles, taps, tap_groups;
   uint64_t desc_templ;
   uint32_t idesc, idesc_bias;
+  int blocked_maps;                     // the tensor maps are the 5-D blocked views (make_tmap_blocked): one load per operand
   uint32_t idesc_pair;                  // NT = 2: one N = 2*BN instruction covers both taps (their X tiles are adjacent in smem)
   float* partial;                       // [splits][Cout*R*S*Cin]
   float* bias_partial;                  // [splits][bias_slots][Cout] or nullptr
@@ -1062,10 +1109,19 @@ struct WgMaps {
 
 // NT = number of filter taps one CTA accumulates against the SAME dY tile (A operand):
 // the dY bytes fetched per MMA halve with NT = 2.
-template <int BN, int NT>
+// KB = pixels per k-block (ring stage): 64, or 32 (bf16 only).  The rows of the MN-major operand tiles are pixels, so a
+// 32-pixel stage has half the 128-byte rows of a 64-pixel one — same TMA efficiency, twice the stages, and a stage's bytes
+// are released after 2 instead of 4 k-steps (the ring is bound by bytes in flight over TMA latency).
+#ifndef MCGM_WG_KB
+#define MCGM_WG_KB 64
+#endif
+template <int BN, int NT, int KB = 64>
 struct WgCfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + NT * kBBytes;
+  static constexpr int kKB = KB;
+  static constexpr int kBlkBytes = KB * 128;           // one 64-wide MN block of a stage: KB pixel rows of 128 B
+  static constexpr int kATile = kTileM * KB * 2;
+  static constexpr int kBBytes = BN * KB * 2;
+  static constexpr int kStageBytes = kATile + NT * kBBytes;
   static constexpr int kBiasCol = NT * BN;             // 16 extra accumulator columns: dY^T x ones = bias gradient
   static constexpr int kTmemRaw = NT * BN + 16;
   static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : kTmemRaw <= 64 ? 64 : kTmemRaw <= 128 ? 128 : kTmemRaw <= 256 ? 256 : 512;
@@ -1081,10 +1137,11 @@ struct WgCfg {
   static_assert(kSmemBytes <= 232448, "wgrad exceeds the 227 KB a CTA may own");
 };
 
-template <int BN, int NT>
+template <int BN, int NT, int KB = 64>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
-  using Cfg = WgCfg<BN, NT>;
+  using Cfg = WgCfg<BN, NT, KB>;
+  constexpr int kABytes = Cfg::kATile;                 // shadows the 64-pixel constant
   // Several independent weight gradients of identical geometry (the layers of one backward pass that share a
   // shape) can share one launch: alone, a small-spatial layer fills 148 SMs only through ~29-way split-K, whose
   // partials then dominate its cost; two to four of them side by side need a quarter of the splits each.
@@ -1159,17 +1216,25 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        if (p.blocked_maps) {                    // one operation per operand: all its 64-channel blocks in one 5-D box
+          tma_load_5d(sa, &tmap_dy, full_bar(stage), 0, w0 * p.AS + ac, h0 * p.AS + ar, n0, co0 / 64);
+#pragma unroll
+          for (int q = 0; q < NT; ++q)
+            if (q < ntaps)
+              tma_load_5d(sa + kABytes + q * Cfg::kBBytes, &tmap_x, full_bar(stage), 0, w0 * p.BS + ds[q], h0 * p.BS + dr[q], n0, ci0 / 64);
+        } else {
 #pragma unroll
         for (int j = 0; j < kTileM / 64; ++j)
-          tma_load_4d(sa + j * 8192, &tmap_dy, full_bar(stage), co0 + 64 * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
+          tma_load_4d(sa + j * Cfg::kBlkBytes, &tmap_dy, full_bar(stage), co0 + 64 * j, w0 * p.AS + ac, h0 * p.AS + ar, n0);
 #pragma unroll
         for (int q = 0; q < NT; ++q) {
           if (q < ntaps) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * 8192, &tmap_x, full_bar(stage), ci0 + 64 * j,
+              tma_load_4d(sa + kABytes + q * Cfg::kBBytes + j * Cfg::kBlkBytes, &tmap_x, full_bar(stage), ci0 + 64 * j,
                           w0 * p.BS + ds[q], h0 * p.BS + dr[q], n0);
           }
+        }
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         if (++bw == p.kb_w) { bw = 0; if (++bh == p.kb_h) { bh = 0; ++bn; } }
@@ -1191,7 +1256,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
           // bandwidth (TMA writes + both MMA operands), and this removes a quarter of the operand reads.
           const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
+          for (int k = 0; k < KB / 16; ++k)
             umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc_pair, acc_on | (uint32_t)(k != 0));
         } else
 #pragma unroll
@@ -1199,7 +1264,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
           if (q < ntaps) {
             const uint64_t bdesc = smem_desc(p.desc_templ, sa + kABytes + q * Cfg::kBBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)   // 16 pixel rows of 128 B per MMA
+            for (int k = 0; k < KB / 16; ++k)   // 16 pixel rows of 128 B per MMA
               umma_f16(tmem_base + q * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
                        acc_on | (uint32_t)(k != 0));
           }
@@ -1207,7 +1272,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
         if (do_bias) {
           const uint64_t odesc = smem_desc(p.desc_templ, ones_base);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
+          for (int k = 0; k < KB / 16; ++k)
             umma_f16(tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * 128), odesc, p.idesc_bias,
                      acc_on | (uint32_t)(k != 0));
         }
@@ -1398,10 +1463,10 @@ static int launch_fwd_t(const FwdMaps& maps, const ConvFwdParams& p, bool f32, c
   return launch_fwd<BN, MT, __nv_bfloat16>(maps, p, st);
 }
 
-template <int BN, int NT>
+template <int BN, int NT, int KB = 64>
 static int launch_wgrad(const WgMaps& maps, const WgradParams& p, int grid, cudaStream_t st) {
-  using Cfg = WgCfg<BN, NT>;
-  auto kern = conv_wgrad_kernel<BN, NT>;
+  using Cfg = WgCfg<BN, NT, KB>;
+  auto kern = conv_wgrad_kernel<BN, NT, KB>;
   static bool configured = false;
   if (!configured) {
     MCGM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -1440,7 +1505,7 @@ static int plan_wgrad(int kind, int tf32, int N, int H, int W, int Cin, int Cout
     return fail(MCGM_E_ARG, "wgrad: unknown kind %d", kind);
   }
   // k-block = 64 grid pixels of bf16 or 32 of fp32: its operand tiles are the same bytes either way
-  if (!pick_pixel_box(pl->Hg, pl->Wg, tf32 ? 32 : 64, &pl->KW, &pl->KH, &pl->KN))
+  if (!pick_pixel_box(pl->Hg, pl->Wg, (tf32 || MCGM_WG_KB == 32) ? 32 : 64, &pl->KW, &pl->KH, &pl->KN))
     return fail(MCGM_E_UNSUPPORTED, "wgrad: grid H=%d W=%d cannot be tiled into k-block boxes", pl->Hg, pl->Wg);
   pl->BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
   pl->cin_tiles = Cin / pl->BN;
@@ -1488,6 +1553,7 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 14: g_knobs.wg_pair = (uint32_t)value; break;
     case 15: g_knobs.fwd_dbg = (uint32_t)value; break;
     case 16: g_knobs.pair_mma = (uint32_t)value; break;
+    case 17: g_knobs.wg_blocked = (uint32_t)value; break;
     case 12: g_thin_umma_wgrad = (int)value; break;       // thin (RGB-side) convs: tcgen05 / TMA kernels (1) or mma.sync kernels (0)
     case 13: g_thin_umma_fwd = (int)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
@@ -1748,7 +1814,9 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   p.KW = pl.KW; p.KH = pl.KH; p.KN = pl.KN; p.kb_w = pl.Wg / pl.KW; p.kb_h = pl.Hg / pl.KH;
   p.total_kb = pl.total_kb; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
   p.cout_tiles = pl.cout_tiles; p.cin_tiles = pl.cin_tiles; p.taps = pl.taps; p.tap_groups = pl.tap_groups;
-  p.desc_templ = make_smem_desc_hi_lbo(tf32 ? 4096 : g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
+  p.blocked_maps = g_knobs.wg_blocked ? 1 : 0;
+  constexpr bool kb32 = (MCGM_WG_KB == 32);            // bf16 k-blocks of 32 pixels: MN blocks are 4 KB apart
+  p.desc_templ = make_smem_desc_hi_lbo((tf32 || kb32) ? 4096 : g_knobs.mn_lbo, g_knobs.mn_sbo, g_knobs.version, g_knobs.layout);
   p.idesc = make_idesc_bf16(kTileM, pl.BN, 1, 1, tf32);
   p.idesc_pair = (g_knobs.wg_pair && 2 * pl.BN <= 256) ? make_idesc_bf16(kTileM, 2 * pl.BN, 1, 1, tf32) : 0u;
   p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1, tf32);
@@ -1769,15 +1837,20 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   WgMaps maps{};
   WgReduceOut out{};
   for (int g = 0; g < n; ++g) {
-    {
-      const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
-      const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
-      if (int e = make_tmap(&maps.dy[g], dys[g], 4, dims, box, pl.AS, tf32)) return e;
-    }
-    {
-      const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-      const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
-      if (int e = make_tmap(&maps.x[g], xs[g], 4, dims, box, pl.BS, tf32)) return e;
+    if (p.blocked_maps) {
+      if (int e = make_tmap_blocked(&maps.dy[g], dys[g], Cout, Wdy, Hdy, N, pl.KW * pl.AS, pl.KH * pl.AS, pl.KN, kTileM / 64, pl.AS)) return e;
+      if (int e = make_tmap_blocked(&maps.x[g], xs[g], Cin, W, H, N, pl.KW * pl.BS, pl.KH * pl.BS, pl.KN, pl.BN / 64, pl.BS)) return e;
+    } else {
+      {
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wdy, (uint64_t)Hdy, (uint64_t)N};
+        const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.AS), (uint32_t)(pl.KH * pl.AS), (uint32_t)pl.KN};
+        if (int e = make_tmap(&maps.dy[g], dys[g], 4, dims, box, pl.AS, tf32)) return e;
+      }
+      {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        const uint32_t box[4] = {64u, (uint32_t)(pl.KW * pl.BS), (uint32_t)(pl.KH * pl.BS), (uint32_t)pl.KN};
+        if (int e = make_tmap(&maps.x[g], xs[g], 4, dims, box, pl.BS, tf32)) return e;
+      }
     }
     out.dw[g] = dws[g];
     out.dbias[g] = want_bias ? dbs[g] : nullptr;
@@ -1786,6 +1859,13 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = p.ctas_per_group * n;
   int e;
+  if (kb32 && !tf32) {
+    switch (pl.BN) {
+      case 256: e = launch_wgrad<256, 1, 32>(maps, p, grid, st); break;
+      case 128: e = pl.NT == 2 ? launch_wgrad<128, 2, 32>(maps, p, grid, st) : launch_wgrad<128, 1, 32>(maps, p, grid, st); break;
+      default: e = pl.NT == 2 ? launch_wgrad<64, 2, 32>(maps, p, grid, st) : launch_wgrad<64, 1, 32>(maps, p, grid, st); break;
+    }
+  } else
   switch (pl.BN) {
     case 256: e = launch_wgrad<256, 1>(maps, p, grid, st); break;
     case 128: e = pl.NT == 2 ? launch_wgrad<128, 2>(maps, p, grid, st) : launch_wgrad<128, 1>(maps, p, grid, st); break;

@@ -449,13 +449,16 @@ def check_conv_variants():
     """The same parity rows with the alternative tilings forced on / off through mcgm_debug_set."""
     rows = []
     big = [sh for sh in CONV_SHAPES if sh[0] >= 40]
-    for key, val, tag in [(7, 1, "BN256/MT2"), (6, 0, "MT1 only"), (8, 0, "NT1 only")]:
+    for key, val, tag in [(7, 1, "BN256/MT2"), (6, 0, "MT1 only"), (8, 0, "NT1 only"), (17, 1, "wgrad blocked 5-D maps"),
+                          (16, 0, "no CTA pairs")]:
         _lib.call("mcgm_debug_set", key, val)
         try:
-            rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_fwd(big) if n.startswith("conv")]
-            rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_wgrad(big)]
+            if key != 17:
+                rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_fwd(big) if n.startswith("conv")]
+            if key != 16:
+                rows += [(f"[{tag}] {n}", e, t) for (n, e, t) in check_conv_wgrad(big)]
         finally:
-            _lib.call("mcgm_debug_set", key, {7: 0, 6: 1, 8: 1}[key])
+            _lib.call("mcgm_debug_set", key, {7: 0, 6: 1, 8: 1, 17: 0, 16: 3}[key])
     return rows
 
 
