@@ -135,13 +135,15 @@ def hinge_d(d_real, d_fake):
     return F.relu(1.0 - d_real).mean() + F.relu(1.0 + d_fake).mean()
 
 
-def d_forward_backward(model, img, label, z):
+def d_forward_backward(model, img, label, z, generated=None):
     """Forward + backward of one D update (src/train_gan.py:143-157); returns the hinge loss.
-    G(z) is detached by the reference (:148), so the generator runs without an autograd tape."""
+    G(z) is detached by the reference (:148), so the generator runs without an autograd tape.
+    generated: G(z) computed by the caller (``train_step_pipelined``); z is then unused."""
     from . import ops
     d_x = model.discriminate(img, label)
-    with torch.no_grad():
-        generated = model.generate(label, z)
+    if generated is None:
+        with torch.no_grad():
+            generated = model.generate(label, z)
     d_g = model.discriminate(generated, label)
     d_loss = hinge_d(d_x, d_g)
     ops.reset_deferred()
@@ -219,6 +221,75 @@ def train_step(model, optimizer, input, z=None, reducers=None):
             reducers['discriminator'].enabled = True
         optimizer['generator'].step()
     total = (d_loss - g_loss).abs() if d_loss is not None and g_loss is not None else None
+    return {'loss': total, 'loss_D': d_loss, 'loss_G': g_loss}
+
+
+def train_step_pipelined(model, optimizer, input, z=None, reducers=None, side=None):
+    """``train_step`` with the SAME operations in a schedule that hides each D update's gradient all-reduce and Adam
+    update: G(z) of the NEXT update (and the generator forward of the G update) does not depend on the discriminator, so
+    it is issued on the current stream while ``side`` runs all-reduce + Adam of the update just finished; the streams
+    join before the discriminator is used again.  Every tensor gets the value ``train_step`` gives it (the generator
+    forward moves in front of D(real) inside an update — the two are independent); inside a CUDA graph the fork / join
+    become graph edges.  What stays exposed is the G update's own all-reduce at the end of the iteration."""
+    img, label = input['img'], input[cfg.get('subset', 'label')]
+    n = img.size(0)
+    n_d, n_g = GAN_HYPER['iter']['discriminator'], GAN_HYPER['iter']['generator']
+    if side is None or n_d < 1 or n_g != 1:
+        return train_step(model, optimizer, input, z=z, reducers=reducers)
+    zi = iter(z) if z is not None else None
+    main = torch.cuda.current_stream()
+
+    def draw():
+        if zi is not None:
+            return next(zi)
+        return torch.randn(n, model.latent_size, device=img.device)
+
+    def zero():
+        if reducers is not None:
+            reducers['discriminator'].zero_grad()
+            reducers['generator'].zero_grad()
+        else:
+            optimizer['discriminator'].zero_grad()
+            optimizer['generator'].zero_grad()
+
+    with torch.no_grad():
+        generated = model.generate(label, draw())
+    d_loss = g_loss = None
+    for k in range(n_d):
+        zero()                                                 # after the join: D's Adam has consumed the old gradients
+        if reducers is not None:
+            reducers['generator'].enabled = False
+        d_loss = d_forward_backward(model, img, label, None, generated=generated)
+        if reducers is not None:
+            reducers['generator'].enabled = True
+        side.wait_stream(main)
+        with torch.cuda.stream(side):                          # all-reduce + Adam of this update ...
+            if reducers is not None:
+                reducers['discriminator'].finish()
+            optimizer['discriminator'].step()
+        if k + 1 < n_d:                                        # ... under the next update's G(z)
+            with torch.no_grad():
+                generated = model.generate(label, draw())
+        else:                                                  # ... or under the G update's generator forward (taped)
+            generated = model.generate(label, draw())
+        main.wait_stream(side)
+    zero()
+    if reducers is not None:
+        reducers['discriminator'].enabled = False
+    d_params = [p for p in model.discriminator.parameters() if p.requires_grad]
+    for p in d_params:
+        p.requires_grad_(False)
+    try:
+        g_loss = -model.discriminate(generated, label).mean()
+        g_loss.backward()
+    finally:
+        for p in d_params:
+            p.requires_grad_(True)
+    if reducers is not None:
+        reducers['generator'].finish()
+        reducers['discriminator'].enabled = True
+    optimizer['generator'].step()
+    total = (d_loss - g_loss).abs()
     return {'loss': total, 'loss_D': d_loss, 'loss_G': g_loss}
 
 
@@ -402,11 +473,12 @@ class GraphedDDPIngraphTrainStep:
     update's flat gradient buffer and the Adam updates are all captured (NCCL collectives are capturable; the
     ranks replay the same graph in lock step).  The host issues one ``cudaGraphLaunch`` per iteration at any
     world size — no launch gaps around the collectives, no eager optimiser launches, 1/world folded into Adam.
-    What stays exposed: the all-reduce itself (4.2 MB x 5 + 17.1 MB per iteration; the spectral-normed weight
-    gradients are produced by the batched launch at the END of D's backward, so nothing of D's backward is left
-    to hide it behind) and Adam, which depends on it."""
+    The D updates' all-reduce (4.2 MB each) + Adam run on a forked stream under the next update's G(z) forward
+    (``train_step_pipelined``; MCGM_DDP_PIPELINE=0 restores the serial schedule).  What stays exposed: the G update's
+    all-reduce (17.1 MB) + Adam at the end of the iteration."""
 
-    launch_form = "one CUDA graph per iteration, NCCL all-reduce + Adam captured inside (1/world folded into Adam)"
+    launch_form = ("one CUDA graph per iteration, NCCL all-reduce + Adam captured inside (1/world folded into Adam), "
+                   "D's all-reduce + Adam overlapped with the next G(z)")
 
     def __init__(self, model, optimizer, reducers, batch_size, warmup=2, inject_noise=False):
         from .optim import StateGuard
@@ -424,11 +496,18 @@ class GraphedDDPIngraphTrainStep:
                   if inject_noise else None)
         batch = {'img': self.img, 'label': self.label}
         guard = StateGuard(model, optimizer.values())
+        import os
+        self.pipelined = os.environ.get('MCGM_DDP_PIPELINE', '1') != '0'
+        self.comm_stream = torch.cuda.Stream() if self.pipelined else None      # all-reduce + Adam of the D updates
+        if not self.pipelined:
+            self.launch_form = "one CUDA graph per iteration, NCCL all-reduce + Adam captured inside (1/world folded into Adam)"
+        step_fn = (lambda: train_step_pipelined(model, optimizer, batch, z=self.z, reducers=reducers, side=self.comm_stream)) \
+            if self.pipelined else (lambda: train_step(model, optimizer, batch, z=self.z, reducers=reducers))
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):                     # also brings up the NCCL communicator before the capture
-                train_step(model, optimizer, batch, z=self.z, reducers=reducers)
+                step_fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if dist.is_initialized():
@@ -439,7 +518,7 @@ class GraphedDDPIngraphTrainStep:
         _ops.clear_pack_caches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
-            self.out = train_step(model, optimizer, batch, z=self.z, reducers=reducers)
+            self.out = step_fn()
         self.native_launches = _lib.launch_count - c0
         guard.restore()
 
