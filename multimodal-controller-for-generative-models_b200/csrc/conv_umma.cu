@@ -186,6 +186,7 @@ struct DescKnobs {
   // wgrad: 5-D blocked tensor maps = one TMA operation per operand instead of one per 64 channels.  Parity green, time
   // unchanged (404 vs 406 us, 130 vs 132 us): the ring is not bound by the operation count.  Off by default.
   uint32_t wg_blocked = 0;
+  uint32_t wg_bias_last = 1;                 // wgrad, NT = 2, odd tap count: dbias on the single-tap group (0: on group 0)
   uint32_t wg_pair = 1;                      // wgrad, NT = 2: one N = 2*BN MMA per k step for both taps (0: one MMA per tap)
   // staged forward epilogue: bit 2 = fetch the residual / ReLU-sign tile by TMA load (else through registers)
   uint32_t tma_epi = 7;
@@ -1096,6 +1097,7 @@ struct WgradParams {
   float* partial;                       // [splits][Cout*R*S*Cin]
   float* bias_partial;                  // [splits][bias_slots][Cout] or nullptr
   int bias_taps[4], bias_slots;         // taps whose dY pixels tile dY exactly once (stride-2 dY: 4 parity classes)
+  int bias_spread;                      // bias MMAs dealt round-robin over ALL tap groups (bias_slots = tap_groups)
   // grouped launch: `groups` independent problems of identical geometry share one grid (CTA -> group by index)
   int groups, ctas_per_group;
   size_t group_partial_stride, group_bias_stride;      // floats between the groups' partial / bias-partial blocks
@@ -1176,7 +1178,14 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (i < p.bias_slots && p.bias_taps[i] == tap0) bias_slot = i;
+  // bias_spread: EVERY tap group takes the bias MMAs of the k-blocks with kb % tap_groups == its index (slot = group):
+  // a few percent on every CTA instead of +44 % on the CTAs of one group, which then set the time of the one-wave launch
+  const int tgroup = tap0 / NT;
+  if (p.bias_spread) bias_slot = tgroup;
   const bool do_bias = bias_partial != nullptr && bias_slot >= 0 && cin_t == 0;
+  // k-blocks of this CTA that carry a bias MMA (spread mode: a stride-tap_groups subset, possibly empty)
+  const int bias_first = p.bias_spread ? kb0 + ((tgroup - kb0 % p.tap_groups) + p.tap_groups) % p.tap_groups : kb0;
+  const bool bias_any = bias_first < kb1;
   if (do_bias && warp >= 2) {
     const uint32_t ones2 = 0x3f803f80u;              // two bf16 1.0
     for (int i = (warp - 2) * 32 + lane; i < Cfg::kOnesBytes / 16; i += 128)
@@ -1269,12 +1278,13 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
                        acc_on | (uint32_t)(k != 0));
           }
         }
-        if (do_bias) {
+        if (do_bias && (!p.bias_spread || kb % p.tap_groups == tgroup)) {
           const uint64_t odesc = smem_desc(p.desc_templ, ones_base);
+          const uint32_t bias_acc = kb > bias_first;
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)
             umma_f16(tmem_base + Cfg::kBiasCol, adesc + (uint64_t)(k * 128), odesc, p.idesc_bias,
-                     acc_on | (uint32_t)(k != 0));
+                     bias_acc | (uint32_t)(k != 0));
         }
         umma_commit(empty_bar(stage));
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -1292,7 +1302,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgradParams pin) {
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kBiasCol, acc);
       tmem_ld_wait();
       if (co < p.Cout)
-        bias_partial[((size_t)split * p.bias_slots + bias_slot) * p.Cout + co] = (kb1 > kb0) ? __uint_as_float(acc[0]) : 0.0f;
+        bias_partial[((size_t)split * p.bias_slots + bias_slot) * p.Cout + co] = bias_any ? __uint_as_float(acc[0]) : 0.0f;
     }
     for (int q = 0; q < ntaps; ++q) {
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + q * BN;
@@ -1477,6 +1487,8 @@ static int launch_wgrad(const WgMaps& maps, const WgradParams& p, int grid, cuda
   return 0;
 }
 
+static constexpr int kWgMaxBiasSlots = 16;     // bias-gradient partial rows per split the workspace is sized for
+
 struct WgradPlan {
   int BN, NT, tap_groups, cout_tiles, cin_tiles, taps, splits, kb_per_split, total_kb, KW, KH, KN;
   int Hg, Wg, AS, BS;           // grid dims and traversal strides of dY / X
@@ -1554,6 +1566,7 @@ extern "C" int mcgm_debug_set(int key, uint64_t value) {
     case 15: g_knobs.fwd_dbg = (uint32_t)value; break;
     case 16: g_knobs.pair_mma = (uint32_t)value; break;
     case 17: g_knobs.wg_blocked = (uint32_t)value; break;
+    case 18: g_knobs.wg_bias_last = (uint32_t)value; break;
     case 12: g_thin_umma_wgrad = (int)value; break;       // thin (RGB-side) convs: tcgen05 / TMA kernels (1) or mma.sync kernels (0)
     case 13: g_thin_umma_fwd = (int)value; break;
     default: return fail(MCGM_E_ARG, "debug_set: unknown key %d", key);
@@ -1783,7 +1796,7 @@ static size_t wgrad_ws_bytes(int kind, int in_dtype, int N, int H, int W, int Ci
   WgradPlan pl;
   if (plan_wgrad(kind, in_dtype == MCGM_F32, N, H, W, Cin, Cout, R, S, &pl)) return 0;
   size_t bytes = (size_t)pl.splits * pl.per_split * sizeof(float);
-  bytes += (size_t)pl.splits * 4 * Cout * sizeof(float);  // bias-gradient partials (up to 4 slots)
+  bytes += (size_t)pl.splits * kWgMaxBiasSlots * Cout * sizeof(float);  // bias-gradient partials (4 parity slots, or one per tap group)
   return bytes;
 }
 
@@ -1821,6 +1834,16 @@ static int conv_wgrad_grouped_impl(int kind, int in_dtype, int n, const void* co
   p.idesc_pair = (g_knobs.wg_pair && 2 * pl.BN <= 256) ? make_idesc_bf16(kTileM, 2 * pl.BN, 1, 1, tf32) : 0u;
   p.idesc_bias = make_idesc_bf16(kTileM, 16, 1, 1, tf32);
   p.bias_slots = 1; p.bias_taps[0] = 0;
+  // The bias gradient (one extra N = 16 MMA per k step) rides on the tap group with the LEAST work: with two taps per CTA
+  // a 3x3 kernel has four two-tap groups and one single-tap group, whose CTAs issue half the MMAs.  On group 0 the extra
+  // MMAs made those CTAs the critical path of the one-wave launch (+29 us at 128->128 32x32, knob 18 = 0 restores it).
+  if (g_knobs.wg_bias_last && pl.NT == 2 && (pl.taps & 1)) p.bias_taps[0] = pl.taps - 1;
+  // One tap per CTA (256-wide layers): every group has the same work, so the bias MMAs are dealt round-robin over all of
+  // them (k-block kb -> group kb % tap_groups): 576 -> ~420 us at 256->256 32x32 instead of +44 % on group 0's CTAs.
+  if (g_knobs.wg_bias_last && pl.NT == 1 && pl.taps > 1 && !pl.a_shift && pl.tap_groups <= kWgMaxBiasSlots) {
+    p.bias_spread = 1;
+    p.bias_slots = pl.tap_groups;
+  }
   if (kind == MCGM_CONV_PHASE2) {          // dY is read with stride 2: the four offsets in {0,1}^2 cover it once
     p.bias_slots = 4; p.bias_taps[0] = 5; p.bias_taps[1] = 6; p.bias_taps[2] = 9; p.bias_taps[3] = 10;
   }
@@ -1894,7 +1917,7 @@ static int conv_wgrad_impl(int kind, int in_dtype, const void* x, const void* dy
 extern "C" size_t mcgm_conv_wgrad_grouped_workspace_bytes(int n, int N, int H, int W, int Cin, int Cout, int R, int S) {
   WgradPlan pl;
   if (n < 1 || n > kWgMaxGroups || plan_wgrad(MCGM_CONV_S1, 0, N, H, W, Cin, Cout, R, S, &pl, n)) return 0;
-  return ((size_t)n * pl.splits * pl.per_split + (size_t)n * pl.splits * 4 * Cout) * sizeof(float);
+  return ((size_t)n * pl.splits * pl.per_split + (size_t)n * pl.splits * kWgMaxBiasSlots * Cout) * sizeof(float);
 }
 extern "C" int mcgm_conv_wgrad_grouped(int n, const void* const* x_host, const void* const* dy_host, float* const* dw_host,
                                        float* const* dbias_host, int N, int H, int W, int Cin, int Cout, int R, int S,
@@ -1907,7 +1930,7 @@ extern "C" int mcgm_conv_wgrad_grouped(int n, const void* const* x_host, const v
 extern "C" size_t mcgm_conv_wgrad_taps_workspace_bytes(int N, int H, int W, int Cin, int Cout, int n_taps) {
   WgradPlan pl;
   if (plan_wgrad(MCGM_CONV_TAPS, 0, N, H, W, Cin, Cout, 0, 0, &pl, 1, n_taps)) return 0;
-  return ((size_t)pl.splits * pl.per_split + (size_t)pl.splits * 4 * Cout) * sizeof(float);
+  return ((size_t)pl.splits * pl.per_split + (size_t)pl.splits * kWgMaxBiasSlots * Cout) * sizeof(float);
 }
 extern "C" int mcgm_conv_wgrad_taps(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W, int Cin,
                                     int Cout, int n_taps, const signed char* taps_dh_host, const signed char* taps_dw_host,

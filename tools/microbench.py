@@ -130,3 +130,11 @@ if "legs" in which:
             t = timeit(lambda: ops.conv_fwd(x, w, torch.bfloat16, bias, res, None, None, None, fl))
             print(f"legs {H}x{H} {C}->{C} f{fl:#x} {name:28s}: {t * 1e6:8.1f} us", flush=True)
         _lib.call("mcgm_debug_set", 15, 0)
+if "wgbias" in which:
+    # weight gradient with / without the fused bias gradient
+    for (H, C) in [(32, 128), (16, 128), (32, 256)]:
+        x = torch.randn(N, H, H, C, device=dev).to(torch.bfloat16)
+        dy = torch.randn(N, H, H, C, device=dev).to(torch.bfloat16)
+        for wb in (False, True):
+            t = timeit(lambda: ops.conv_wgrad(x, dy, 3, 3, want_bias=wb))
+            print(f"conv_wgrad {H}x{H} {C}->{C} k3 want_bias={int(wb)}: {t * 1e6:8.1f} us", flush=True)
