@@ -122,8 +122,8 @@ if tag != "r01":
                "conv 512x32x32 128->128 k3 f0x3 bf16": ("prof_conv_fwd_d.ncu-rep", (105, 175)),
                "thin_conv 512x32x32 3->128 k3 gate1": ("prof_thin.ncu-rep", (44, 60)),
                "gate_fwd 512x32x32x256 f0xb raw0": ("prof_gate.ncu-rep", (90, 110)),
-               "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", (480, 600)),
-               "wgrad 512x32x32 128->128 k3": ("prof_wgrad_d.ncu-rep", (150, 185))}
+               "wgrad 512x32x32 256->256 k3": ("prof_wgrad.ncu-rep", (330, 600)),
+               "wgrad 512x32x32 128->128 k3": ("prof_wgrad_d.ncu-rep", (105, 185))}
 traffic = {}
 for desc, (rep, idx) in TRAFFIC.items():
     pth = os.path.join(SRC, rep)
