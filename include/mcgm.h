@@ -368,10 +368,20 @@ int mcgm_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
 int mcgm_pool2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream);
 int mcgm_unpool2(const void* dy, void* dx, int dtype, int N, int H, int W, int C, float scale, void* stream);
 
-/* ---- debug / bring-up: override shared-memory-descriptor fields of the tcgen05
- * kernels (key 0/1: K-major LBO/SBO bytes, 2/3: MN-major LBO/SBO bytes, 4: version,
- * 5: layout code).  Lets one GPU session try several encodings.  Not used by the
- * product path. */
+/* ---- debug / bring-up / same-box A-B knobs.  The product path never sets them; the defaults are the measured best.
+ *   0/1   K-major LBO / SBO bytes, 2/3 MN-major LBO / SBO bytes, 4 descriptor version, 5 layout code (bring-up)
+ *   6     forward conv: two M tiles per CTA for BN <= 128 (1)          7   ... for BN = 256 (0)
+ *   8     weight gradient: two taps per CTA (1)                         9   force the split-K factor (0 = automatic)
+ *   10    staged epilogue: bit 0 on, bit 2 residual / ReLU-sign tile by TMA load (7)
+ *   11    forward conv: multicast clusters of 1 / 2 / 4 CTAs (1 = off; bit-identical, no gain)
+ *   12/13 RGB-side convs: tcgen05 kernels for the weight gradient / the forward (1; 0 = the mma.sync kernels)
+ *   14    weight gradient: one N = 2*BN MMA per tap pair (1)
+ *   15    forward conv TIMING DIAGNOSTICS, results are garbage: bit 0 skip MMAs, 1 skip activation loads,
+ *         2 skip weight loads, 3 skip the epilogue body (tools/microbench.py legs)
+ *   16    forward conv as CTA pairs / cta_group::2 MMAs: bit 0 the 256-wide tiles, bit 1 the 128-wide pair tiles (3)
+ *   17    weight gradient: blocked 5-D tensor maps, one TMA operation per operand (0; parity green, no gain)
+ *   18    weight gradient: bias-gradient MMAs on the least-loaded tap group / dealt over all groups (1)
+ * Every variant is parity-tested (tests/gpu_checks.py: check_conv_variants, check_conv_cluster). */
 int mcgm_debug_set(int key, uint64_t value);
 
 #ifdef __cplusplus
